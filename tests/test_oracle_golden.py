@@ -1,0 +1,372 @@
+"""Pins the CPU oracle against the reference's own golden vectors.
+
+Every test cites the reference test / data it reproduces (paths relative to the
+reference checkout).  These run on CPU (`-m "not gpu"`).
+"""
+import ctypes as C
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def planes(rows):
+    return np.array([v for row in rows for v in row], dtype=np.float32)
+
+
+# ---------------------------------------------------------------- network/repr.rs
+
+
+def test_repr_starting_position(oracle):
+    """repr.rs:260-301 `starting_position`: Game::<3,0>::default()."""
+    x, o = 1.0, 0.0
+    want = planes([[o] * 9] * 18 + [[x] * 9, [o] * 9, [x] * 9, [o] * 9, [o] * 9, [o] * 9])
+    got = oracle.game_repr(oracle.new_game(3, 0))
+    assert got.shape == (24 * 9,)
+    np.testing.assert_array_equal(got, want)
+
+
+def test_repr_complicated_position(oracle):
+    """repr.rs:303-360 `complicated_position`: 5x5, komi 2, black to move."""
+    x, o = 1.0, 0.0
+    p = np.float32(5.0) / np.float32(21.0)
+    q = np.float32(10.0) / np.float32(21.0)
+    d = np.float32(-3.0) / np.float32(25.0)
+    z = [o] * 25
+    rows = [
+        # my pieces
+        [o, o, o, x, o, o, x, o, o, o, o, x, o, o, x, x, o, x, o, o, o, o, o, o, o],  # flat
+        [o, o, o, o, o, o, o, o, o, o, o, o, o, x, o, o, o, o, o, o, o, o, o, o, o],  # wall
+        [o, o, o, o, o, o, o, o, o, o, o, o, o, o, o, o, x, o, o, o, o, o, o, o, o],  # cap
+        [o, o, x, o, o, o, o, x, o, o, o, o, x, o, o, o, o, o, o, o, o, o, x, o, o],
+        [o, o, x, o, o, x, o, o, o, o, o, x, o, o, o, o, o, o, o, o, o, o, x, o, o],
+        [o, o, o, o, o, x, o, o, o, o, o, o, o, o, o, o, o, o, o, o, o, o, o, o, o],
+        z, z, z, z, z, z, z,
+        # opponent pieces
+        [o, o, o, o, o, o, o, x, x, x, o, o, o, o, o, o, o, o, x, o, o, o, x, o, o],  # flat
+        [o, o, x, o, o, x, o, o, o, o, o, o, o, o, o, o, o, o, o, o, o, o, o, o, x],  # wall
+        [o, o, o, o, o, o, o, o, o, o, o, o, x, o, o, o, o, o, o, o, o, o, o, o, o],  # cap
+        [o, o, o, o, o, x, o, o, o, o, o, x, o, o, o, o, o, o, o, o, o, o, o, o, o],
+        z,
+        [o, o, o, o, o, o, o, o, o, o, o, o, o, o, o, o, o, o, o, o, o, o, x, o, o],
+        z, z, z, z, z, z, z,
+        [p] * 25, z, [q] * 25, z, [x] * 25, [d] * 25,
+    ]
+    want = planes(rows)
+    g = oracle.from_tps(5, 4, "x2,1221,x,1S/2,2C,2,1,x/x,212,21C,2S,2/2211S,2,21,1,1/x2,221S,2,x 2 23")
+    got = oracle.game_repr(g)
+    assert got.shape == (32 * 25,) == want.shape
+    np.testing.assert_array_equal(got, want)
+
+
+def test_repr_tall_stack(oracle):
+    """repr.rs:362-409 `tall_stack`: 3x3, HALF_KOMI=-1, layer truncation at 2N."""
+    x, o = 1.0, 0.0
+    p = np.float32(5.0) / np.float32(10.0)
+    q = np.float32(4.0) / np.float32(10.0)
+    d = np.float32(0.5) / np.float32(9.0)
+    z = [o] * 9
+    c = [o, o, o, o, x, o, o, o, o]
+    rows = [z, z, z, c, z, z, c, c, z, z, c, z, z, c, c, z, z, c, [p] * 9, z, [q] * 9, z, z, [d] * 9]
+    g = oracle.from_tps(3, -1, "x3/x,21212112212S,x/x3 1 12")
+    np.testing.assert_array_equal(oracle.game_repr(g), planes(rows))
+
+
+def test_policy_index_and_legal_moves(oracle):
+    """repr.rs:411-499 `policy`: full 27x3x3 output of the Simple agent, which pins
+    both `move_index` and the complete legal-move set of the position."""
+    f, w, s, o = 4.0, 2.0, 1.0, 0.0
+    z = [o] * 9
+    rows = [
+        [f, o, o, o, o, f, o, o, f],
+        [w, o, o, o, o, w, o, o, w],
+        z,
+        [o, o, o, o, s, o, o, o, o],  # 3#+3
+        [o, o, o, o, s, o, o, o, o],  # 2#+2
+        z,
+        [o, o, o, s, s, o, o, o, o],  # 1#+1
+        z, z,
+        [o, o, o, o, s, o, o, o, o],  # 3#>3
+        [o, o, o, o, s, o, o, o, o],  # 2#>2
+        z,
+        [o, o, o, s, s, o, o, s, o],  # 1#>1
+        z, z,
+        z, z, z,
+        [o, o, o, s, o, o, o, s, o],  # 1#-1
+        z, z,
+        z, z, z,
+        [o, o, o, o, o, o, o, s, o],  # 1#<1
+        z, z,
+    ]
+    want = planes(rows)
+    g = oracle.from_tps(3, 0, "2,1,x/1S,221,x/x,2S,2 1 6")
+    moves = oracle.possible_moves(g)
+    assert len(moves) == 18
+    # Simple agent logits scattered by move_index == policy_tensor (repr.rs:89-99)
+    L = oracle.lib()
+    n = len(moves)
+    acts = (C.c_uint16 * oracle.MAX_MOVES)(*moves)
+    logits = (C.c_float * oracle.MAX_MOVES)()
+    value, var = C.c_float(), C.c_float()
+    na = C.c_int(n)
+    L.tk_agent_simple(None, 1, C.byref(g), acts, C.byref(na), oracle.MAX_MOVES, logits, C.byref(value), C.byref(var))
+    got = np.zeros(27 * 9, dtype=np.float32)
+    for i, m in enumerate(moves):
+        idx = oracle.move_index(3, m)
+        assert got[idx] == 0.0, "move_index collision"
+        got[idx] = logits[i]
+    np.testing.assert_array_equal(got, want)
+
+
+def test_move_index_ranges(oracle):
+    """repr.rs:103-116 output sizes: 243 / 944 / 3075 / 9036."""
+    assert [oracle.lib().tk_output_channels(n) * n * n for n in (3, 4, 5, 6)] == [243, 944, 3075, 9036]
+    assert [oracle.lib().tk_input_channels(n) for n in (3, 4, 5, 6)] == [24, 28, 32, 36]
+
+
+# ---------------------------------------------------------------- policy.rs / eval.rs
+
+
+def test_softmax_known_answer(oracle):
+    """policy.rs:172-187 `softmax_works`."""
+    got = oracle.softmax([1, 2, 3, 4, 5])
+    want = np.array([0.011_656_231, 0.031_684_92, 0.086_128_55, 0.234_121_65, 0.636_408_6], dtype=np.float32)
+    assert np.all(np.abs(got - want) < np.finfo(np.float32).eps)
+
+
+def test_eval_order(oracle):
+    """eval.rs:169-194 `eval_order`."""
+    E = oracle.make_eval
+    contempt = np.float32(-0.05)
+    evals = [
+        E(oracle.E_VALUE, 1.0), E(oracle.E_VALUE, float(contempt + np.float32(0.1))), E(oracle.E_VALUE, -1.0),
+        E(oracle.E_WIN, 5), E(oracle.E_WIN, 10), E(oracle.E_DRAW, 5), E(oracle.E_DRAW, 10),
+        E(oracle.E_LOSS, 5), E(oracle.E_LOSS, 10),
+    ]
+    import functools
+
+    evals.sort(key=functools.cmp_to_key(lambda a, b: oracle.lib().tk_eval_cmp(a, b)))
+    got = [(e.tag, e.u.ply if e.tag else round(e.u.value, 4)) for e in evals]
+    want = [
+        (oracle.E_LOSS, 5), (oracle.E_LOSS, 10), (oracle.E_VALUE, -1.0), (oracle.E_DRAW, 10), (oracle.E_DRAW, 5),
+        (oracle.E_VALUE, 0.05), (oracle.E_VALUE, 1.0), (oracle.E_WIN, 10), (oracle.E_WIN, 5),
+    ]
+    assert got == want
+
+
+def test_eval_negate_and_f32(oracle):
+    """eval.rs:40-47 negate adds a ply; :95-105 0.997^ply scaling."""
+    L = oracle.lib()
+    e = L.tk_eval_negate(oracle.make_eval(oracle.E_WIN, 3))
+    assert (e.tag, e.u.ply) == (oracle.E_LOSS, 4)
+    v = L.tk_eval_to_f32(e)
+    want = np.float32(1.0)
+    a = np.float32(0.997)
+    # compiler-rt __powisf2 for b = 4: a^2 then squared
+    a2 = np.float32(a * a)
+    want = np.float32(a2 * a2) * np.float32(-1.0)
+    assert np.float32(v) == want
+
+
+# ---------------------------------------------------------------- mcts.rs
+
+
+def test_find_tinue_easy(oracle):
+    """mcts.rs:345-376 `find_tinue_easy`: Dummy agent, beta=1, root proven within 5000 sims, losing child b1."""
+    game = oracle.from_ptn_moves(3, 0, ["a3", "c1", "c2", "c3", "b3", "c3-"])
+    tree = oracle.Tree()
+    solved = False
+    for _ in range(5000):
+        if tree.simulate_simple("dummy", game, 1.0) == oracle.E_WIN:
+            solved = True
+            break
+    assert solved, "This position is solvable with MAX_VISITS."
+    losing = [a for a, c in oracle.node_children(tree.node) if c.evaluation.tag == oracle.E_LOSS]
+    assert oracle.move_str(losing[0]) == "b1"
+
+
+def test_find_tinue_deeper(oracle):
+    """mcts.rs:378-411 `find_tinue_deeper`: Simple agent, winning move b2 or c2."""
+    game = oracle.from_ptn_moves(3, 0, ["a3", "a1", "b1", "c1"])
+    tree = oracle.Tree()
+    solved = False
+    for _ in range(50_000):
+        if tree.simulate_simple("simple", game, 1.0) == oracle.E_WIN:
+            solved = True
+            break
+    assert solved
+    losing = [a for a, c in oracle.node_children(tree.node) if c.evaluation.tag == oracle.E_LOSS]
+    assert oracle.move_str(losing[0]) in ("b2", "c2")
+
+
+# ---------------------------------------------------------------- runs/*.txt golden data
+
+
+def _golden_move_lists():
+    with gzip.open(os.path.join(GOLDEN, "runs_moves_5x5.txt.gz"), "rt") as fh:
+        return [ln.split(",") for ln in fh.read().strip().split("\n")]
+
+
+def test_move_generation_order_rule(oracle):
+    """runs/*.txt: 1024 child-order 5x5 legal-move lists produced by the reference.
+    Every list must be strictly increasing under the oracle's ordering rule."""
+    L = oracle.lib()
+    lists = _golden_move_lists()
+    assert len(lists) == 1024
+    for moves in lists:
+        keys = [L.tk_move_order_key(oracle.parse_move(s), 5) for s in moves]
+        assert all(a < b for a, b in zip(keys, keys[1:])), moves
+        # notation round trip
+        assert [oracle.move_str(oracle.parse_move(s)) for s in moves] == moves
+
+
+def _synthesise_position(oracle, moves):
+    """Builds a 5x5 position whose legal-move list could be `moves` (the logs do not
+    record positions): empty squares <- placements, mover's stacks <- spreads with
+    height = max carry, blockers inferred from the reach of each spread; a
+    direction whose longest drop sequences all end in a single piece although
+    longer final drops would fit is a capstone flattening a wall."""
+    n = 5
+    parsed = [oracle.parse_move(s) for s in moves]
+    empties, stacks = set(), {}
+    has_cap_placement = any(((m >> 8) == 0 and ((m >> 6) & 3) == 2) for m in parsed)
+    has_flat_placement = any(((m >> 8) == 0 and ((m >> 6) & 3) == 0) for m in parsed)
+    for m in parsed:
+        col, row, kind, pat = m & 7, (m >> 3) & 7, (m >> 6) & 3, m >> 8
+        if pat == 0:
+            empties.add((row, col))
+            continue
+        c = 8 - ((pat & -pat).bit_length() - 1)
+        parts = bin(pat).count("1")
+        last_drop_is_one = bool(pat & 0x80)
+        st = stacks.setdefault((row, col), {"maxc": 0, "pats": [[] for _ in range(4)]})
+        st["maxc"] = max(st["maxc"], c)
+        st["pats"][kind].append((c, parts, last_drop_is_one))
+    dr, dc = [1, -1, 0, 0], [0, 0, -1, 1]
+    # requirements on non-empty squares: 'F' flat, 'W' wall (gets flattened),
+    # 'C' capstone (blocks a capstone stack that could otherwise flatten it),
+    # 'B' any blocker
+    reqs = {}
+
+    def analyse(st, d):
+        pats = st["pats"][d]
+        reach = max((p for _, p, _ in pats), default=0)
+        smash = False
+        if reach > 0 and st["maxc"] > reach and all(one for _, p, one in pats if p == reach):
+            smash = True
+            reach -= 1
+        return reach, smash
+
+    cap_stacks = {sq for sq, st in stacks.items() if any(analyse(st, d)[1] for d in range(4))}
+    while True:  # a stack forced to be a capstone makes its own blockers capstones too
+        reqs = {}
+        for (row, col), st in stacks.items():
+            for d in range(4):
+                reach, smash = analyse(st, d)
+                r, c = row, col
+                for step in range(1, st["maxc"] + 1):
+                    r, c = r + dr[d], c + dc[d]
+                    if not (0 <= r < n and 0 <= c < n):
+                        break
+                    if step <= reach:
+                        if (r, c) not in empties:
+                            reqs.setdefault((r, c), set()).add("F")
+                    else:
+                        if (r, c) in empties:
+                            return None
+                        kind = "W" if smash else ("C" if (row, col) in cap_stacks else "B")
+                        reqs.setdefault((r, c), set()).add(kind)
+                        break
+        for sq in cap_stacks:
+            reqs.setdefault(sq, set()).add("C")
+        grown = cap_stacks | {sq for sq, rs in reqs.items() if sq in stacks and "C" in rs}
+        if grown == cap_stacks:
+            break
+        cap_stacks = grown
+    types = {}
+    for sq, rs in reqs.items():
+        if "F" in rs:
+            if len(rs) > 1:
+                return None
+            types[sq] = "F"
+        elif "W" in rs and "C" in rs:
+            return None
+        elif "C" in rs:
+            types[sq] = "B"
+        else:
+            types[sq] = "W"
+    g = oracle.new_game(n, 4)
+    g.ply = 20
+    g.to_move = 0  # synthesise with White to move
+    code = {"F": 0, "W": 1, "B": 2}
+    for row in range(n):
+        for col in range(n):
+            sq = row * n + col
+            if (row, col) in empties:
+                continue
+            own = (row, col) in stacks
+            g.height[sq] = stacks[(row, col)]["maxc"] if own else 1
+            g.stack[sq] = 0 if own else 1
+            g.top[sq] = code[types.get((row, col), "F")]
+    g.stones[0] = 10 if has_flat_placement else 0
+    g.caps[0] = 1 if has_cap_placement else 0
+    g.stones[1] = 10
+    return g
+
+
+def test_move_generation_reproduces_reference_lists(oracle):
+    """Positions are not recorded in runs/*.txt, so a consistent position is
+    synthesised from each list and the oracle's movegen must return exactly the
+    reference's list, in the reference's order (covers reach limits, walls,
+    capstone flattening, carry limits, reserve-dependent placements)."""
+    lists = _golden_move_lists()
+    checked = 0
+    for moves in lists:
+        g = _synthesise_position(oracle, moves)
+        if g is None:
+            continue
+        got = [oracle.move_str(m) for m in oracle.possible_moves(g)]
+        assert got == moves, (oracle.to_tps(g), sorted(set(got) ^ set(moves)))
+        checked += 1
+    assert checked >= 900, checked  # the rest admit no position under this simple synthesis
+
+
+def test_halving_visit_schedule(oracle):
+    """runs/seqhal_*: k=64 -> {126x2,62x2,30x4,14x8,6x16,2x32}; k=16,b=640 -> {150x2,70x2,30x4,10x8}.
+    The oracle must produce the same visit multiset on a root with >= k children."""
+    meta = json.load(open(os.path.join(GOLDEN, "runs_visits.json")))["seqhal"]
+    for fname, k, budget in (("seqhal_64_no_beta_linear_50_puct.txt", 64, 768),
+                             ("seqhal_16_no_beta_linear_50_puct.txt", 16, 640)):
+        want = meta[fname]["top_multiset"]
+        assert sum(want) == budget and meta[fname]["k"] == k
+        env = oracle.new_opening(5, 4, 0, 0)
+        b = oracle.Batched([env])
+        rng = np.random.default_rng(7)
+        gum = rng.gumbel(size=(1, oracle.MAX_MOVES)).astype(np.float32)
+        b.gumbel_sequential_halving("synthetic", [0.0], k, budget, gum)
+        root = b.node(0)
+        got = sorted((c.visit_count for _, c in oracle.node_children(root) if c.visit_count), reverse=True)
+        assert got == want
+        assert root.visit_count == budget + 1
+
+
+def test_unvisited_children_carry_parent_eval(oracle):
+    """runs/puct.txt line 1: every zero-visit child prints the same eval:std pair,
+    i.e. children start as Value(-parent_eval) with the parent's std_dev
+    (mcts.rs:199-217, mod.rs:66-79)."""
+    line = json.load(open(os.path.join(GOLDEN, "runs_visits.json")))["puct_first_line"]
+    toks = [t.split(":") for t in line.strip(",").split(",")]
+    zero = {(t[2], t[3]) for t in toks if t[1] == "0"}
+    assert zero == {("0.6604345", "0.7421294")}
+    env = oracle.new_opening(5, 4, 3, 1)
+    tree = oracle.Tree()
+    tree.simulate_simple("synthetic", env, 0.0)
+    root = tree.node
+    vals = {(np.float32(c.evaluation.u.value).item(), np.float32(c.std_dev).item()) for _, c in oracle.node_children(root)}
+    assert len(vals) == 1
+    (v, s), = vals
+    assert np.float32(v) == -np.float32(root.evaluation.u.value) and np.float32(s) == np.float32(root.std_dev)
