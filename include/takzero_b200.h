@@ -1,0 +1,184 @@
+/*
+ * takzero_b200.h -- C ABI of libtakzero_b200.so, the B200-native batched self-play search.
+ *
+ * The reference (ViliamVadocz/takzero, Rust) has no FFI of its own: its extension points are
+ * the traits `Environment` (takzero/src/search/env.rs:11-25), `Agent` (search/agent.rs:5-14),
+ * `Network` (network/mod.rs:10-45) and the struct `BatchedMCTS` (search/node/batched.rs:24-409).
+ * Every entry point below names the reference item it replaces; INTEGRATION.md shows the
+ * `extern "C"` block a Rust maintainer would add to bind them.
+ *
+ * Conventions: plain pointers and sizes only; all `host` pointers are caller-owned host
+ * memory (pinned memory from tz_host_alloc makes the copies asynchronous); device memory is
+ * owned by the handle.  Calls on one handle must come from one thread at a time.  Every call
+ * returns 0 on success or a negative TZ_E* code, with a message in tz_last_error(); nothing
+ * panics or throws across the ABI (the reference panics on the same conditions).
+ * There is no CPU fallback: without a CUDA device tz_create fails.
+ */
+#ifndef TAKZERO_B200_H
+#define TAKZERO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TZ_API __attribute__((visibility("default")))
+
+#define TZ_MAX_SQ 36
+#define TZ_MAX_MOVES 1024 /* upper bound of legal moves per position handled by the library */
+#define TZ_MAX_PLIES 1024 /* longest recorded replay */
+#define TZ_MAX_K 64       /* largest `sampled_actions` */
+
+/* return codes */
+enum {
+    TZ_OK = 0,
+    TZ_EINVAL = -1,   /* bad argument (the reference would assert/panic) */
+    TZ_ECUDA = -2,    /* CUDA runtime error */
+    TZ_ESEARCH = -3,  /* sticky device-side search error, see tz_status() */
+    TZ_ENOMEM = -4,
+    TZ_ENOWEIGHTS = -5,
+};
+
+/* tz_status() bits (device-side invariant violations; the reference panics on these) */
+enum {
+    TZ_STATUS_ARENA_FULL = 1,      /* a game's node arena overflowed: raise arena_slots */
+    TZ_STATUS_DEPTH = 2,           /* selection path longer than 256 plies */
+    TZ_STATUS_NO_CHILD = 4,        /* "there should always be a child to simulate" */
+    TZ_STATUS_TOO_MANY_MOVES = 8,  /* more legal moves than move_stride */
+    TZ_STATUS_BAD_MOVE = 16,       /* "Action should be valid" (env.rs:44) */
+    TZ_STATUS_NAN = 32,            /* NaN logit / value (net6_simhash.rs:304) */
+    TZ_STATUS_SET_EMPTY = 64,      /* sequential halving on a root without children */
+    TZ_STATUS_REPLAY_FULL = 128,
+};
+
+/* Move (takparse `Move`, 2 bytes):
+ *   bits 0..2 column (file a = 0), bits 3..5 row (rank 1 = 0),
+ *   bits 6..7 placement: piece (0 flat, 1 wall, 2 cap); spread: direction (0 '+', 1 '-', 2 '<', 3 '>'),
+ *   bits 8..15 spread pattern = takparse `Pattern::mask()` byte (MSB aligned); 0 for placements. */
+typedef uint16_t tz_move_t;
+
+/* Game state (fast-tak `Game<N, HALF_KOMI>` fields used by the reference: env.rs:50,62,
+ * repr.rs:177-223).  N and HALF_KOMI are properties of the handle.  384 bytes. */
+typedef struct tz_state_t {
+    uint64_t stack[TZ_MAX_SQ]; /* bit i = colour (1 = black) of the piece at height i; square = row*N + col */
+    uint8_t height[TZ_MAX_SQ];
+    uint8_t top[TZ_MAX_SQ]; /* 0 flat, 1 wall, 2 cap; valid when height > 0 */
+    uint8_t to_move;        /* 0 white, 1 black */
+    uint8_t stones[2];
+    uint8_t caps[2];
+    uint8_t pad0;
+    uint16_t ply;
+    uint16_t reversible_plies;
+    uint8_t pad1[14];
+} tz_state_t;
+
+typedef struct tz_config_t {
+    int board_n;           /* 3..6 */
+    int half_komi;         /* e.g. 4 for Game<6,4> */
+    int n_games;           /* BATCH_SIZE of BatchedMCTS, dynamic here */
+    int device;            /* CUDA ordinal */
+    int game_base;         /* global id of game 0 (sharding: RNG streams are keyed by global id) */
+    int reversible_limit;  /* reversible-ply draw threshold; 0 = default 100 (unpinned) */
+    int move_stride;       /* row stride of per-game move/logit tables; 0 = default for board_n */
+    uint32_t arena_slots;  /* node slots per game per arena half; 0 = sized from free HBM */
+} tz_config_t;
+
+typedef struct tz_handle tz_handle;
+
+/* `Agent::policy_value_uncertainty` (agent.rs:5-14) as a host callback: fill un-normalised logits
+ * (same order as the action lists), value and variance for `batch` positions. */
+typedef void (*tz_agent_fn)(void* ctx, int batch, const tz_state_t* envs, const tz_move_t* actions,
+                            const int* n_actions, int stride, float* logits, float* values,
+                            float* variances);
+
+enum {
+    TZ_AGENT_SYNTHETIC = 0, /* deterministic integer-hash agent, bit-identical to the oracle's */
+    TZ_AGENT_HOST = 1,      /* tz_agent_fn callback ("reference network outputs injected") */
+    TZ_AGENT_NETWORK = 2,   /* the bf16 ResNet on the device (tz_set_weights first) */
+};
+
+typedef struct tz_counters_t {
+    uint64_t simulations; /* calls of Node::forward */
+    uint64_t evaluations; /* positions sent to the agent */
+    uint64_t known;       /* forwards that ended in Forward::Known */
+    uint64_t expansions;
+} tz_counters_t;
+
+typedef struct tz_root_t {
+    uint32_t eval_tag;  /* 0 Value, 1 Win, 2 Loss, 3 Draw (eval.rs:8-13) */
+    uint32_t eval_bits; /* f32 bits of the value, or the ply */
+    uint32_t visit_count;
+    uint32_t std_dev_bits;
+    uint32_t n_children;
+    uint32_t arena_used;
+} tz_root_t;
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+TZ_API const char* tz_last_error(void);
+TZ_API const char* tz_version(void);
+TZ_API int tz_create(const tz_config_t* cfg, tz_handle** out);            /* BatchedMCTS::new (batched.rs:33-47) */
+TZ_API void tz_destroy(tz_handle* h);
+TZ_API int tz_sync(tz_handle* h);
+TZ_API int tz_status(tz_handle* h, uint32_t* out_bits);                    /* syncs; 0 bits = healthy */
+TZ_API int tz_clear_status(tz_handle* h);
+TZ_API int tz_info(tz_handle* h, int* out_move_stride, uint32_t* out_arena_slots, int* out_input_channels,
+            int* out_output_channels);
+TZ_API void* tz_host_alloc(size_t bytes);                                  /* pinned host memory */
+TZ_API void tz_host_free(void* p);
+
+/* ---- rules / encoding parity hooks (stateless) ---------------------------------------- */
+/* Environment::populate_actions -> Game::possible_moves (env.rs:39-41), fast-tak order */
+TZ_API int tz_legal_moves(tz_handle* h, const tz_state_t* states, int count, int stride, tz_move_t* out_moves,
+                   int* out_n);
+/* Environment::step -> Game::play (env.rs:43-45); out_ok[i] = 0 where the reference would panic */
+TZ_API int tz_apply(tz_handle* h, tz_state_t* states, const tz_move_t* moves, int count, int* out_ok);
+/* Environment::terminal (env.rs:47-59): 0 none, 1 win, 2 loss, 3 draw for the side to move */
+TZ_API int tz_result(tz_handle* h, const tz_state_t* states, int count, int* out_terminal);
+
+/* ---- positions ------------------------------------------------------------------------- */
+/* BatchedMCTS::from_envs / nodes_and_envs_mut writes (reanalyze/src/main.rs:159-165); roots reset */
+TZ_API int tz_set_positions(tz_handle* h, const tz_state_t* states, const uint8_t* mask);
+TZ_API int tz_get_positions(tz_handle* h, tz_state_t* out);
+/* Env::new_opening (env.rs:65-79); sym/adj NULL = draw from the library RNG with `seed` */
+TZ_API int tz_new_openings(tz_handle* h, const uint8_t* mask, const int* sym, const int* adj, uint64_t seed);
+TZ_API int tz_reset_roots(tz_handle* h, const uint8_t* mask);              /* *node = Node::default() */
+
+/* ---- search ----------------------------------------------------------------------------- */
+TZ_API int tz_set_agent(tz_handle* h, int kind, tz_agent_fn fn, void* ctx);
+/* BatchedMCTS::simulate (batched.rs:63-128) */
+TZ_API int tz_simulate(tz_handle* h, const float* betas);
+/* BatchedMCTS::gumbel_sequential_halving (batched.rs:207-409).  gumbel: [n_games][gumbel_stride]
+ * injected Gumbel(0,1) draws, one per root child in child order, or NULL to draw them on the
+ * device from `seed` (readable afterwards with tz_last_gumbel). */
+TZ_API int tz_gumbel_sequential_halving(tz_handle* h, const float* betas, int sampled_actions,
+                                 uint32_t search_budget, const float* gumbel, int gumbel_stride,
+                                 uint64_t seed, tz_move_t* out_moves);
+TZ_API int tz_last_gumbel(tz_handle* h, float* out, int stride);
+/* BatchedMCTS::step (batched.rs:131-144) incl. Node::descend subtree reuse */
+TZ_API int tz_step(tz_handle* h, const tz_move_t* moves);
+/* BatchedMCTS::restart_terminal_envs (batched.rs:185-203); out_terminal[g] as tz_result */
+TZ_API int tz_restart_terminal(tz_handle* h, const int* sym, const int* adj, uint64_t seed, int* out_terminal);
+/* Replay of the game that tz_restart_terminal just finished / of the game in progress */
+TZ_API int tz_finished_replay(tz_handle* h, int game, tz_state_t* out_start, tz_move_t* out_moves, int cap);
+TZ_API int tz_replay(tz_handle* h, int game, tz_state_t* out_start, tz_move_t* out_moves, int cap);
+
+/* ---- root read-backs (direct `Node` field reads of the callers) ---------------------------- */
+TZ_API int tz_root_children(tz_handle* h, int stride, int* out_n, tz_move_t* moves, uint32_t* visits,
+                     uint32_t* eval_tag, uint32_t* eval_bits, float* logit, float* prob, float* std_dev);
+TZ_API int tz_root_stats(tz_handle* h, tz_root_t* out);
+/* Node::improved_policy (policy.rs:36-48; visitations < 0 = most_visited_count()) and
+ * Node::ube_target (node/mod.rs:215-230) */
+TZ_API int tz_targets(tz_handle* h, float visitations, float beta, int stride, float* out_policy, float* out_ube,
+               int* out_n, tz_move_t* out_moves);
+/* select_best_actions / select_actions_in_selfplay (batched.rs:152-183) */
+TZ_API int tz_select_best(tz_handle* h, tz_move_t* out_moves);
+TZ_API int tz_select_selfplay(tz_handle* h, int weighted_random_plies, uint32_t threshold, float allowed_eval_drop,
+                       const uint64_t* randoms, uint64_t seed, tz_move_t* out_moves);
+TZ_API int tz_counters(tz_handle* h, tz_counters_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -147,6 +147,8 @@ def lib():
     L.tk_eval_to_f32.restype = C.c_float
     L.tk_softmax.argtypes = [P(C.c_float), C.c_int, P(C.c_float)]
     L.tk_set_exact_math.argtypes = [C.c_int]
+    L.tk_expf_restated.argtypes = [C.c_float]
+    L.tk_expf_restated.restype = C.c_float
     L.tk_node_new.restype = P(Node)
     L.tk_node_free.argtypes = [P(Node)]
     L.tk_node_reset.argtypes = [P(Node)]

@@ -97,7 +97,8 @@ tk_eval tk_eval_negate(tk_eval e);
 int tk_eval_cmp(tk_eval a, tk_eval b);
 float tk_eval_to_f32(tk_eval e);
 void tk_softmax(const float* logits, int n, float* out);
-void tk_set_exact_math(int on); /* 1: expf/logf as correctly rounded double->float */
+void tk_set_exact_math(int on); /* 1: expf = tk_expf_restated (what the CUDA library executes) */
+float tk_expf_restated(float x);
 
 /* search/node/mod.rs */
 typedef struct tk_node {

@@ -17,8 +17,8 @@
  * Float semantics: every f32 expression is evaluated in the reference's order in
  * IEEE binary32 (compile with -ffp-contract=off, no fast-math); `powi` follows
  * compiler-rt __powisf2; `exp`/`ln` are libm expf/logf like Rust's f32::exp/ln on
- * Linux (tk_set_exact_math(1) switches them to correctly rounded double->float,
- * which is what the CUDA path computes; tests assert both modes agree).
+ * Linux (tk_set_exact_math(1) switches expf to the restated glibc algorithm that the
+ * CUDA path executes; tests assert both modes agree).
  * The `rand` streams of the reference are parity-unpinned, so Gumbel noise,
  * openings and sampling randomness are injected by the caller.
  */
@@ -32,10 +32,58 @@
 #define DISCOUNT_FACTOR 0.997f /* search/mod.rs:7 */
 #define CONTEMPT (-0.05f)      /* eval.rs:128 */
 
+/* Math modes.  0: the host libm's expf/logf, i.e. what Rust's f32::exp / f32::ln call on
+ * Linux.  1: expf through `tk_expf_restated`, the algorithm of glibc's generic expf
+ * (sysdeps/ieee754/flt-32/e_expf.c: exp2f_data table, N = 32, degree-3 polynomial in
+ * double) written out without FMA contraction -- the same sequence of IEEE operations the
+ * CUDA library executes (takzero_b200/csrc/tree.cuh `expf_libm`), so GPU-vs-oracle
+ * comparisons are bit-exact by construction.  tests/ assert that mode 1 agrees with mode 0
+ * on sampled inputs (a libm built with FMA may differ in ~1e-9 of inputs).  ln is always
+ * the host logf (the CUDA library tabulates it with the host logf as well). */
 static int g_exact_math = 0;
 void tk_set_exact_math(int on) { g_exact_math = on; }
-static inline float f_exp(float x) { return g_exact_math ? (float)exp((double)x) : expf(x); }
-static inline float f_ln(float x) { return g_exact_math ? (float)log((double)x) : logf(x); }
+
+static const uint64_t exp2f_tab[32] = {
+    0x3ff0000000000000ULL, 0x3fefd9b0d3158574ULL, 0x3fefb5586cf9890fULL, 0x3fef9301d0125b51ULL,
+    0x3fef72b83c7d517bULL, 0x3fef54873168b9aaULL, 0x3fef387a6e756238ULL, 0x3fef1e9df51fdee1ULL,
+    0x3fef06fe0a31b715ULL, 0x3feef1a7373aa9cbULL, 0x3feedea64c123422ULL, 0x3feece086061892dULL,
+    0x3feebfdad5362a27ULL, 0x3feeb42b569d4f82ULL, 0x3feeab07dd485429ULL, 0x3feea47eb03a5585ULL,
+    0x3feea09e667f3bcdULL, 0x3fee9f75e8ec5f74ULL, 0x3feea11473eb0187ULL, 0x3feea589994cce13ULL,
+    0x3feeace5422aa0dbULL, 0x3feeb737b0cdc5e5ULL, 0x3feec49182a3f090ULL, 0x3feed503b23e255dULL,
+    0x3feee89f995ad3adULL, 0x3feeff76f2fb5e47ULL, 0x3fef199bdd85529cULL, 0x3fef3720dcef9069ULL,
+    0x3fef5818dcfba487ULL, 0x3fef7c97337b9b5fULL, 0x3fefa4afa2a490daULL, 0x3fefd0765b6e4540ULL};
+
+float tk_expf_restated(float x) {
+    if (x != x) return x;
+    if (x > 0x1.62e42ep6f) return INFINITY;
+    if (x < -0x1.9fe368p6f) return 0.0f;
+    const double N = 32.0;
+    const double inv_ln2_n = 0x1.71547652b82fep+0 * N;
+    const double c0 = 0x1.c6af84b912394p-5 / N / N / N;
+    const double c1 = 0x1.ebfce50fac4f3p-3 / N / N;
+    const double c2 = 0x1.62e42ff0c52d6p-1 / N;
+    const double shift = 0x1.8p+52;
+    const double xd = (double)x;
+    double z = inv_ln2_n * xd;
+    double kd = z + shift;
+    uint64_t ki;
+    memcpy(&ki, &kd, 8);
+    kd = kd - shift;
+    const double r = z - kd;
+    uint64_t t = exp2f_tab[ki & 31];
+    t += ki << (52 - 5);
+    double s;
+    memcpy(&s, &t, 8);
+    z = c0 * r + c1;
+    const double r2 = r * r;
+    double y = c2 * r + 1.0;
+    y = z * r2 + y;
+    y = y * s;
+    return (float)y;
+}
+
+static inline float f_exp(float x) { return g_exact_math ? tk_expf_restated(x) : expf(x); }
+static inline float f_ln(float x) { return logf(x); }
 
 /* ---- Eval ------------------------------------------------------------ */
 

@@ -1,0 +1,715 @@
+// api.cu -- the C ABI of libtakzero_b200.so (include/takzero_b200.h): handle, device
+// memory, host <-> device staging and the lock-step drivers of
+// BatchedMCTS::{simulate, gumbel_sequential_halving, step, restart_terminal_envs}
+// (takzero/src/search/node/batched.rs:63-409) on top of the kernels in kernels.cu / nn.cu.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/takzero_b200.h"
+#include "handle.cuh"
+#include "kernels.cuh"
+#include "nn.cuh"
+
+static_assert(sizeof(tz_state_t) == sizeof(TzState), "ABI state layout");
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) return fail(TZ_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define CHECK_H(h)                                                    \
+    do {                                                              \
+        if (!(h)) return fail(TZ_EINVAL, "null handle");              \
+        CU(cudaSetDevice((h)->device));                               \
+    } while (0)
+
+extern "C" TZ_API const char* tz_last_error(void) { return g_err; }
+extern "C" TZ_API const char* tz_version(void) { return "takzero_b200 0.1 (sm_100a)"; }
+
+extern "C" TZ_API void* tz_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" TZ_API void tz_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+template <typename T>
+static cudaError_t dmalloc(tz_handle* h, T** p, size_t count) {
+    void* v = nullptr;
+    cudaError_t e = cudaMalloc(&v, count * sizeof(T));
+    if (e == cudaSuccess) {
+        h->allocs.push_back(v);
+        *p = (T*)v;
+    }
+    return e;
+}
+
+static int default_stride(int n) { return n <= 3 ? 128 : n == 4 ? 256 : n == 5 ? 512 : 1024; }
+
+extern "C" TZ_API int tz_create(const tz_config_t* cfg, tz_handle** out) {
+    if (!cfg || !out) return fail(TZ_EINVAL, "null argument");
+    if (cfg->board_n < 3 || cfg->board_n > 6) return fail(TZ_EINVAL, "board_n must be 3..6");
+    if (cfg->n_games <= 0) return fail(TZ_EINVAL, "n_games must be positive");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(TZ_ECUDA, "no CUDA device: takzero_b200 has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(TZ_EINVAL, "bad device ordinal %d", cfg->device);
+    CU(cudaSetDevice(cfg->device));
+    tz_handle* h = new tz_handle();
+    h->device = cfg->device;
+    h->agent_kind = TZ_AGENT_SYNTHETIC;
+    TzDev& d = h->d;
+    memset(&d, 0, sizeof(d));
+    d.n = cfg->board_n;
+    d.nn = d.n * d.n;
+    d.half_komi = cfg->half_komi;
+    d.rev_limit = cfg->reversible_limit > 0 ? cfg->reversible_limit : 100;
+    d.G = cfg->n_games;
+    d.M = cfg->move_stride > 0 ? cfg->move_stride : default_stride(d.n);
+    if (d.M > TZ_MAX_MOVES) return fail(TZ_EINVAL, "move_stride > %d", TZ_MAX_MOVES);
+    d.game_base = cfg->game_base;
+    const size_t G = (size_t)d.G;
+
+    uint32_t cap = cfg->arena_slots;
+    if (cap == 0) {
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        size_t c = (size_t)((double)free_b * 0.5 / ((double)G * 2.0 * 28.0));
+        if (c > 262144) c = 262144;
+        if (c < 4096) c = 4096;
+        cap = (uint32_t)c;
+    }
+    d.arena.cap = cap;
+    const size_t slots = G * 2 * (size_t)cap;
+    cudaError_t e = cudaSuccess;
+#define DM(ptr, count)                                   \
+    if (e == cudaSuccess) e = dmalloc(h, &(ptr), (count))
+    DM(d.arena.eval, slots);
+    DM(d.arena.meta, slots);
+    DM(d.arena.visits, slots);
+    DM(d.arena.prob, slots);
+    DM(d.arena.std_dev, slots);
+    DM(d.arena.logit, slots);
+    DM(d.arena.first, slots);
+    DM(d.arena.half, G);
+    DM(d.arena.next_slot, G);
+    DM(d.env, G);
+    DM(d.start_env, G);
+    DM(d.replay, G * TZ_MAX_PLIES);
+    DM(d.replay_len, G);
+    DM(d.traj, G * TZ_MAX_DEPTH);
+    DM(d.traj_len, G);
+    DM(d.nn_queue, G);
+    DM(d.nn_count, 1);
+    DM(d.leaf_state, G);
+    DM(d.actions, G * d.M);
+    DM(d.n_actions, G);
+    DM(d.logits, G * d.M);
+    DM(d.value, G);
+    DM(d.variance, G);
+    float* ln_table = nullptr;
+    DM(ln_table, (size_t)TZ_LN_TABLE);
+    DM(d.set_child, G * TZ_MAX_K);
+    DM(d.set_key, G * TZ_MAX_K);
+    DM(d.set_len, G);
+    DM(d.counters, G * 4);
+    DM(d.status, 1);
+    // host-facing staging (device side)
+    DM(h->betas, G);
+    DM(h->gumbel, G * d.M);
+    DM(h->moves, G);
+    DM(h->sym, G);
+    DM(h->adj, G);
+    DM(h->mask, G);
+    DM(h->terminal, G);
+    DM(h->randoms, G);
+    DM(h->fin_start, G);
+    DM(h->fin_replay, G * TZ_MAX_PLIES);
+    DM(h->fin_len, G);
+    DM(h->tbl_n, G);
+    DM(h->tbl_moves, G * d.M);
+    DM(h->tbl_u32a, G * d.M);
+    DM(h->tbl_u32b, G * d.M);
+    DM(h->tbl_u32c, G * d.M);
+    DM(h->tbl_f32a, G * d.M);
+    DM(h->tbl_f32b, G * d.M);
+    DM(h->tbl_f32c, G * d.M);
+    DM(h->root_stats, G * 6);
+    DM(h->ube, G);
+#undef DM
+    if (e != cudaSuccess) {
+        const int rc = fail(TZ_ENOMEM, "cudaMalloc: %s (n_games=%d arena_slots=%u)", cudaGetErrorString(e), d.G, cap);
+        tz_destroy(h);
+        return rc;
+    }
+    d.ln_table = ln_table;
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    // exploration_rate(n) = ln((1 + n + 500) / 500) + 4 (policy.rs:140-145), evaluated with the
+    // host libm like Rust's f32::ln, in the reference's operation order
+    {
+        std::vector<float> tab(TZ_LN_TABLE);
+        for (int i = 0; i < TZ_LN_TABLE; i++) {
+            volatile float x = 1.0f + (float)i;
+            x = x + 500.0f;
+            x = x / 500.0f;
+            volatile float l = logf(x);
+            tab[i] = l + 4.0f;
+        }
+        CU(cudaMemcpy(ln_table, tab.data(), sizeof(float) * TZ_LN_TABLE, cudaMemcpyHostToDevice));
+    }
+    CU(cudaMemsetAsync(d.arena.half, 0, G, h->stream));
+    CU(cudaMemsetAsync(d.counters, 0, G * 4 * sizeof(unsigned long long), h->stream));
+    CU(cudaMemsetAsync(d.status, 0, sizeof(uint32_t), h->stream));
+    CU(cudaMemsetAsync(d.nn_count, 0, sizeof(int), h->stream));
+    CU(cudaMemsetAsync(d.set_len, 0, G * sizeof(int), h->stream));
+    CU(cudaMemsetAsync(h->fin_len, 0, G * sizeof(int), h->stream));
+    // host staging for the callback agent and small read-backs
+    CU(cudaHostAlloc((void**)&h->pin_small, 4096, cudaHostAllocDefault));
+    // every game starts from a fresh default position with an empty root
+    std::vector<TzState> init(G);
+    memset(init.data(), 0, G * sizeof(TzState));
+    const int stones = d.n == 3 ? 10 : d.n == 4 ? 15 : d.n == 5 ? 21 : 30;
+    const int caps = d.n >= 5 ? 1 : 0;
+    for (size_t g = 0; g < G; g++) {
+        init[g].stones[0] = init[g].stones[1] = (uint8_t)stones;
+        init[g].caps[0] = init[g].caps[1] = (uint8_t)caps;
+    }
+    CU(cudaMemcpyAsync(h->fin_start, init.data(), G * sizeof(TzState), cudaMemcpyHostToDevice, h->stream));
+    launch_set_positions(d, h->fin_start, nullptr, h->stream);
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    *out = h;
+    return TZ_OK;
+}
+
+extern "C" TZ_API void tz_destroy(tz_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    nn_free(h);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->pin_small) cudaFreeHost(h->pin_small);
+    if (h->pin_states) cudaFreeHost(h->pin_states);
+    if (h->pin_actions) cudaFreeHost(h->pin_actions);
+    if (h->pin_nact) cudaFreeHost(h->pin_nact);
+    if (h->pin_logits) cudaFreeHost(h->pin_logits);
+    if (h->pin_value) cudaFreeHost(h->pin_value);
+    if (h->pin_variance) cudaFreeHost(h->pin_variance);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" TZ_API int tz_sync(tz_handle* h) {
+    CHECK_H(h);
+    CU(cudaStreamSynchronize(h->stream));
+    return TZ_OK;
+}
+
+static const char* status_text(uint32_t bits, char* buf, size_t len) {
+    static const char* names[] = {"arena_full", "depth", "no_child", "too_many_moves",
+                                  "bad_move",   "nan",   "set_empty", "replay_full"};
+    buf[0] = 0;
+    for (int i = 0; i < 8; i++)
+        if (bits & (1u << i)) {
+            strncat(buf, names[i], len - strlen(buf) - 1);
+            strncat(buf, " ", len - strlen(buf) - 1);
+        }
+    return buf;
+}
+
+// sync + sticky device status -> return code
+static int finish(tz_handle* h) {
+    uint32_t* bits = (uint32_t*)h->pin_small;
+    CU(cudaMemcpyAsync(bits, h->d.status, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    if (*bits) {
+        char buf[160];
+        return fail(TZ_ESEARCH, "device search error bits 0x%x: %s", *bits, status_text(*bits, buf, sizeof(buf)));
+    }
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_status(tz_handle* h, uint32_t* out_bits) {
+    CHECK_H(h);
+    uint32_t* bits = (uint32_t*)h->pin_small;
+    CU(cudaMemcpyAsync(bits, h->d.status, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (out_bits) *out_bits = *bits;
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_clear_status(tz_handle* h) {
+    CHECK_H(h);
+    CU(cudaMemsetAsync(h->d.status, 0, sizeof(uint32_t), h->stream));
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_info(tz_handle* h, int* out_move_stride, uint32_t* out_arena_slots, int* out_input_channels,
+                       int* out_output_channels) {
+    if (!h) return fail(TZ_EINVAL, "null handle");
+    const int n = h->d.n;
+    if (out_move_stride) *out_move_stride = h->d.M;
+    if (out_arena_slots) *out_arena_slots = h->d.arena.cap;
+    if (out_input_channels) *out_input_channels = 2 * (2 * n + 3 + 2) + 2;  // repr.rs:133-139
+    if (out_output_channels) *out_output_channels = 3 + 4 * ((1 << n) - 2);  // repr.rs:103-108
+    return TZ_OK;
+}
+
+// ---- rules hooks ---------------------------------------------------------------------------
+
+struct Scratch {
+    std::vector<void*> ptrs;
+    ~Scratch() {
+        for (void* p : ptrs) cudaFree(p);
+    }
+    template <typename T>
+    cudaError_t get(T** p, size_t count) {
+        void* v = nullptr;
+        cudaError_t e = cudaMalloc(&v, (count ? count : 1) * sizeof(T));
+        if (e == cudaSuccess) {
+            ptrs.push_back(v);
+            *p = (T*)v;
+        }
+        return e;
+    }
+};
+
+extern "C" TZ_API int tz_legal_moves(tz_handle* h, const tz_state_t* states, int count, int stride, tz_move_t* out_moves,
+                              int* out_n) {
+    CHECK_H(h);
+    if (!states || count < 0 || stride <= 0 || !out_moves || !out_n) return fail(TZ_EINVAL, "bad argument");
+    if (count == 0) return TZ_OK;
+    Scratch s;
+    TzState* ds;
+    uint16_t* dm;
+    int* dn;
+    CU(s.get(&ds, (size_t)count));
+    CU(s.get(&dm, (size_t)count * stride));
+    CU(s.get(&dn, (size_t)count));
+    CU(cudaMemcpyAsync(ds, states, (size_t)count * sizeof(TzState), cudaMemcpyHostToDevice, h->stream));
+    launch_rules_probe(h->d, ds, count, stride, dm, dn, nullptr, h->stream);
+    CU(cudaMemcpyAsync(out_moves, dm, (size_t)count * stride * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(out_n, dn, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_result(tz_handle* h, const tz_state_t* states, int count, int* out_terminal) {
+    CHECK_H(h);
+    if (!states || count < 0 || !out_terminal) return fail(TZ_EINVAL, "bad argument");
+    if (count == 0) return TZ_OK;
+    Scratch s;
+    TzState* ds;
+    int* dt;
+    CU(s.get(&ds, (size_t)count));
+    CU(s.get(&dt, (size_t)count));
+    CU(cudaMemcpyAsync(ds, states, (size_t)count * sizeof(TzState), cudaMemcpyHostToDevice, h->stream));
+    launch_rules_probe(h->d, ds, count, 0, nullptr, nullptr, dt, h->stream);
+    CU(cudaMemcpyAsync(out_terminal, dt, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_apply(tz_handle* h, tz_state_t* states, const tz_move_t* moves, int count, int* out_ok) {
+    CHECK_H(h);
+    if (!states || !moves || count < 0) return fail(TZ_EINVAL, "bad argument");
+    if (count == 0) return TZ_OK;
+    Scratch s;
+    TzState* ds;
+    uint16_t* dm;
+    int* dk;
+    CU(s.get(&ds, (size_t)count));
+    CU(s.get(&dm, (size_t)count));
+    CU(s.get(&dk, (size_t)count));
+    CU(cudaMemcpyAsync(ds, states, (size_t)count * sizeof(TzState), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(dm, moves, (size_t)count * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
+    launch_apply_moves(h->d, ds, dm, count, dk, h->stream);
+    CU(cudaMemcpyAsync(states, ds, (size_t)count * sizeof(TzState), cudaMemcpyDeviceToHost, h->stream));
+    if (out_ok) CU(cudaMemcpyAsync(out_ok, dk, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return TZ_OK;
+}
+
+// ---- positions --------------------------------------------------------------------------------
+
+static int upload_mask(tz_handle* h, const uint8_t* mask, const uint8_t** dmask) {
+    *dmask = nullptr;
+    if (mask) {
+        CU(cudaMemcpyAsync(h->mask, mask, (size_t)h->d.G, cudaMemcpyHostToDevice, h->stream));
+        *dmask = h->mask;
+    }
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_set_positions(tz_handle* h, const tz_state_t* states, const uint8_t* mask) {
+    CHECK_H(h);
+    if (!states) return fail(TZ_EINVAL, "null states");
+    const uint8_t* dmask;
+    int rc = upload_mask(h, mask, &dmask);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h->d.leaf_state, states, (size_t)h->d.G * sizeof(TzState), cudaMemcpyHostToDevice, h->stream));
+    launch_set_positions(h->d, h->d.leaf_state, dmask, h->stream);
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_get_positions(tz_handle* h, tz_state_t* out) {
+    CHECK_H(h);
+    if (!out) return fail(TZ_EINVAL, "null out");
+    CU(cudaMemcpyAsync(out, h->d.env, (size_t)h->d.G * sizeof(TzState), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return TZ_OK;
+}
+
+static int upload_openings(tz_handle* h, const int* sym, const int* adj, const int** dsym, const int** dadj) {
+    *dsym = *dadj = nullptr;
+    if ((sym == nullptr) != (adj == nullptr)) return fail(TZ_EINVAL, "sym and adj must both be given or both NULL");
+    if (sym) {
+        for (int g = 0; g < h->d.G; g++)
+            if (sym[g] < 0 || sym[g] > 7 || adj[g] < 0 || adj[g] > 1) return fail(TZ_EINVAL, "bad opening for game %d", g);
+        CU(cudaMemcpyAsync(h->sym, sym, (size_t)h->d.G * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->adj, adj, (size_t)h->d.G * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        *dsym = h->sym;
+        *dadj = h->adj;
+    }
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_new_openings(tz_handle* h, const uint8_t* mask, const int* sym, const int* adj, uint64_t seed) {
+    CHECK_H(h);
+    const uint8_t* dmask;
+    const int *dsym, *dadj;
+    int rc = upload_mask(h, mask, &dmask);
+    if (rc) return rc;
+    rc = upload_openings(h, sym, adj, &dsym, &dadj);
+    if (rc) return rc;
+    launch_new_openings(h->d, dmask, dsym, dadj, seed, h->opening_counter++, h->stream);
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_reset_roots(tz_handle* h, const uint8_t* mask) {
+    CHECK_H(h);
+    const uint8_t* dmask;
+    int rc = upload_mask(h, mask, &dmask);
+    if (rc) return rc;
+    launch_reset_roots(h->d, dmask, h->stream);
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return TZ_OK;
+}
+
+// ---- search -------------------------------------------------------------------------------------
+
+extern "C" TZ_API int tz_set_agent(tz_handle* h, int kind, tz_agent_fn fn, void* ctx) {
+    CHECK_H(h);
+    if (kind == TZ_AGENT_HOST) {
+        if (!fn) return fail(TZ_EINVAL, "TZ_AGENT_HOST needs a callback");
+        const size_t G = (size_t)h->d.G, M = (size_t)h->d.M;
+        if (!h->pin_states) {
+            CU(cudaHostAlloc((void**)&h->pin_states, G * sizeof(TzState), cudaHostAllocDefault));
+            CU(cudaHostAlloc((void**)&h->pin_actions, G * M * sizeof(uint16_t), cudaHostAllocDefault));
+            CU(cudaHostAlloc((void**)&h->pin_nact, G * sizeof(int), cudaHostAllocDefault));
+            CU(cudaHostAlloc((void**)&h->pin_logits, G * M * sizeof(float), cudaHostAllocDefault));
+            CU(cudaHostAlloc((void**)&h->pin_value, G * sizeof(float), cudaHostAllocDefault));
+            CU(cudaHostAlloc((void**)&h->pin_variance, G * sizeof(float), cudaHostAllocDefault));
+        }
+    } else if (kind == TZ_AGENT_NETWORK) {
+        if (!nn_ready(h)) return fail(TZ_ENOWEIGHTS, "TZ_AGENT_NETWORK needs tz_set_weights first");
+    } else if (kind != TZ_AGENT_SYNTHETIC) {
+        return fail(TZ_EINVAL, "unknown agent kind %d", kind);
+    }
+    h->agent_kind = kind;
+    h->agent_fn = fn;
+    h->agent_ctx = ctx;
+    return TZ_OK;
+}
+
+// one lock-step simulation of all games (batched.rs:63-128 / :266-333)
+static int lockstep(tz_handle* h, int phase, int halving_i, const float* dbetas) {
+    const TzDev& d = h->d;
+    CU(cudaMemsetAsync(d.nn_count, 0, sizeof(int), h->stream));
+    launch_select(d, phase, halving_i, dbetas, h->stream);
+    if (h->agent_kind == TZ_AGENT_SYNTHETIC) {
+        launch_agent_synth(d, h->stream);
+    } else if (h->agent_kind == TZ_AGENT_NETWORK) {
+        int rc = nn_forward_queue(h);
+        if (rc) return fail(rc, "network forward failed: %s", cudaGetErrorString(cudaGetLastError()));
+    } else {
+        int* cnt = (int*)(h->pin_small + 64);
+        CU(cudaMemcpyAsync(cnt, d.nn_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        const size_t c = (size_t)*cnt, M = (size_t)d.M;
+        if (c > 0) {
+            CU(cudaMemcpyAsync(h->pin_states, d.leaf_state, c * sizeof(TzState), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaMemcpyAsync(h->pin_actions, d.actions, c * M * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaMemcpyAsync(h->pin_nact, d.n_actions, c * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+            h->agent_fn(h->agent_ctx, (int)c, (const tz_state_t*)h->pin_states, h->pin_actions, h->pin_nact, d.M,
+                        h->pin_logits, h->pin_value, h->pin_variance);
+            CU(cudaMemcpyAsync(d.logits, h->pin_logits, c * M * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+            CU(cudaMemcpyAsync(d.value, h->pin_value, c * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+            CU(cudaMemcpyAsync(d.variance, h->pin_variance, c * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        }
+    }
+    launch_expand(d, h->stream);
+    h->launches += 3;
+    return TZ_OK;
+}
+
+static int upload_betas(tz_handle* h, const float* betas, const float** dbetas) {
+    *dbetas = nullptr;
+    if (betas) {
+        CU(cudaMemcpyAsync(h->betas, betas, (size_t)h->d.G * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        *dbetas = h->betas;
+    }
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_simulate(tz_handle* h, const float* betas) {
+    CHECK_H(h);
+    const float* dbetas;
+    int rc = upload_betas(h, betas, &dbetas);
+    if (rc) return rc;
+    rc = lockstep(h, 0, 0, dbetas);
+    if (rc) return rc;
+    return finish(h);
+}
+
+static uint32_t ilog2_u32(uint32_t x) {
+    uint32_t r = 0;
+    while (x >>= 1) r++;
+    return r;
+}
+
+// device-resident body of gumbel_sequential_halving; moves land in h->moves
+int tz_search_device(tz_handle* h, const float* dbetas, int k, uint32_t budget, const float* dgumbel, int stride) {
+    const TzDev& d = h->d;
+    const uint32_t steps = ilog2_u32((uint32_t)k);
+    int rc = lockstep(h, 0, 0, dbetas);  // batched.rs:223
+    if (rc) return rc;
+    launch_gumbel_init(d, k, dgumbel, stride, h->stream);
+    const uint32_t visits_per_step = budget / steps;
+    uint32_t visits_to_most_visited = 0;
+    int remaining = k;
+    for (uint32_t step = 0; step < steps; step++) {
+        const uint32_t visits_per_action = visits_per_step / (uint32_t)remaining;
+        for (int i = 0; i < remaining; i++)
+            for (uint32_t v = 0; v < visits_per_action; v++) {
+                rc = lockstep(h, 1, i, nullptr);
+                if (rc) return rc;
+            }
+        visits_to_most_visited += visits_per_action;
+        remaining /= 2;
+        launch_halve(d, dbetas, (float)visits_to_most_visited, remaining, h->stream);
+    }
+    launch_finalize(d, h->moves, h->stream);
+    h->launches += 2 + steps;
+    h->move_counter++;
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_gumbel_sequential_halving(tz_handle* h, const float* betas, int sampled_actions,
+                                            uint32_t search_budget, const float* gumbel, int gumbel_stride,
+                                            uint64_t seed, tz_move_t* out_moves) {
+    CHECK_H(h);
+    // batched.rs:215-220
+    if (sampled_actions <= 0 || sampled_actions > TZ_MAX_K)
+        return fail(TZ_EINVAL, "At least one action must be sampled (and at most %d)", TZ_MAX_K);
+    const uint32_t steps = ilog2_u32((uint32_t)sampled_actions);
+    if (steps == 0 || search_budget % (steps * (uint32_t)sampled_actions) != 0)
+        return fail(TZ_EINVAL, "The search budget should be a multiple of k*log2(k) for clean visits");
+    if (!out_moves) return fail(TZ_EINVAL, "null out_moves");
+    const float* dbetas;
+    int rc = upload_betas(h, betas, &dbetas);
+    if (rc) return rc;
+    const TzDev& d = h->d;
+    int stride = d.M;
+    if (gumbel) {
+        if (gumbel_stride <= 0 || gumbel_stride > d.M) return fail(TZ_EINVAL, "gumbel_stride must be 1..%d", d.M);
+        stride = gumbel_stride;
+        CU(cudaMemcpyAsync(h->gumbel, gumbel, (size_t)d.G * stride * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    } else {
+        launch_gumbel_noise(d, h->gumbel, stride, seed, h->move_counter, h->stream);
+        h->launches += 1;
+    }
+    h->gumbel_stride = stride;
+    rc = tz_search_device(h, dbetas, sampled_actions, search_budget, h->gumbel, stride);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out_moves, h->moves, (size_t)d.G * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
+    return finish(h);
+}
+
+extern "C" TZ_API int tz_last_gumbel(tz_handle* h, float* out, int stride) {
+    CHECK_H(h);
+    if (!out || stride != h->gumbel_stride) return fail(TZ_EINVAL, "stride must equal the last search's (%d)", h->gumbel_stride);
+    CU(cudaMemcpyAsync(out, h->gumbel, (size_t)h->d.G * stride * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_step(tz_handle* h, const tz_move_t* moves) {
+    CHECK_H(h);
+    if (!moves) return fail(TZ_EINVAL, "null moves");
+    CU(cudaMemcpyAsync(h->moves, moves, (size_t)h->d.G * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
+    launch_step(h->d, h->moves, h->stream);
+    h->launches += 1;
+    return finish(h);
+}
+
+extern "C" TZ_API int tz_restart_terminal(tz_handle* h, const int* sym, const int* adj, uint64_t seed, int* out_terminal) {
+    CHECK_H(h);
+    if (!out_terminal) return fail(TZ_EINVAL, "null out_terminal");
+    const int *dsym, *dadj;
+    int rc = upload_openings(h, sym, adj, &dsym, &dadj);
+    if (rc) return rc;
+    launch_restart(h->d, dsym, dadj, seed, h->opening_counter++, h->terminal, h->fin_start, h->fin_replay, h->fin_len,
+                   h->stream);
+    h->launches += 1;
+    CU(cudaMemcpyAsync(out_terminal, h->terminal, (size_t)h->d.G * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    return finish(h);
+}
+
+static int read_replay(tz_handle* h, int game, const TzState* starts, const uint16_t* replays, const int* lens,
+                       tz_state_t* out_start, tz_move_t* out_moves, int cap) {
+    if (game < 0 || game >= h->d.G) return fail(TZ_EINVAL, "bad game index");
+    int* len = (int*)(h->pin_small + 128);
+    CU(cudaMemcpyAsync(len, lens + game, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (out_start)
+        CU(cudaMemcpyAsync(out_start, starts + game, sizeof(TzState), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    const int n = *len < cap ? *len : cap;
+    if (out_moves && n > 0) {
+        CU(cudaMemcpyAsync(out_moves, replays + (size_t)game * TZ_MAX_PLIES, (size_t)n * sizeof(uint16_t),
+                           cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return *len;
+}
+
+extern "C" TZ_API int tz_finished_replay(tz_handle* h, int game, tz_state_t* out_start, tz_move_t* out_moves, int cap) {
+    CHECK_H(h);
+    return read_replay(h, game, h->fin_start, h->fin_replay, h->fin_len, out_start, out_moves, cap);
+}
+
+extern "C" TZ_API int tz_replay(tz_handle* h, int game, tz_state_t* out_start, tz_move_t* out_moves, int cap) {
+    CHECK_H(h);
+    return read_replay(h, game, h->d.start_env, h->d.replay, h->d.replay_len, out_start, out_moves, cap);
+}
+
+// ---- read-backs ---------------------------------------------------------------------------------
+
+extern "C" TZ_API int tz_root_children(tz_handle* h, int stride, int* out_n, tz_move_t* moves, uint32_t* visits,
+                                uint32_t* eval_tag, uint32_t* eval_bits, float* logit, float* prob, float* std_dev) {
+    CHECK_H(h);
+    const TzDev& d = h->d;
+    if (stride <= 0 || stride > d.M || !out_n) return fail(TZ_EINVAL, "stride must be 1..%d", d.M);
+    launch_root_table(d, stride, h->tbl_n, h->tbl_moves, h->tbl_u32a, h->tbl_u32b, h->tbl_u32c, h->tbl_f32a,
+                      h->tbl_f32b, h->tbl_f32c, h->stream);
+    const size_t cells = (size_t)d.G * stride;
+    CU(cudaMemcpyAsync(out_n, h->tbl_n, (size_t)d.G * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+#define BACK(dst, src, type) \
+    if (dst) CU(cudaMemcpyAsync(dst, src, cells * sizeof(type), cudaMemcpyDeviceToHost, h->stream))
+    BACK(moves, h->tbl_moves, uint16_t);
+    BACK(visits, h->tbl_u32a, uint32_t);
+    BACK(eval_tag, h->tbl_u32b, uint32_t);
+    BACK(eval_bits, h->tbl_u32c, uint32_t);
+    BACK(logit, h->tbl_f32a, float);
+    BACK(prob, h->tbl_f32b, float);
+    BACK(std_dev, h->tbl_f32c, float);
+#undef BACK
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_root_stats(tz_handle* h, tz_root_t* out) {
+    CHECK_H(h);
+    if (!out) return fail(TZ_EINVAL, "null out");
+    launch_root_stats(h->d, h->root_stats, h->stream);
+    CU(cudaMemcpyAsync(out, h->root_stats, (size_t)h->d.G * 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_targets(tz_handle* h, float visitations, float beta, int stride, float* out_policy, float* out_ube,
+                          int* out_n, tz_move_t* out_moves) {
+    CHECK_H(h);
+    const TzDev& d = h->d;
+    if (stride <= 0 || stride > d.M || !out_policy || !out_ube || !out_n) return fail(TZ_EINVAL, "bad argument");
+    launch_targets(d, visitations, beta, stride, h->tbl_f32a, h->ube, h->tbl_n, out_moves ? h->tbl_moves : nullptr,
+                   h->stream);
+    h->launches += 1;
+    const size_t cells = (size_t)d.G * stride;
+    CU(cudaMemcpyAsync(out_policy, h->tbl_f32a, cells * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(out_ube, h->ube, (size_t)d.G * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(out_n, h->tbl_n, (size_t)d.G * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (out_moves) CU(cudaMemcpyAsync(out_moves, h->tbl_moves, cells * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
+    return finish(h);
+}
+
+extern "C" TZ_API int tz_select_best(tz_handle* h, tz_move_t* out_moves) {
+    CHECK_H(h);
+    if (!out_moves) return fail(TZ_EINVAL, "null out_moves");
+    launch_select_actions(h->d, 0, 0, 0.0f, nullptr, 0, 0, h->moves, h->stream);
+    h->launches += 1;
+    CU(cudaMemcpyAsync(out_moves, h->moves, (size_t)h->d.G * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
+    return finish(h);
+}
+
+extern "C" TZ_API int tz_select_selfplay(tz_handle* h, int weighted_random_plies, uint32_t threshold, float allowed_eval_drop,
+                                  const uint64_t* randoms, uint64_t seed, tz_move_t* out_moves) {
+    CHECK_H(h);
+    if (!out_moves) return fail(TZ_EINVAL, "null out_moves");
+    const unsigned long long* dr = nullptr;
+    if (randoms) {
+        CU(cudaMemcpyAsync(h->randoms, randoms, (size_t)h->d.G * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+        dr = h->randoms;
+    }
+    launch_select_actions(h->d, weighted_random_plies, threshold, allowed_eval_drop, dr, seed, h->move_counter, h->moves,
+                          h->stream);
+    h->launches += 1;
+    CU(cudaMemcpyAsync(out_moves, h->moves, (size_t)h->d.G * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
+    return finish(h);
+}
+
+extern "C" TZ_API int tz_counters(tz_handle* h, tz_counters_t* out) {
+    CHECK_H(h);
+    if (!out) return fail(TZ_EINVAL, "null out");
+    std::vector<unsigned long long> c((size_t)h->d.G * 4);
+    CU(cudaMemcpyAsync(c.data(), h->d.counters, c.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    memset(out, 0, sizeof(*out));
+    for (int g = 0; g < h->d.G; g++) {
+        out->simulations += c[(size_t)g * 4 + 0];
+        out->evaluations += c[(size_t)g * 4 + 1];
+        out->known += c[(size_t)g * 4 + 2];
+        out->expansions += c[(size_t)g * 4 + 3];
+    }
+    return TZ_OK;
+}

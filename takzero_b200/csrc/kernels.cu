@@ -1,0 +1,917 @@
+// kernels.cu -- warp-per-game rules / tree kernels of the batched self-play search (sm_100a).
+//
+// One warp owns one game for the whole kernel: the position lives in shared memory
+// (TzState, 384 B), the tree in the game's struct-of-arrays arena in HBM (children of a
+// node are contiguous, so a warp reads 32 children per 128-byte transaction).
+// What each kernel replaces in the reference (paths relative to takzero/src/):
+//   k_select        search/node/mcts.rs:107-163 (forward, backward_known_eval) as driven by
+//                   search/node/batched.rs:63-100,254-295; env.rs:39-59 (fast-tak rules)
+//   k_expand        node/policy.rs:10-19 (softmax), mcts.rs:171-225 (backward_network_eval)
+//   k_gumbel_init   batched.rs:226-244      k_halve     batched.rs:338-355
+//   k_finalize      batched.rs:358-406      k_step      batched.rs:131-144, node/mod.rs:95-102
+//   k_restart       batched.rs:185-203, env.rs:65-79
+//   k_targets       node/policy.rs:23-48, node/mod.rs:215-230
+//   k_select_actions node/mod.rs:132-207
+#include "kernels.cuh"
+#include "rules.cuh"
+#include "tree.cuh"
+
+#define WPB TZ_WARPS_PER_BLOCK
+
+__device__ __forceinline__ void flag_error(const TzDev& d, uint32_t bit, int lane) {
+    if (lane == 0) atomicOr(d.status, bit);
+}
+
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+
+// ---- one lock-step simulation: selection -----------------------------------------
+
+__global__ void __launch_bounds__(32 * WPB) k_select(TzDev d, int phase, int halving_i, const float* betas) {
+    __shared__ TzState s_state[WPB];
+    __shared__ uint16_t s_moves[WPB][TZ_MAX_MOVES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * WPB + warp;
+    if (g >= d.G) return;
+    TzState* st = &s_state[warp];
+    warp_load_state(st, &d.env[g], lane);
+    const GameTree t = game_tree(d.arena, g);
+    uint32_t* traj = d.traj + (size_t)g * TZ_MAX_DEPTH;
+    unsigned long long* ctr = d.counters + (size_t)g * 4;
+
+    uint32_t slot = 0;
+    float beta = 0.0f;
+    if (phase == 0) {
+        beta = betas ? betas[g] : 0.0f;
+    } else {
+        // batched.rs:255-264: simulate below the i-th surviving root child (index wraps)
+        const int len = d.set_len[g];
+        if (len <= 0) {
+            flag_error(d, TZ_ERR_SET_EMPTY, lane);
+            return;
+        }
+        const int child = d.set_child[(size_t)g * TZ_MAX_K + (halving_i % len)];
+        slot = t.first[0] + (uint32_t)child;
+        if (!warp_apply(st, d.n, (uint16_t)tz_meta_move(t.meta[slot]), lane)) flag_error(d, TZ_ERR_BAD_MOVE, lane);
+    }
+    if (lane == 0) ctr[0] += 1;
+
+    int len = 0;
+    bool known = false;
+    Ev known_ev = ev_value(0.0f);
+    while (true) {
+        if (len >= TZ_MAX_DEPTH) {
+            flag_error(d, TZ_ERR_DEPTH, lane);
+            return;
+        }
+        if (lane == 0) {
+            t.visits[slot] += 1;
+            traj[len] = slot;
+        }
+        len++;
+        __syncwarp();
+        const uint32_t meta = t.meta[slot];
+        const uint32_t tag = tz_meta_tag(meta);
+        if (tag != TZ_E_VALUE && t.eval[slot] == 0) {  // is_terminal
+            known = true;
+            known_ev = ev_make(tag, 0);
+            break;
+        }
+        if (tz_meta_nchild(meta) == 0 && tag == TZ_E_VALUE) {  // needs_initialization
+            const int term = warp_terminal(st, d.n, d.half_komi, d.rev_limit, lane);
+            if (term != TZ_T_NONE) {
+                known = true;
+                known_ev = ev_make(term == TZ_T_WIN ? TZ_E_WIN : (term == TZ_T_LOSS ? TZ_E_LOSS : TZ_E_DRAW), 0);
+                if (lane == 0) {
+                    node_set_eval(t, slot, known_ev);
+                    t.std_dev[slot] = 0.0f;
+                }
+                __syncwarp();
+            }
+            break;
+        }
+        bool nan_seen;
+        const int idx = warp_select_puct(t, slot, beta, d.ln_table, lane, &nan_seen);
+        if (nan_seen) flag_error(d, TZ_ERR_NAN, lane);
+        if (idx < 0) {
+            flag_error(d, TZ_ERR_NO_CHILD, lane);
+            return;
+        }
+        slot = t.first[slot] + (uint32_t)idx;
+        if (!warp_apply(st, d.n, (uint16_t)tz_meta_move(t.meta[slot]), lane)) flag_error(d, TZ_ERR_BAD_MOVE, lane);
+    }
+
+    if (known) {
+        if (lane == 0) ctr[2] += 1;
+        Propagated p;
+        p.eval = known_ev;
+        p.variance = 0.0f;
+        warp_backup(t, traj, len, p, lane);
+        return;
+    }
+    // Forward::NeedsNetwork: legal moves + leaf position go to the evaluation queue
+    const int cnt = warp_movegen(st, d.n, s_moves[warp], lane);
+    if (cnt < 0 || cnt > d.M) {
+        flag_error(d, TZ_ERR_TOO_MANY_MOVES, lane);
+        return;
+    }
+    int q = 0;
+    if (lane == 0) {
+        q = atomicAdd(d.nn_count, 1);
+        d.nn_queue[q] = g;
+        d.n_actions[q] = cnt;
+        d.traj_len[g] = len;
+        ctr[1] += 1;
+    }
+    q = __shfl_sync(FULL_MASK, q, 0);
+    warp_store_state(&d.leaf_state[q], st, lane);
+    uint16_t* out = d.actions + (size_t)q * d.M;
+    for (int i = lane; i < cnt; i += 32) out[i] = s_moves[warp][i];
+}
+
+// ---- synthetic agent (oracle/tak_search.c `tk_agent_synthetic`) ----------------------
+
+__global__ void __launch_bounds__(32 * WPB) k_agent_synth(TzDev d) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * WPB + warp;
+    if (q >= *d.nn_count) return;
+    const uint64_t h = warp_state_hash(&d.leaf_state[q], d.nn, lane);
+    const int cnt = d.n_actions[q];
+    const uint16_t* act = d.actions + (size_t)q * d.M;
+    float* lg = d.logits + (size_t)q * d.M;
+    for (int i = lane; i < cnt; i += 32) {
+        const uint64_t hm = tz_mix64(h ^ ((uint64_t)act[i] * 0x9e3779b97f4a7c15ULL));
+        lg[i] = (float)((int)(hm & 0x7fff) - 16384) * (1.0f / 4096.0f);
+    }
+    if (lane == 0) {
+        d.value[q] = (float)((int)((h >> 20) & 0xffff) - 32768) * (0.75f / 32768.0f);
+        d.variance[q] = (float)((h >> 40) & 0xffff) * (1.0f / 65536.0f);
+    }
+}
+
+// ---- one lock-step simulation: softmax + expansion + backup ------------------------------
+
+// softmax of policy.rs:10-19 over `n` values already staged in `buf` (shared memory):
+// max, exp(x - max) with the libm-exact expf, SEQUENTIAL f32 sum, division.
+__device__ __forceinline__ bool warp_softmax_inplace(float* buf, int n, int lane) {
+    float mx = -__int_as_float(0x7f800000);
+    bool bad = false;
+    for (int i = lane; i < n; i += 32) {
+        const float x = buf[i];
+        bad = bad || x != x;
+        mx = fmaxf(mx, x);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL_MASK, mx, o));
+    if (n == 0) mx = 0.0f;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) buf[i] = expf_libm(fsub(buf[i], mx));
+    __syncwarp();
+    float sum = 0.0f;
+    if (lane == 0)
+        for (int i = 0; i < n; i++) sum = fadd(sum, buf[i]);
+    sum = __shfl_sync(FULL_MASK, sum, 0);
+    for (int i = lane; i < n; i += 32) buf[i] = fdiv(buf[i], sum);
+    __syncwarp();
+    return !__any_sync(FULL_MASK, bad);
+}
+
+__global__ void __launch_bounds__(32 * WPB) k_expand(TzDev d) {
+    __shared__ float s_p[WPB][TZ_MAX_MOVES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * WPB + warp;
+    if (q >= *d.nn_count) return;
+    const int g = d.nn_queue[q];
+    const int n = d.n_actions[q];
+    const GameTree t = game_tree(d.arena, g);
+    const uint32_t* traj = d.traj + (size_t)g * TZ_MAX_DEPTH;
+    const int len = d.traj_len[g];
+    const float* lg = d.logits + (size_t)q * d.M;
+    const uint16_t* act = d.actions + (size_t)q * d.M;
+    float* p = s_p[warp];
+    for (int i = lane; i < n; i += 32) p[i] = lg[i];
+    __syncwarp();
+    const float value = d.value[q], variance = d.variance[q];
+    if (!warp_softmax_inplace(p, n, lane) || value != value || variance != variance)
+        flag_error(d, TZ_ERR_NAN, lane);
+
+    // leaf: running mean / std (mcts.rs:190-197); the leaf's evaluation is a Value here
+    const uint32_t leaf = traj[len - 1];
+    const float nv = (float)t.visits[leaf];
+    float m = __uint_as_float(t.eval[leaf]);
+    float sd = t.std_dev[leaf];
+    m = fadd(m, fdiv(fadd(fneg(m), value), nv));
+    sd = fadd(sd, fdiv(fadd(fneg(sd), fsqrt(variance)), nv));
+    // children (mcts.rs:199-217, node/mod.rs:66-79)
+    uint32_t start = 0;
+    if (lane == 0) {
+        start = d.arena.next_slot[g];
+        if (start + (uint32_t)n > d.arena.cap) {
+            start = 0;
+        } else {
+            d.arena.next_slot[g] = start + (uint32_t)n;
+            d.counters[(size_t)g * 4 + 3] += 1;
+        }
+    }
+    start = __shfl_sync(FULL_MASK, start, 0);
+    if (start == 0) {
+        flag_error(d, TZ_ERR_ARENA_FULL, lane);
+        return;
+    }
+    const uint32_t child_eval = __float_as_uint(fneg(m));
+    for (int i = lane; i < n; i += 32) {
+        const uint32_t c = start + i;
+        t.eval[c] = child_eval;
+        t.meta[c] = tz_meta(act[i], TZ_E_VALUE, 0);
+        t.visits[c] = 0;
+        t.prob[c] = p[i];
+        t.std_dev[c] = sd;
+        t.logit[c] = lg[i];
+        t.first[c] = 0;
+    }
+    if (lane == 0) {
+        t.eval[leaf] = __float_as_uint(m);
+        t.std_dev[leaf] = sd;
+        t.meta[leaf] = tz_meta(tz_meta_move(t.meta[leaf]), TZ_E_VALUE, (uint32_t)n);
+        t.first[leaf] = start;
+    }
+    __syncwarp();
+    Propagated pr;
+    pr.eval = ev_value(fmul(value, 0.997f));
+    pr.variance = fmul(fmul(variance, 0.997f), 0.997f);
+    warp_backup(t, traj, len, pr, lane);
+}
+
+// ---- Gumbel top-k and sequential halving -----------------------------------------------
+
+__device__ __forceinline__ uint64_t rng_hash(uint64_t seed, uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t h = tz_mix64(seed ^ 0x9e3779b97f4a7c15ULL);
+    h = tz_mix64(h ^ (a * 0xbf58476d1ce4e5b9ULL));
+    h = tz_mix64(h ^ (b * 0x94d049bb133111ebULL));
+    return tz_mix64(h ^ (c * 0xd6e8feb86659fd93ULL));
+}
+
+// Gumbel(0,1) noise for every (game, child index): the reference draws from `rand`
+// (batched.rs:226-227), whose stream is not pinned, so this is our own counter-based
+// generator keyed by the GLOBAL game id (sharded == unsharded).
+__global__ void k_gumbel_noise(TzDev d, float* out, int stride, unsigned long long seed,
+                               unsigned long long counter) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)d.G * stride) return;
+    const int g = (int)(idx / stride), i = (int)(idx % stride);
+    const uint64_t h = rng_hash(seed, (uint64_t)(d.game_base + g), counter, (uint64_t)i);
+    const float u = ((float)(h >> 40) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
+    out[idx] = -logf(-logf(u));
+}
+
+// stable descending rank of element `i` among `n` keys in shared memory
+__device__ __forceinline__ int stable_desc_rank(const float* keys, int n, int i) {
+    const float k = keys[i];
+    int rank = 0;
+    for (int j = 0; j < n; j++) {
+        const float o = keys[j];
+        rank += (o > k) || (o == k && j < i);
+    }
+    return rank;
+}
+
+__global__ void __launch_bounds__(32 * WPB) k_gumbel_init(TzDev d, int k, const float* gumbel, int stride) {
+    __shared__ float s_key[WPB][TZ_MAX_MOVES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * WPB + warp;
+    if (g >= d.G) return;
+    const GameTree t = game_tree(d.arena, g);
+    const int n = (int)tz_meta_nchild(t.meta[0]);
+    const uint32_t first = t.first[0];
+    float* keys = s_key[warp];
+    bool bad = false;
+    for (int i = lane; i < n; i += 32) {
+        const float key = fadd(t.logit[first + i], gumbel[(size_t)g * stride + i]);
+        bad = bad || key != key;
+        keys[i] = key;
+    }
+    if (__any_sync(FULL_MASK, bad)) flag_error(d, TZ_ERR_NAN, lane);
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+        const int r = stable_desc_rank(keys, n, i);
+        if (r < k) {
+            d.set_child[(size_t)g * TZ_MAX_K + r] = (uint16_t)i;
+            d.set_key[(size_t)g * TZ_MAX_K + r] = keys[i];
+        }
+    }
+    if (lane == 0) d.set_len[g] = n < k ? n : k;
+}
+
+__global__ void __launch_bounds__(32 * WPB) k_halve(TzDev d, const float* betas, float visits, int remaining) {
+    __shared__ float s_key[WPB][TZ_MAX_K];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * WPB + warp;
+    if (g >= d.G) return;
+    const GameTree t = game_tree(d.arena, g);
+    const uint32_t first = t.first[0];
+    const int len = d.set_len[g];
+    const float beta = betas ? betas[g] : 0.0f;
+    float* keys = s_key[warp];
+    uint16_t child[TZ_MAX_K / 32];
+    float base[TZ_MAX_K / 32];
+#pragma unroll
+    for (int r = 0; r < TZ_MAX_K / 32; r++) {
+        const int j = lane + 32 * r;
+        if (j < len) {
+            child[r] = d.set_child[(size_t)g * TZ_MAX_K + j];
+            base[r] = d.set_key[(size_t)g * TZ_MAX_K + j];
+            const uint32_t c = first + child[r];
+            const float q = ev_notnan(ev_negate(node_eval(t, c)));
+            // sigma_select (policy.rs:121-128)
+            const float sig = fmul(fadd(q, fmul(t.std_dev[c], beta)), fadd(50.0f, visits));
+            keys[j] = fadd(base[r], sig);
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < TZ_MAX_K / 32; r++) {
+        const int j = lane + 32 * r;
+        if (j < len) {
+            const int rank = stable_desc_rank(keys, len, j);
+            if (rank < remaining) {
+                d.set_child[(size_t)g * TZ_MAX_K + rank] = child[r];
+                d.set_key[(size_t)g * TZ_MAX_K + rank] = base[r];
+            }
+        }
+    }
+    if (lane == 0) d.set_len[g] = len < remaining ? len : remaining;
+}
+
+// root statistics recompute of batched.rs:373-406; warp-convergent
+__device__ __forceinline__ void warp_root_recompute(const TzDev& d, const GameTree& t, float* buf, int lane) {
+    const uint32_t meta = t.meta[0];
+    const int n = (int)tz_meta_nchild(meta);
+    const uint32_t first = t.first[0];
+    uint32_t sum = 0;
+    for (int i = lane; i < n; i += 32) sum += t.visits[first + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL_MASK, sum, o);
+    const int flags = warp_children_flags(t, first, n, lane);
+    if (lane == 0) t.visits[0] = sum + 1;
+    if (n == 0) return;  // reference: `.min().unwrap()` panics; callers flag the empty root
+    if ((flags & 2) || (flags & 1)) {
+        Ev m;
+        warp_min_child(t, first, n, lane, &m);
+        if (lane == 0) {
+            node_set_eval(t, 0, ev_negate(m));
+            t.std_dev[0] = 0.0f;
+        }
+    } else {
+        // sum of p, then sum of p*q, each SEQUENTIALLY over the visited children
+        const float skip = __int_as_float(0x7fc00000);  // NaN marks an unvisited child
+        for (int i = lane; i < n; i += 32) buf[i] = t.visits[first + i] > 0 ? t.prob[first + i] : skip;
+        __syncwarp();
+        float sum_p = 0.0f;
+        if (lane == 0)
+            for (int i = 0; i < n; i++) {
+                const float x = buf[i];
+                if (x == x) sum_p = fadd(sum_p, x);
+            }
+        __syncwarp();
+        for (int i = lane; i < n; i += 32)
+            if (t.visits[first + i] > 0)
+                buf[i] = fmul(t.prob[first + i], ev_to_f32(ev_negate(node_eval(t, first + i))));
+        __syncwarp();
+        if (lane == 0) {
+            float wq = 0.0f;
+            for (int i = 0; i < n; i++) {
+                const float x = buf[i];
+                if (x == x) wq = fadd(wq, x);
+            }
+            node_set_eval(t, 0, ev_value(fdiv(wq, sum_p)));
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(32 * WPB) k_finalize(TzDev d, uint16_t* out_moves) {
+    __shared__ float s_buf[WPB][TZ_MAX_MOVES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * WPB + warp;
+    if (g >= d.G) return;
+    const GameTree t = game_tree(d.arena, g);
+    if (d.set_len[g] != 1) {
+        flag_error(d, TZ_ERR_SET_EMPTY, lane);
+        if (lane == 0) out_moves[g] = 0xffff;
+    } else if (lane == 0) {
+        const uint32_t c = t.first[0] + d.set_child[(size_t)g * TZ_MAX_K];
+        out_moves[g] = (uint16_t)tz_meta_move(t.meta[c]);
+    }
+    warp_root_recompute(d, t, s_buf[warp], lane);
+}
+
+// ---- step: re-root with subtree reuse ---------------------------------------------------
+
+__device__ __forceinline__ void copy_node(const GameTree& dst, uint32_t to, const GameTree& src, uint32_t from) {
+    dst.eval[to] = src.eval[from];
+    dst.meta[to] = src.meta[from];
+    dst.visits[to] = src.visits[from];
+    dst.prob[to] = src.prob[from];
+    dst.std_dev[to] = src.std_dev[from];
+    dst.logit[to] = src.logit[from];
+    dst.first[to] = src.first[from];
+}
+
+__global__ void __launch_bounds__(32 * WPB) k_step(TzDev d, const uint16_t* moves) {
+    __shared__ TzState s_state[WPB];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * WPB + warp;
+    if (g >= d.G) return;
+    const int half = d.arena.half[g];
+    const GameTree src = game_tree_half(d.arena, g, half);
+    const uint32_t rmeta = src.meta[0];
+    if (tz_meta_tag(rmeta) != TZ_E_VALUE && src.eval[0] == 0) return;  // terminal root: batched.rs:139
+    const uint16_t mv = moves[g];
+    // Node::descend (node/mod.rs:95-102)
+    const int n = (int)tz_meta_nchild(rmeta);
+    const uint32_t first = src.first[0];
+    int found = 0x7fffffff;
+    for (int i = lane; i < n; i += 32)
+        if (tz_meta_move(src.meta[first + i]) == mv && i < found) found = i;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(FULL_MASK, found, o));
+    if (found == 0x7fffffff) {
+        if (lane == 0) {
+            node_reset(src, 0);
+            d.arena.next_slot[g] = 1;
+        }
+    } else {
+        // Cheney copy of the kept subtree into the other half, breadth first
+        const GameTree dst = game_tree_half(d.arena, g, half ^ 1);
+        if (lane == 0) copy_node(dst, 0, src, first + (uint32_t)found);
+        __syncwarp();
+        uint32_t scan = 0, alloc = 1;
+        while (scan < alloc) {
+            const uint32_t s = scan + lane;
+            uint32_t nch = 0, oldf = 0;
+            if (s < alloc) {
+                nch = tz_meta_nchild(dst.meta[s]);
+                oldf = dst.first[s];
+            }
+            uint32_t incl = nch;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(FULL_MASK, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const uint32_t total = __shfl_sync(FULL_MASK, incl, 31);
+            const uint32_t newf = alloc + incl - nch;
+            if (nch > 0) dst.first[s] = newf;
+            uint32_t has = __ballot_sync(FULL_MASK, nch > 0);
+            while (has) {
+                const int L = __ffs(has) - 1;
+                has &= has - 1;
+                const uint32_t of = __shfl_sync(FULL_MASK, oldf, L);
+                const uint32_t nf = __shfl_sync(FULL_MASK, newf, L);
+                const uint32_t cnt = __shfl_sync(FULL_MASK, nch, L);
+                for (uint32_t i = lane; i < cnt; i += 32) copy_node(dst, nf + i, src, of + i);
+            }
+            const uint32_t before = alloc;
+            alloc += total;
+            scan = scan + 32 < before ? scan + 32 : before;
+            __syncwarp();
+        }
+        if (lane == 0) {
+            d.arena.half[g] = (uint8_t)(half ^ 1);
+            d.arena.next_slot[g] = alloc;
+        }
+    }
+    // replay.push(action); env.step(action)
+    TzState* st = &s_state[warp];
+    warp_load_state(st, &d.env[g], lane);
+    if (!warp_apply(st, d.n, mv, lane)) flag_error(d, TZ_ERR_BAD_MOVE, lane);
+    warp_store_state(&d.env[g], st, lane);
+    if (lane == 0) {
+        const int rl = d.replay_len[g];
+        if (rl < TZ_MAX_PLIES) {
+            d.replay[(size_t)g * TZ_MAX_PLIES + rl] = mv;
+            d.replay_len[g] = rl + 1;
+        } else {
+            atomicOr(d.status, TZ_ERR_REPLAY_FULL);
+        }
+    }
+}
+
+// ---- positions, openings, restarts ------------------------------------------------------
+
+__device__ __forceinline__ void state_init(TzState* s, int n) {
+    // standard Tak reserves (consistent with network/repr.rs:303-409: 3 -> 10/0, 5 -> 21/1)
+    const int stones = n == 3 ? 10 : n == 4 ? 15 : n == 5 ? 21 : 30;
+    const int caps = n >= 5 ? 1 : 0;
+    uint32_t* w = reinterpret_cast<uint32_t*>(s);
+    for (int i = 0; i < (int)(sizeof(TzState) / 4); i++) w[i] = 0;
+    s->stones[0] = s->stones[1] = (uint8_t)stones;
+    s->caps[0] = s->caps[1] = (uint8_t)caps;
+}
+
+// env.rs:65-79: two flat placements on opposite / adjacent corners under one of 8
+// symmetries (bit 0 mirror columns, bit 1 mirror rows, bit 2 transpose; the crate's own
+// index order is not pinned by the reference)
+__device__ __forceinline__ void warp_new_opening(TzState* st, int n, int symmetry, int adjacent, int lane) {
+    if (lane == 0) state_init(st, n);
+    __syncwarp();
+    for (int i = 0; i < 2; i++) {
+        int col = i == 0 ? 0 : (adjacent ? 0 : n - 1);
+        int row = i == 0 ? 0 : n - 1;
+        if (symmetry & 1) col = n - 1 - col;
+        if (symmetry & 2) row = n - 1 - row;
+        if (symmetry & 4) {
+            const int tmp = col;
+            col = row;
+            row = tmp;
+        }
+        warp_apply(st, n, tz_mk_move(row, col, TZ_FLAT, 0), lane);
+    }
+}
+
+__device__ __forceinline__ void warp_fresh_game(const TzDev& d, int g, const TzState* st, int lane) {
+    warp_store_state(&d.env[g], st, lane);
+    warp_store_state(&d.start_env[g], st, lane);
+    if (lane == 0) {
+        node_reset(game_tree(d.arena, g), 0);
+        d.arena.next_slot[g] = 1;
+        d.replay_len[g] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(32 * WPB) k_new_openings(TzDev d, const uint8_t* mask, const int* sym,
+                                                           const int* adj, unsigned long long seed,
+                                                           unsigned long long counter) {
+    __shared__ TzState s_state[WPB];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * WPB + warp;
+    if (g >= d.G || (mask && !mask[g])) return;
+    const uint64_t h = rng_hash(seed, (uint64_t)(d.game_base + g), counter, 0x0fe11ULL);
+    warp_new_opening(&s_state[warp], d.n, sym ? sym[g] : (int)(h & 7), adj ? adj[g] : (int)((h >> 3) & 1), lane);
+    warp_fresh_game(d, g, &s_state[warp], lane);
+}
+
+__global__ void __launch_bounds__(32 * WPB) k_set_positions(TzDev d, const TzState* states, const uint8_t* mask) {
+    __shared__ TzState s_state[WPB];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * WPB + warp;
+    if (g >= d.G || (mask && !mask[g])) return;
+    warp_load_state(&s_state[warp], &states[g], lane);
+    warp_fresh_game(d, g, &s_state[warp], lane);
+}
+
+__global__ void k_reset_roots(TzDev d, const uint8_t* mask) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= d.G || (mask && !mask[g])) return;
+    node_reset(game_tree(d.arena, g), 0);
+    d.arena.next_slot[g] = 1;
+}
+
+// batched.rs:185-203.  A finished game's replay is parked in fin_* before the reset so the
+// host can still read it.
+__global__ void __launch_bounds__(32 * WPB) k_restart(TzDev d, const int* sym, const int* adj,
+                                                      unsigned long long seed, unsigned long long counter,
+                                                      int* out_terminal, TzState* fin_start, uint16_t* fin_replay,
+                                                      int* fin_len) {
+    __shared__ TzState s_state[WPB];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * WPB + warp;
+    if (g >= d.G) return;
+    TzState* st = &s_state[warp];
+    warp_load_state(st, &d.env[g], lane);
+    const int term = warp_terminal(st, d.n, d.half_komi, d.rev_limit, lane);
+    if (lane == 0) out_terminal[g] = term;
+    if (term == TZ_T_NONE) return;
+    const int rl = d.replay_len[g];
+    for (int i = lane; i < rl; i += 32)
+        fin_replay[(size_t)g * TZ_MAX_PLIES + i] = d.replay[(size_t)g * TZ_MAX_PLIES + i];
+    if (lane == 0) fin_len[g] = rl;
+    __syncwarp();
+    warp_load_state(st, &d.start_env[g], lane);
+    warp_store_state(&fin_start[g], st, lane);
+    __syncwarp();
+    const uint64_t h = rng_hash(seed, (uint64_t)(d.game_base + g), counter, 0x0fe11ULL);
+    warp_new_opening(st, d.n, sym ? sym[g] : (int)(h & 7), adj ? adj[g] : (int)((h >> 3) & 1), lane);
+    warp_fresh_game(d, g, st, lane);
+}
+
+// ---- root read-backs ---------------------------------------------------------------------
+
+__global__ void __launch_bounds__(32 * WPB) k_root_table(TzDev d, int stride, int* out_n, uint16_t* moves,
+                                                         uint32_t* visits, uint32_t* eval_tag, uint32_t* eval_bits,
+                                                         float* logit, float* prob, float* std_dev) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * WPB + warp;
+    if (g >= d.G) return;
+    const GameTree t = game_tree(d.arena, g);
+    int n = (int)tz_meta_nchild(t.meta[0]);
+    const uint32_t first = t.first[0];
+    if (lane == 0) out_n[g] = n;
+    if (n > stride) n = stride;
+    for (int i = lane; i < n; i += 32) {
+        const uint32_t c = first + i;
+        const size_t o = (size_t)g * stride + i;
+        const uint32_t m = t.meta[c];
+        moves[o] = (uint16_t)tz_meta_move(m);
+        visits[o] = t.visits[c];
+        eval_tag[o] = tz_meta_tag(m);
+        eval_bits[o] = t.eval[c];
+        logit[o] = t.logit[c];
+        prob[o] = t.prob[c];
+        std_dev[o] = t.std_dev[c];
+    }
+}
+
+// per game: {eval tag, eval bits, visits, std bits, child count, arena slots in use}
+__global__ void k_root_stats(TzDev d, uint32_t* out) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= d.G) return;
+    const GameTree t = game_tree(d.arena, g);
+    const uint32_t m = t.meta[0];
+    uint32_t* o = out + (size_t)g * 6;
+    o[0] = tz_meta_tag(m);
+    o[1] = t.eval[0];
+    o[2] = t.visits[0];
+    o[3] = __float_as_uint(t.std_dev[0]);
+    o[4] = tz_meta_nchild(m);
+    o[5] = d.arena.next_slot[g];
+}
+
+// improved policy (policy.rs:23-48) and UBE target (node/mod.rs:215-230) of every root.
+// visitations < 0 selects `most_visited_count()` per root (reanalyze/src/main.rs:196-202).
+__global__ void __launch_bounds__(32 * WPB) k_targets(TzDev d, float visitations, float beta, int stride,
+                                                      float* out_policy, float* out_ube, int* out_n,
+                                                      uint16_t* out_moves) {
+    __shared__ float s_p[WPB][TZ_MAX_MOVES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * WPB + warp;
+    if (g >= d.G) return;
+    const GameTree t = game_tree(d.arena, g);
+    const uint32_t meta = t.meta[0];
+    const int n = (int)tz_meta_nchild(meta);
+    const uint32_t first = t.first[0];
+    const Ev root_ev = ev_make(tz_meta_tag(meta), t.eval[0]);
+    float* p = s_p[warp];
+    float v = visitations;
+    if (v < 0.0f) {
+        uint32_t mx = 0;
+        for (int i = lane; i < n; i += 32) mx = max(mx, t.visits[first + i]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, o));
+        v = (float)mx;
+    }
+    const float root_v = fsqrt(v);
+    const float root_q = ev_notnan(root_ev);
+    // ube: LAST child maximising -eval + std * beta
+    float best = 0.0f;
+    int best_i = -1;
+    for (int i = lane; i < n; i += 32) {
+        const uint32_t c = first + i;
+        const uint32_t cm = t.meta[c];
+        const Ev e = ev_make(tz_meta_tag(cm), t.eval[c]);
+        const bool needs_init = tz_meta_nchild(cm) == 0 && e.tag == TZ_E_VALUE;
+        const float sd = t.std_dev[c];
+        const float cq = needs_init ? root_q : ev_notnan(ev_negate(e));
+        // sigma_improve(q, std, 0.0, v) + logit
+        p[i] = fadd(fmul(fadd(cq, fmul(sd, 0.0f)), root_v), t.logit[c]);
+        const float key = fadd(ev_notnan(ev_negate(e)), fmul(sd, beta));
+        if (best_i < 0 || !(key < best)) {
+            best = key;
+            best_i = i;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ok = __shfl_xor_sync(FULL_MASK, best, o);
+        const int oi = __shfl_xor_sync(FULL_MASK, best_i, o);
+        if (oi >= 0 && (best_i < 0 || ok > best || (ok == best && oi > best_i))) {
+            best = ok;
+            best_i = oi;
+        }
+    }
+    __syncwarp();
+    if (!warp_softmax_inplace(p, n, lane)) flag_error(d, TZ_ERR_NAN, lane);
+    const int m = n < stride ? n : stride;
+    for (int i = lane; i < m; i += 32) {
+        out_policy[(size_t)g * stride + i] = p[i];
+        if (out_moves) out_moves[(size_t)g * stride + i] = (uint16_t)tz_meta_move(t.meta[first + i]);
+    }
+    if (lane == 0) {
+        out_n[g] = n;
+        float ube = 0.0f;
+        if (!ev_known(root_ev) && n > 0) {
+            const float sd = t.std_dev[first + best_i];
+            ube = fmul(sd, sd);
+        }
+        out_ube[g] = ube;
+    }
+}
+
+// select_best_action (node/mod.rs:132-163); returns the child index, -1 without children
+__device__ __forceinline__ int warp_select_best(const GameTree& t, int lane) {
+    const uint32_t meta = t.meta[0];
+    const int n = (int)tz_meta_nchild(meta);
+    const uint32_t first = t.first[0];
+    if (n == 0) return -1;
+    if (tz_meta_tag(meta) != TZ_E_VALUE) {
+        Ev m;
+        return warp_min_child(t, first, n, lane, &m);
+    }
+    // last maximum of visits, else last maximum of probability
+    uint32_t bv = 0;
+    int bvi = -1;
+    float bp = 0.0f;
+    int bpi = -1;
+    for (int i = lane; i < n; i += 32) {
+        const uint32_t vis = t.visits[first + i];
+        const float pr = t.prob[first + i];
+        if (bvi < 0 || vis >= bv) {
+            bv = vis;
+            bvi = i;
+        }
+        if (bpi < 0 || !(pr < bp)) {
+            bp = pr;
+            bpi = i;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t ov = __shfl_xor_sync(FULL_MASK, bv, o);
+        const int ovi = __shfl_xor_sync(FULL_MASK, bvi, o);
+        if (ovi >= 0 && (bvi < 0 || ov > bv || (ov == bv && ovi > bvi))) {
+            bv = ov;
+            bvi = ovi;
+        }
+        const float op = __shfl_xor_sync(FULL_MASK, bp, o);
+        const int opi = __shfl_xor_sync(FULL_MASK, bpi, o);
+        if (opi >= 0 && (bpi < 0 || op > bp || (op == bp && opi > bpi))) {
+            bp = op;
+            bpi = opi;
+        }
+    }
+    return bv == 0 ? bpi : bvi;
+}
+
+// select_best_actions / select_actions_in_selfplay (batched.rs:152-183, node/mod.rs:170-207).
+// `randoms` replaces the `rand` draw of choose_weighted: the sampled child is the first
+// whose cumulative weight exceeds randoms[g] % total (same rule as the oracle).
+__global__ void __launch_bounds__(32 * WPB) k_select_actions(TzDev d, int weighted_random_plies, uint32_t threshold,
+                                                             float allowed_drop, const unsigned long long* randoms,
+                                                             unsigned long long seed, unsigned long long counter,
+                                                             uint16_t* out_moves) {
+    __shared__ uint32_t s_w[WPB][TZ_MAX_MOVES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * WPB + warp;
+    if (g >= d.G) return;
+    const GameTree t = game_tree(d.arena, g);
+    const uint32_t meta = t.meta[0];
+    const int n = (int)tz_meta_nchild(meta);
+    const uint32_t first = t.first[0];
+    if (n == 0) {
+        if (!(tz_meta_tag(meta) != TZ_E_VALUE && t.eval[0] == 0)) flag_error(d, TZ_ERR_NO_CHILD, lane);
+        if (lane == 0) out_moves[g] = 0xffff;
+        return;
+    }
+    int pick = -1;
+    const bool sample = tz_meta_tag(meta) == TZ_E_VALUE && (int)d.env[g].ply < weighted_random_plies;
+    if (sample) {
+        Ev best_eval;
+        warp_min_child(t, first, n, lane, &best_eval);
+        Ev limit = best_eval;
+        if (limit.tag == TZ_E_VALUE) limit.bits = __float_as_uint(fadd(__uint_as_float(limit.bits), allowed_drop));
+        uint32_t* w = s_w[warp];
+        unsigned long long part = 0;
+        for (int i = lane; i < n; i += 32) {
+            const uint32_t c = first + i;
+            const Ev e = node_eval(t, c);
+            const uint32_t vis = t.visits[c];
+            const bool drop = vis < threshold || e.tag == TZ_E_WIN || ev_cmp(e, limit) > 0;
+            w[i] = drop ? 0u : vis;
+            part += w[i];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL_MASK, part, o);
+        __syncwarp();
+        if (part > 0) {
+            const unsigned long long r =
+                randoms ? randoms[g] : rng_hash(seed, (uint64_t)(d.game_base + g), counter, 0x5e1ecULL);
+            if (lane == 0) {
+                unsigned long long x = r % part;
+                for (int i = 0; i < n; i++) {
+                    if (w[i] == 0) continue;
+                    if (x < w[i]) {
+                        pick = i;
+                        break;
+                    }
+                    x -= w[i];
+                }
+            }
+            pick = __shfl_sync(FULL_MASK, pick, 0);
+        }
+    }
+    if (pick < 0) pick = warp_select_best(t, lane);
+    if (lane == 0) out_moves[g] = (uint16_t)tz_meta_move(t.meta[first + (uint32_t)pick]);
+}
+
+// ---- rules parity hooks --------------------------------------------------------------------
+
+__global__ void __launch_bounds__(32 * WPB) k_rules_probe(TzDev d, const TzState* states, int count, int stride,
+                                                          uint16_t* out_moves, int* out_n, int* out_terminal) {
+    __shared__ TzState s_state[WPB];
+    __shared__ uint16_t s_moves[WPB][TZ_MAX_MOVES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * WPB + warp;
+    if (i >= count) return;
+    TzState* st = &s_state[warp];
+    warp_load_state(st, &states[i], lane);
+    if (out_terminal) {
+        const int term = warp_terminal(st, d.n, d.half_komi, d.rev_limit, lane);
+        if (lane == 0) out_terminal[i] = term;
+    }
+    if (out_moves) {
+        const int cnt = warp_movegen(st, d.n, s_moves[warp], lane);
+        if (lane == 0) out_n[i] = cnt;
+        const int m = cnt < stride ? cnt : stride;
+        for (int j = lane; j < m; j += 32) out_moves[(size_t)i * stride + j] = s_moves[warp][j];
+    }
+}
+
+__global__ void __launch_bounds__(32 * WPB) k_apply_moves(TzDev d, TzState* states, const uint16_t* moves, int count,
+                                                          int* out_ok) {
+    __shared__ TzState s_state[WPB];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * WPB + warp;
+    if (i >= count) return;
+    TzState* st = &s_state[warp];
+    warp_load_state(st, &states[i], lane);
+    const bool ok = warp_apply(st, d.n, moves[i], lane);
+    warp_store_state(&states[i], st, lane);
+    if (lane == 0 && out_ok) out_ok[i] = ok ? 1 : 0;
+}
+
+// ---- launchers -------------------------------------------------------------------------------
+
+static inline int blocks_for(int items) { return (items + WPB - 1) / WPB; }
+
+void launch_select(const TzDev& d, int phase, int halving_i, const float* betas, cudaStream_t st) {
+    k_select<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, phase, halving_i, betas);
+}
+void launch_agent_synth(const TzDev& d, cudaStream_t st) { k_agent_synth<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d); }
+void launch_expand(const TzDev& d, cudaStream_t st) { k_expand<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d); }
+void launch_gumbel_noise(const TzDev& d, float* out, int stride, unsigned long long seed, unsigned long long counter,
+                         cudaStream_t st) {
+    const size_t total = (size_t)d.G * stride;
+    k_gumbel_noise<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d, out, stride, seed, counter);
+}
+void launch_gumbel_init(const TzDev& d, int k, const float* gumbel, int stride, cudaStream_t st) {
+    k_gumbel_init<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, k, gumbel, stride);
+}
+void launch_halve(const TzDev& d, const float* betas, float visits, int remaining, cudaStream_t st) {
+    k_halve<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, betas, visits, remaining);
+}
+void launch_finalize(const TzDev& d, uint16_t* out_moves, cudaStream_t st) {
+    k_finalize<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, out_moves);
+}
+void launch_step(const TzDev& d, const uint16_t* moves, cudaStream_t st) {
+    k_step<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, moves);
+}
+void launch_new_openings(const TzDev& d, const uint8_t* mask, const int* sym, const int* adj, unsigned long long seed,
+                         unsigned long long counter, cudaStream_t st) {
+    k_new_openings<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, mask, sym, adj, seed, counter);
+}
+void launch_set_positions(const TzDev& d, const TzState* states, const uint8_t* mask, cudaStream_t st) {
+    k_set_positions<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, states, mask);
+}
+void launch_reset_roots(const TzDev& d, const uint8_t* mask, cudaStream_t st) {
+    k_reset_roots<<<(d.G + 127) / 128, 128, 0, st>>>(d, mask);
+}
+void launch_restart(const TzDev& d, const int* sym, const int* adj, unsigned long long seed, unsigned long long counter,
+                    int* out_terminal, TzState* fin_start, uint16_t* fin_replay, int* fin_len, cudaStream_t st) {
+    k_restart<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, sym, adj, seed, counter, out_terminal, fin_start, fin_replay,
+                                                    fin_len);
+}
+void launch_root_table(const TzDev& d, int stride, int* out_n, uint16_t* moves, uint32_t* visits, uint32_t* eval_tag,
+                       uint32_t* eval_bits, float* logit, float* prob, float* std_dev, cudaStream_t st) {
+    k_root_table<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, stride, out_n, moves, visits, eval_tag, eval_bits, logit, prob,
+                                                       std_dev);
+}
+void launch_root_stats(const TzDev& d, uint32_t* out, cudaStream_t st) {
+    k_root_stats<<<(d.G + 127) / 128, 128, 0, st>>>(d, out);
+}
+void launch_targets(const TzDev& d, float visitations, float beta, int stride, float* out_policy, float* out_ube,
+                    int* out_n, uint16_t* out_moves, cudaStream_t st) {
+    k_targets<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, visitations, beta, stride, out_policy, out_ube, out_n, out_moves);
+}
+void launch_select_actions(const TzDev& d, int weighted_random_plies, uint32_t threshold, float allowed_drop,
+                           const unsigned long long* randoms, unsigned long long seed, unsigned long long counter,
+                           uint16_t* out_moves, cudaStream_t st) {
+    k_select_actions<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, weighted_random_plies, threshold, allowed_drop, randoms,
+                                                           seed, counter, out_moves);
+}
+void launch_rules_probe(const TzDev& d, const TzState* states, int count, int stride, uint16_t* out_moves, int* out_n,
+                        int* out_terminal, cudaStream_t st) {
+    k_rules_probe<<<blocks_for(count), 32 * WPB, 0, st>>>(d, states, count, stride, out_moves, out_n, out_terminal);
+}
+void launch_apply_moves(const TzDev& d, TzState* states, const uint16_t* moves, int count, int* out_ok,
+                        cudaStream_t st) {
+    k_apply_moves<<<blocks_for(count), 32 * WPB, 0, st>>>(d, states, moves, count, out_ok);
+}

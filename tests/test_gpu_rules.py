@@ -1,0 +1,83 @@
+"""GPU parity: Tak rules through the C ABI vs the CPU oracle, bit-exact.
+
+Reference boundary: fast-tak `Game::{possible_moves, play, result}` as called from
+takzero/src/search/env.rs:39-59."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from takzero_b200 import capi
+
+from helpers import games_to_states, random_playout_states, state_to_game, states_equal
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def handles():
+    hs = {}
+    for n, hk in ((3, 0), (4, 4), (5, 4), (6, 4)):
+        hs[n] = capi.BatchedMCTS(n, hk, 4, arena_slots=4096)
+    yield hs
+    for h in hs.values():
+        h.close()
+
+
+@pytest.mark.parametrize("n,half_komi,games", [(3, 0, 60), (4, 4, 60), (5, 4, 40), (6, 4, 40)])
+def test_rules_random_playouts(handles, n, half_komi, games):
+    h = handles[n]
+    positions = []
+    for seed in range(games):
+        positions += random_playout_states(n, half_komi, 10_000 * n + seed)
+    states = games_to_states(positions)
+    moves, counts = h.legal_moves(states)
+    terms = h.result(states)
+    n_terminal = 0
+    chosen = np.zeros(len(positions), dtype=np.uint16)
+    expect_next = []
+    rng = np.random.default_rng(n)
+    for i, g in enumerate(positions):
+        t = O.terminal(g)
+        assert terms[i] == t, f"terminal mismatch at {O.to_tps(g)}"
+        want = O.possible_moves(g)
+        assert counts[i] == len(want), f"move count mismatch at {O.to_tps(g)}"
+        assert list(moves[i, : counts[i]]) == want, f"move list/order mismatch at {O.to_tps(g)}"
+        n_terminal += t != O.T_NONE
+        m = want[int(rng.integers(len(want)))]
+        chosen[i] = m
+        g2 = g.copy()
+        O.play(g2, m)
+        expect_next.append(g2)
+    after, ok = h.apply(states, chosen)
+    assert ok.all()
+    expect = games_to_states(expect_next)
+    for i in range(len(positions)):
+        assert states_equal(after[i], expect[i]), f"apply mismatch at {O.to_tps(positions[i])} {O.move_str(int(chosen[i]))}"
+    assert n_terminal >= games // 2  # playouts really reach finished games (roads / flat wins)
+
+
+def test_rules_golden_position(handles):
+    """repr.rs:411-499: the 18 legal moves of `2,1,x/1S,221,x/x,2S,2 1 6` (3x3)."""
+    g = O.from_tps(3, 0, "2,1,x/1S,221,x/x,2S,2 1 6")
+    moves, counts = handles[3].legal_moves(games_to_states([g]))
+    assert counts[0] == 18
+    assert list(moves[0, :18]) == O.possible_moves(g)
+
+
+def test_rules_tinue_positions(handles):
+    """mcts.rs:345-411 positions: road detection after the winning replies."""
+    g = O.from_ptn_moves(3, 0, ["a3", "c1", "c2", "c3", "b3", "c3-", "b1"])
+    states = games_to_states([g])
+    assert handles[3].result(states)[0] == O.terminal(g)
+
+
+def test_empty_and_invalid(handles):
+    h = handles[4]
+    moves, counts = h.legal_moves(np.zeros(0, dtype=capi.STATE_DTYPE))
+    assert moves.shape[0] == 0 and counts.shape[0] == 0
+    g = O.new_game(4, 4)
+    st = games_to_states([g])
+    # a spread on ply 0 and a placement on an occupied square are rejected like Game::play
+    bad = np.array([O.parse_move("a1+")], dtype=np.uint16)
+    _, ok = h.apply(st, bad)
+    assert ok[0] == 0

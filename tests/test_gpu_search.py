@@ -1,0 +1,230 @@
+"""GPU parity: the batched search through the C ABI vs the CPU oracle, bit-exact.
+
+With identical agent outputs (the integer-hash synthetic agent on both sides, or the oracle's
+agents injected through the host callback) and identical injected Gumbel noise / openings,
+visit counts, evaluations (f32 bits), priors, selected moves, targets and replays must be
+identical to the restated reference (takzero/src/search/node/{mcts,batched,policy,mod}.rs)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from takzero_b200 import capi
+
+from helpers import (assert_roots_equal, games_to_states, host_agent_from_oracle, random_playout_states,
+                     states_equal)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _device_matching_math():
+    O.lib().tk_set_exact_math(1)
+    yield
+    O.lib().tk_set_exact_math(0)
+
+
+def make_pair(n, half_komi, G, seed, arena_slots=1 << 15, from_playouts=False):
+    rng = np.random.default_rng(seed)
+    if from_playouts:
+        games = []
+        while len(games) < G:
+            ps = [p for p in random_playout_states(n, half_komi, int(rng.integers(1 << 30)), keep_terminal=False)]
+            games.append(ps[int(rng.integers(len(ps)))])
+    else:
+        games = [O.new_opening(n, half_komi, int(rng.integers(8)), int(rng.integers(2))) for _ in range(G)]
+    ob = O.Batched(games)
+    m = capi.BatchedMCTS(n, half_komi, G, arena_slots=arena_slots)
+    m.set_positions(games_to_states(games))
+    return m, ob, rng
+
+
+@pytest.mark.parametrize("n,half_komi,G,sims", [(3, 0, 16, 300), (4, 4, 32, 120), (5, 4, 16, 80), (6, 4, 16, 60)])
+def test_simulate_synthetic(n, half_komi, G, sims):
+    m, ob, rng = make_pair(n, half_komi, G, 100 + n)
+    betas = rng.random(G).astype(np.float32) * 0.5
+    for s in range(sims):
+        m.simulate(betas)
+        ob.simulate("synthetic", betas)
+        if s in (0, 1, 5, sims // 2):
+            assert_roots_equal(m, ob, f"after sim {s}")
+    assert_roots_equal(m, ob, "final")
+    c, oc = m.counters(), ob.counters()
+    assert (c.simulations, c.evaluations, c.known) == (oc.simulations, oc.evaluations, oc.known)
+    m.close()
+
+
+@pytest.mark.parametrize("agent", ["simple", "dummy"])
+def test_simulate_injected_agent(agent):
+    """Reference agents `Dummy` / `Simple` (agent.rs:16-87) injected through the host callback."""
+    n, hk, G = 4, 4, 8
+    m, ob, rng = make_pair(n, hk, G, 7, from_playouts=True)
+    cb = host_agent_from_oracle(agent, n, hk)
+    m.set_agent(capi.AGENT_HOST, cb)
+    betas = np.zeros(G, dtype=np.float32)
+    for s in range(150):
+        m.simulate(betas)
+        ob.simulate(agent, betas)
+    assert_roots_equal(m, ob, agent)
+    m.close()
+
+
+def test_solver_finds_tinue():
+    """mcts.rs:345-376 `find_tinue_easy` on the GPU trees (Dummy agent, beta = 1... here 0)."""
+    g = O.from_ptn_moves(3, 0, ["a3", "c1", "c2", "c3", "b3", "c3-"])
+    G = 4
+    m = capi.BatchedMCTS(3, 0, G, arena_slots=1 << 16)
+    m.set_positions(games_to_states([g] * G))
+    m.set_agent(capi.AGENT_HOST, host_agent_from_oracle("dummy", 3, 0))
+    ob = O.Batched([g] * G)
+    betas = np.ones(G, dtype=np.float32)
+    solved = False
+    for s in range(5000):
+        m.simulate(betas)
+        ob.simulate("dummy", betas)
+        if s % 50 == 49:
+            st = m.root_stats()
+            if (st["eval_tag"] == capi.E_WIN).all():
+                solved = True
+                break
+    assert solved
+    assert_roots_equal(m, ob, "tinue")
+    tbl = m.root_children()
+    loss = [i for i in range(tbl["n"][0]) if tbl["eval_tag"][0, i] == capi.E_LOSS]
+    assert [O.move_str(int(tbl["moves"][0, i])) for i in loss] == ["b1"]
+    assert O.move_str(int(m.select_best_actions()[0])) == "b1"
+    m.close()
+
+
+def run_selfplay_pair(n, half_komi, G, k, budget, moves, seed, agent="synthetic"):
+    m, ob, rng = make_pair(n, half_komi, G, seed)
+    if agent != "synthetic":
+        m.set_agent(capi.AGENT_HOST, host_agent_from_oracle(agent, n, half_komi))
+    stride = m.move_stride
+    finished = 0
+    for mv in range(moves):
+        betas = (rng.random(G) < 0.5).astype(np.float32) * 0.25
+        gumbel = rng.gumbel(size=(G, stride)).astype(np.float32)
+        got = m.gumbel_sequential_halving(betas, k, budget, gumbel)
+        want = ob.gumbel_sequential_halving(agent, betas, k, budget, gumbel)
+        assert list(got) == want, f"move {mv}: selected actions"
+        assert_roots_equal(m, ob, f"move {mv} after search")
+        # targets (selfplay/src/main.rs:243-256): improved policy + ube target
+        vis = float((budget // int(np.log2(k)) // k) * (k - 1))
+        pol, ube, cnt = m.targets(vis, 0.25)
+        for g in range(G):
+            node = ob.node_ptr(g)
+            want_pol = O.improved_policy(node, vis)
+            assert cnt[g] == len(want_pol)
+            assert np.array_equal(pol[g, : cnt[g]].view(np.uint32), want_pol.view(np.uint32)), f"move {mv} game {g}: improved policy"
+            want_ube = O.lib().tk_node_ube_target(node, 0.25)
+            assert np.float32(ube[g]).view(np.uint32) == np.float32(want_ube).view(np.uint32)
+        # early plies: visit-weighted sampling with injected randomness (node/mod.rs:170-207)
+        randoms = rng.integers(0, 1 << 62, size=G, dtype=np.uint64)
+        sel = m.select_actions_in_selfplay(10, 8, 0.5, randoms)
+        for g in range(G):
+            env = ob.env(g)
+            w = O.lib().tk_node_select_selfplay_action(ob.node_ptr(g), int(env.ply < 10), 8, 0.5, int(randoms[g]))
+            assert sel[g] == w, f"move {mv} game {g}: selfplay action"
+        best = m.select_best_actions()
+        assert list(best) == ob.select_best_actions()
+        play = np.where(np.arange(G) % 2 == 0, got, sel).astype(np.uint16)
+        m.step(play)
+        ob.step([int(x) for x in play])
+        assert_roots_equal(m, ob, f"move {mv} after step")
+        sym = rng.integers(0, 8, size=G).astype(np.int32)
+        adj = rng.integers(0, 2, size=G).astype(np.int32)
+        term = m.restart_terminal_envs(sym, adj)
+        replays_before = [ob.replay(g) for g in range(G)]
+        want_term = ob.restart_terminal_envs([int(x) for x in sym], [int(x) for x in adj])
+        assert list(term) == want_term
+        for g in range(G):
+            if term[g] != capi.T_NONE:
+                finished += 1
+                _, mv_list = m.finished_replay(g)
+                assert list(mv_list) == replays_before[g]
+        pos = m.positions()
+        want_pos = games_to_states([ob.env(g) for g in range(G)])
+        for g in range(G):
+            assert states_equal(pos[g], want_pos[g]), f"move {mv} game {g}: env"
+            _, cur = m.replay(g)
+            assert list(cur) == ob.replay(g)
+    c, oc = m.counters(), ob.counters()
+    assert (c.simulations, c.evaluations, c.known) == (oc.simulations, oc.evaluations, oc.known)
+    m.close()
+    return finished
+
+
+def test_gumbel_selfplay_4x4():
+    finished = run_selfplay_pair(4, 4, 24, 16, 64, 40, seed=1)
+    assert finished > 0  # games ended and restarted inside the run
+
+
+def test_gumbel_selfplay_3x3_long():
+    finished = run_selfplay_pair(3, 0, 16, 4, 32, 40, seed=2)
+    assert finished > 4
+
+
+def test_gumbel_selfplay_5x5():
+    run_selfplay_pair(5, 4, 8, 16, 64, 6, seed=3)
+
+
+def test_gumbel_selfplay_6x6():
+    run_selfplay_pair(6, 4, 8, 16, 128, 4, seed=4)
+
+
+def test_gumbel_selfplay_simple_agent():
+    run_selfplay_pair(4, 4, 8, 8, 48, 12, seed=5, agent="simple")
+
+
+def test_device_gumbel_noise_is_reproducible_and_injectable():
+    """Library RNG mode: the noise it drew can be read back and injected into the oracle."""
+    n, hk, G = 4, 4, 16
+    m, ob, rng = make_pair(n, hk, G, 11)
+    betas = np.zeros(G, dtype=np.float32)
+    got = m.gumbel_sequential_halving(betas, 16, 64, None, seed=99)
+    noise = m.last_gumbel()
+    assert np.isfinite(noise).all() and noise.std() > 0.5
+    want = ob.gumbel_sequential_halving("synthetic", betas, 16, 64, noise)
+    assert list(got) == want
+    assert_roots_equal(m, ob, "device noise")
+    m.close()
+
+
+def test_sharded_equals_unsharded():
+    """Games are independent: two handles over halves of the batch == one handle."""
+    n, hk, G = 4, 4, 16
+    full = capi.BatchedMCTS(n, hk, G, arena_slots=1 << 14)
+    lo = capi.BatchedMCTS(n, hk, G // 2, game_base=0, arena_slots=1 << 14)
+    hi = capi.BatchedMCTS(n, hk, G // 2, game_base=G // 2, arena_slots=1 << 14)
+    for h in (full, lo, hi):
+        h.new_openings(seed=5)
+    moves_full = full.gumbel_sequential_halving(None, 8, 48, None, seed=7)
+    moves = np.concatenate([lo.gumbel_sequential_halving(None, 8, 48, None, seed=7),
+                            hi.gumbel_sequential_halving(None, 8, 48, None, seed=7)])
+    assert np.array_equal(moves_full, moves)
+    a = full.root_children()
+    b0, b1 = lo.root_children(), hi.root_children()
+    assert np.array_equal(a["visits"], np.concatenate([b0["visits"], b1["visits"]]))
+    for h in (full, lo, hi):
+        h.close()
+
+
+def test_argument_errors():
+    m = capi.BatchedMCTS(4, 4, 4, arena_slots=4096)
+    m.new_openings(seed=1)
+    with pytest.raises(capi.TakzeroError, match="multiple of k"):
+        m.gumbel_sequential_halving(None, 16, 100, None)  # batched.rs:216-220
+    with pytest.raises(capi.TakzeroError):
+        m.gumbel_sequential_halving(None, 0, 64, None)  # batched.rs:215
+    with pytest.raises(capi.TakzeroError, match="tz_set_weights"):
+        m.set_agent(capi.AGENT_NETWORK)
+    m.close()
+
+
+def test_arena_overflow_is_reported():
+    m = capi.BatchedMCTS(5, 4, 4, arena_slots=256)
+    m.new_openings(seed=1)
+    with pytest.raises(capi.TakzeroError, match="arena_full"):
+        for _ in range(20):
+            m.simulate(None)
+    m.close()
