@@ -99,6 +99,14 @@ enum {
     TZ_AGENT_NETWORK = 2,   /* the bf16 ResNet on the device (tz_set_weights first) */
 };
 
+/* One named f32 tensor of the network (host memory), see tz_set_weights. */
+typedef struct tz_tensor_t {
+    const char* name;
+    const float* data;
+    const int64_t* shape;
+    int ndim;
+} tz_tensor_t;
+
 typedef struct tz_counters_t {
     uint64_t simulations; /* calls of Node::forward */
     uint64_t evaluations; /* positions sent to the agent */
@@ -177,6 +185,26 @@ TZ_API int tz_select_best(tz_handle* h, tz_move_t* out_moves);
 TZ_API int tz_select_selfplay(tz_handle* h, int weighted_random_plies, uint32_t threshold, float allowed_eval_drop,
                        const uint64_t* randoms, uint64_t seed, tz_move_t* out_moves);
 TZ_API int tz_counters(tz_handle* h, tz_counters_t* out);
+
+/* ---- network (takzero/src/network/{net4_simhash,net5,net6_simhash,residual,repr}.rs) ----------- */
+/* Net::load (network/mod.rs:16-35): f32 tensors in PyTorch layout, named
+ *   core.input_conv2d.weight [256,C,3,3]; core.batch_norm.{weight,bias,running_mean,running_var} [256];
+ *   core.res_block_{b}.{0,1}.conv2d.weight [256,256,3,3]; core.res_block_{b}.{0,1}.batch_norm.* [256];
+ *   policy.conv2d.{weight [O,256,3,3], bias [O]}; {value,ube}.conv2d.{weight [1,256,1,1], bias [1]};
+ *   {value,ube}.linear.{weight [1,N*N], bias [1]}.
+ * The number of residual blocks is taken from the names (16 for net4/net6, 20 for net5).  BatchNorm is
+ * folded (eval mode, eps 1e-5) and the convolutions are converted to bf16 here. */
+TZ_API int tz_set_weights(tz_handle* h, const tz_tensor_t* tensors, int count);
+/* `impl Agent for Net`::policy_value_uncertainty (net6_simhash.rs:259-324) on host buffers:
+ * count <= n_games positions, actions [count][stride] -> logits [count][stride], values, variances */
+TZ_API int tz_evaluate(tz_handle* h, const tz_state_t* states, int count, const tz_move_t* actions,
+                const int* n_actions, int stride, float* logits, float* values, float* variances);
+/* game_repr (repr.rs:169-228): f32 planes [count][C][N][N] */
+TZ_API int tz_encode_planes(tz_handle* h, const tz_state_t* states, int count, float* out);
+/* test hooks: stop the tower after `limit` convolutions (-1 = full network); read back an activation
+ * buffer (0 block stream, 1 block middle, 2 input planes) of the last tz_evaluate as f32 [count][N*N][ch] */
+TZ_API int tz_debug_layer_limit(tz_handle* h, int limit);
+TZ_API int tz_debug_activations(tz_handle* h, int which, int count, float* out);
 
 #ifdef __cplusplus
 }

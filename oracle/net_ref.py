@@ -1,0 +1,133 @@
+"""CPU ORACLE (test infrastructure, NOT product code): f32 PyTorch restatement of the reference
+network, used to check the CUDA network and as the forward pass of the restated CPU baseline.
+
+Follows takzero/src/network/net6_simhash.rs:43-119,194-201,259-324 (net4_simhash.rs is the same
+with N = 4; net5.rs:45 has 20 residual blocks) and residual.rs:13-63.  The reference builds these
+layers through tch/libtorch, i.e. the same ATen kernels this file calls; the reference's tests pin
+shapes only (net6_simhash.rs:340-367), so numerical parity of the network is "unpinned" and this
+restatement is the de-facto oracle.  The SimHash set of a freshly initialised reference network is
+empty, so `forward_hash` returns MAXIMUM_VARIANCE = 4.0 for every position (:243-256)."""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import oracle as O
+
+FILTERS = 256
+MAXIMUM_VARIANCE = 4.0
+
+
+def res_blocks_for(n: int) -> int:
+    return 20 if n == 5 else 16
+
+
+class SmallBlock(nn.Module):  # residual.rs:13-43
+    def __init__(self, cin: int, cout: int):
+        super().__init__()
+        self.conv2d = nn.Conv2d(cin, cout, 3, stride=1, padding=1, bias=False)
+        self.batch_norm = nn.BatchNorm2d(cout, eps=1e-5, momentum=0.1)
+
+    def forward(self, x):
+        return self.batch_norm(self.conv2d(x))
+
+
+class ResidualBlock(nn.Sequential):  # residual.rs:45-63
+    def __init__(self, channels: int):
+        super().__init__(SmallBlock(channels, channels), SmallBlock(channels, channels))
+
+    def forward(self, x):
+        return torch.relu(self[1](torch.relu(self[0](x))) + x)
+
+
+class Core(nn.Module):  # net6_simhash.rs:43-72
+    def __init__(self, cin: int, blocks: int):
+        super().__init__()
+        self.input_conv2d = nn.Conv2d(cin, FILTERS, 3, stride=1, padding=1, bias=False)
+        self.batch_norm = nn.BatchNorm2d(FILTERS, eps=1e-5, momentum=0.1)
+        for b in range(blocks):
+            self.add_module(f"res_block_{b}", ResidualBlock(FILTERS))
+        self.blocks = blocks
+
+    def forward(self, x):
+        x = torch.relu(self.batch_norm(self.input_conv2d(x)))
+        for b in range(self.blocks):
+            x = getattr(self, f"res_block_{b}")(x)
+        return x
+
+
+class Head(nn.Module):  # value_net / ube_net, net6_simhash.rs:88-119
+    def __init__(self, n: int, tanh: bool):
+        super().__init__()
+        self.conv2d = nn.Conv2d(FILTERS, 1, 1, stride=1)
+        self.linear = nn.Linear(n * n, 1)
+        self.n, self.tanh = n, tanh
+
+    def forward(self, x):
+        y = self.linear(torch.relu(self.conv2d(x)).view(-1, self.n * self.n))
+        return torch.tanh(y) if self.tanh else y
+
+
+class Policy(nn.Module):  # net6_simhash.rs:74-86
+    def __init__(self, cout: int):
+        super().__init__()
+        self.conv2d = nn.Conv2d(FILTERS, cout, 3, stride=1, padding=1)
+
+    def forward(self, x):
+        return self.conv2d(x)
+
+
+class Net(nn.Module):
+    def __init__(self, n: int, seed: int = 123, blocks: int | None = None, randomize_bn: bool = False):
+        super().__init__()
+        torch.manual_seed(seed)
+        L = O.lib()
+        self.n = n
+        self.cin = L.tk_input_channels(n)
+        self.cout = L.tk_output_channels(n)
+        self.core = Core(self.cin, blocks if blocks is not None else res_blocks_for(n))
+        self.policy = Policy(self.cout)
+        self.value = Head(n, True)
+        self.ube = Head(n, False)
+        if randomize_bn:  # exercise the BN folding with non-trivial statistics
+            g = torch.Generator().manual_seed(seed + 1)
+            for m in self.modules():
+                if isinstance(m, nn.BatchNorm2d):
+                    m.weight.data = 0.5 + torch.rand(m.weight.shape, generator=g)
+                    m.bias.data = 0.2 * torch.randn(m.bias.shape, generator=g)
+                    m.running_mean.data = 0.2 * torch.randn(m.running_mean.shape, generator=g)
+                    m.running_var.data = 0.5 + torch.rand(m.running_var.shape, generator=g)
+        self.eval()
+
+    @torch.no_grad()
+    def forward(self, xs):  # forward_t(xs, false), net6_simhash.rs:194-201
+        core = self.core(xs)
+        return self.policy(core), self.value(core), self.ube(core)
+
+    def tensors(self) -> Dict[str, np.ndarray]:
+        """Named f32 tensors in the layout tz_set_weights documents."""
+        return {k: v.detach().cpu().numpy().astype(np.float32).copy() for k, v in self.state_dict().items()
+                if not k.endswith("num_batches_tracked")}
+
+    @torch.no_grad()
+    def policy_value_uncertainty(self, envs: Sequence[O.Game], actions: Sequence[Sequence[int]]):
+        """`impl Agent for Net` (net6_simhash.rs:259-324): per position (logits of the legal moves, value,
+        variance)."""
+        n = self.n
+        xs = torch.from_numpy(np.stack([O.game_repr(g).reshape(self.cin, n, n) for g in envs]))
+        policy, values, ube = self.forward(xs)
+        policy = policy.reshape(len(envs), -1)
+        out_logits: List[np.ndarray] = []
+        for i, acts in enumerate(actions):
+            idx = torch.tensor([O.move_index(n, a) for a in acts], dtype=torch.long)
+            out_logits.append(policy[i, idx].numpy().astype(np.float32))
+        local = torch.full((len(envs),), MAXIMUM_VARIANCE)
+        unc = torch.clamp(torch.maximum(torch.exp(ube.view(-1)), local), 0.0, MAXIMUM_VARIANCE)
+        return out_logits, values.view(-1).numpy().astype(np.float32), unc.numpy().astype(np.float32)
+
+    def as_oracle_agent(self):
+        """Adapter to oracle.py_agent: (envs, actions) -> (logits, values, variances)."""
+        return O.py_agent(lambda envs, acts: self.policy_value_uncertainty(envs, acts))

@@ -713,3 +713,95 @@ extern "C" TZ_API int tz_counters(tz_handle* h, tz_counters_t* out) {
     }
     return TZ_OK;
 }
+
+// ---- network ----------------------------------------------------------------------------------------
+
+extern "C" TZ_API int tz_set_weights(tz_handle* h, const tz_tensor_t* tensors, int count) {
+    CHECK_H(h);
+    if (!tensors || count <= 0) return fail(TZ_EINVAL, "no tensors");
+    std::vector<const char*> names(count);
+    std::vector<const float*> data(count);
+    std::vector<std::vector<long long>> shapes(count);
+    std::vector<const long long*> shape_ptrs(count);
+    std::vector<int> ndims(count);
+    for (int i = 0; i < count; i++) {
+        if (!tensors[i].name || !tensors[i].data || tensors[i].ndim < 0 || tensors[i].ndim > 4)
+            return fail(TZ_EINVAL, "bad tensor %d", i);
+        names[i] = tensors[i].name;
+        data[i] = tensors[i].data;
+        for (int k = 0; k < tensors[i].ndim; k++) shapes[i].push_back((long long)tensors[i].shape[k]);
+        shape_ptrs[i] = shapes[i].data();
+        ndims[i] = tensors[i].ndim;
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    const int rc = nn_set_weights(h, names.data(), data.data(), shape_ptrs.data(), ndims.data(), count);
+    if (rc) return fail(rc, "tz_set_weights: %s", nn_last_error());
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_evaluate(tz_handle* h, const tz_state_t* states, int count, const tz_move_t* actions,
+                                  const int* n_actions, int stride, float* logits, float* values, float* variances) {
+    CHECK_H(h);
+    const TzDev& d = h->d;
+    if (!nn_ready(h)) return fail(TZ_ENOWEIGHTS, "tz_evaluate needs tz_set_weights first");
+    if (!states || !actions || !n_actions || !logits || !values || !variances) return fail(TZ_EINVAL, "null argument");
+    if (count <= 0 || count > d.G) return fail(TZ_EINVAL, "count must be 1..n_games");
+    if (stride != d.M) return fail(TZ_EINVAL, "stride must equal move_stride (%d)", d.M);
+    for (int i = 0; i < count; i++)
+        if (n_actions[i] < 0 || n_actions[i] > stride) return fail(TZ_EINVAL, "bad n_actions[%d]", i);
+    const size_t c = (size_t)count;
+    CU(cudaMemcpyAsync(d.leaf_state, states, c * sizeof(TzState), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d.actions, actions, c * d.M * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d.n_actions, n_actions, c * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    const int rc = nn_forward(h, d.leaf_state, nullptr, count, d.actions, d.n_actions, d.logits, d.value, d.variance);
+    if (rc) return fail(rc, "network forward failed: %s", cudaGetErrorString(cudaGetLastError()));
+    CU(cudaMemcpyAsync(logits, d.logits, c * d.M * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(values, d.value, c * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(variances, d.variance, c * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_encode_planes(tz_handle* h, const tz_state_t* states, int count, float* out) {
+    CHECK_H(h);
+    if (!states || !out || count < 0) return fail(TZ_EINVAL, "bad argument");
+    if (count == 0) return TZ_OK;
+    const int n = h->d.n, C = 2 * (2 * n + 3 + 2) + 2;
+    Scratch s;
+    TzState* ds;
+    float* dout;
+    CU(s.get(&ds, (size_t)count));
+    CU(s.get(&dout, (size_t)count * C * n * n));
+    CU(cudaMemcpyAsync(ds, states, (size_t)count * sizeof(TzState), cudaMemcpyHostToDevice, h->stream));
+    const int rc = nn_encode_planes(h, ds, count, dout);
+    if (rc) return fail(rc, "encode failed");
+    CU(cudaMemcpyAsync(out, dout, (size_t)count * C * n * n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_debug_layer_limit(tz_handle* h, int limit) {
+    CHECK_H(h);
+    if (!nn_ready(h)) return fail(TZ_ENOWEIGHTS, "no weights");
+    nn_set_layer_limit(h, limit);
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_debug_activations(tz_handle* h, int which, int count, float* out) {
+    CHECK_H(h);
+    if (!nn_ready(h)) return fail(TZ_ENOWEIGHTS, "no weights");
+    if (which < 0 || which > 2 || count <= 0 || count > h->d.G || !out) return fail(TZ_EINVAL, "bad argument");
+    const int n = h->d.n, ch = which == 2 ? 64 : 256;
+    const size_t total = (size_t)count * n * n * ch;
+    Scratch s;
+    float* dout;
+    CU(s.get(&dout, total));
+    const int rc = nn_debug_read(h, which, count, dout);
+    if (rc) return fail(rc, "debug read failed");
+    CU(cudaMemcpyAsync(out, dout, total * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return TZ_OK;
+}

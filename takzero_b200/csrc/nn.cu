@@ -1,4 +1,495 @@
+// nn.cu -- the policy / value / uncertainty ResNet of the reference as a device agent.
+//
+// Replaces `impl Agent<Env> for Net` (takzero/src/network/net6_simhash.rs:259-324 and its
+// N = 4 / N = 5 siblings): board -> input planes (network/repr.rs:169-228) -> conv tower
+// (net6_simhash.rs:43-72, residual.rs) -> policy conv + legal-logit gather (:74-86,277-306),
+// value / UBE heads (:88-119) and the uncertainty combine (:309-317), without libtorch.
+// The 3x3 convolutions run on tcgen05 (conv_tcgen05.cuh); everything else here is small.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "conv_tcgen05.cuh"
 #include "nn.cuh"
+#include "rules.cuh"
+
+#define WPB TZ_WARPS_PER_BLOCK
+#define FILTERS 256
+#define CIN_PAD 64
+
+struct ConvLayer {
+    __nv_bfloat16* w = nullptr;  // pre-arranged blocks
+    float* bias = nullptr;
+    int cin = 0;
+};
+
+struct NnState {
+    int n = 0, blocks = 0;
+    int in_channels = 0, out_channels = 0;
+    int max_positions = 0;
+    size_t rows = 0;  // rows of the activation buffers
+    ConvLayer input, policy;
+    std::vector<ConvLayer> tower;  // 2 per residual block
+    float* head_w = nullptr;       // [2][256] conv1x1 weights (value, ube)
+    float* head_misc = nullptr;    // [2] conv bias, [2][36] linear weights, [2] linear bias
+    __nv_bfloat16* planes = nullptr;  // [rows][64]
+    __nv_bfloat16* act_x = nullptr;   // [rows][256]
+    __nv_bfloat16* act_t = nullptr;   // [rows][256]
+    float* logits_full = nullptr;     // [max_positions * n*n][256]
+    int layer_limit = -1;             // debug: stop the tower after this many convolutions
+    std::vector<void*> allocs;
+    int sm_count = 148;
+};
+
 bool nn_ready(const tz_handle* h) { return h->nn != nullptr; }
-void nn_free(tz_handle*) {}
-int nn_forward_queue(tz_handle*) { return TZ_ENOWEIGHTS; }
+
+void nn_free(tz_handle* h) {
+    if (!h->nn) return;
+    for (void* p : h->nn->allocs) cudaFree(p);
+    delete h->nn;
+    h->nn = nullptr;
+}
+
+// ---- input planes (network/repr.rs:169-228) ----------------------------------------------------
+
+// One warp per position.  out_f32: [count][C][N][N] exactly like `game_repr` (parity hook);
+// out_bf16: padded-row layout [rows][64] feeding the first convolution.
+__global__ void __launch_bounds__(32 * WPB) k_encode(const TzState* states, const int* count_ptr, int count_max, int n,
+                                                      int half_komi, float* out_f32, __nv_bfloat16* out_bf16,
+                                                      int guard) {
+    __shared__ TzState s_state[WPB];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * WPB + warp;
+    const int count = count_ptr ? *count_ptr : count_max;
+    if (q >= count) return;
+    TzState* st = &s_state[warp];
+    warp_load_state(st, &states[q], lane);
+    const int nn = n * n, ss = 2 * n + 3, C = 2 * (ss + 2) + 2, w1 = n + 1;
+    const int me = st->to_move, other = me ^ 1;
+    const TzBoards b = warp_boards(st, nn, lane);
+    const int s0 = n == 3 ? 10 : n == 4 ? 15 : n == 5 ? 21 : 30;
+    const int c0 = n >= 5 ? 1 : 0;
+    const float my_stones = __fdiv_rn((float)st->stones[me], (float)s0);
+    const float my_caps = c0 ? __fdiv_rn((float)st->caps[me], (float)c0) : 0.0f;
+    const float op_stones = __fdiv_rn((float)st->stones[other], (float)s0);
+    const float op_caps = c0 ? __fdiv_rn((float)st->caps[other], (float)c0) : 0.0f;
+    const float fcd = __fsub_rn((float)(__popcll(b.flat[0]) - __popcll(b.flat[1])), __fdiv_rn((float)half_komi, 2.0f));
+    const float fcd_sq = __fdiv_rn(fcd, (float)nn);
+    const float side = me == 1 ? 1.0f : 0.0f;
+    for (int sq = lane; sq < nn; sq += 32) {
+        float v[CIN_PAD];
+#pragma unroll
+        for (int c = 0; c < CIN_PAD; c++) v[c] = 0.0f;
+        const int h = st->height[sq];
+        if (h > 0) {
+            const uint64_t stack = st->stack[sq];
+            const int top_col = (int)((stack >> (h - 1)) & 1ull);
+            v[st->top[sq] + (top_col != me ? ss : 0)] = 1.0f;
+            for (int i = 0; i < ss - 3 && h - 2 - i >= 0; i++) {
+                const int col = (int)((stack >> (h - 2 - i)) & 1ull);
+                v[3 + i + (col != me ? ss : 0)] = 1.0f;
+            }
+        }
+        const int base = 2 * ss;
+        v[base] = my_stones;
+        v[base + 1] = my_caps;
+        v[base + 2] = op_stones;
+        v[base + 3] = op_caps;
+        v[base + 4] = side;
+        v[base + 5] = fcd_sq;
+        if (out_f32) {
+            float* o = out_f32 + (size_t)q * C * nn + sq;
+            for (int c = 0; c < C; c++) o[(size_t)c * nn] = v[c];
+        }
+        if (out_bf16) {
+            const int row = sq / n, col = sq % n;
+            const size_t r = (size_t)guard + (size_t)q * (w1 * w1) + (size_t)(row + 1) * w1 + col;
+            uint4* o = reinterpret_cast<uint4*>(out_bf16 + r * CIN_PAD);
+#pragma unroll
+            for (int j = 0; j < CIN_PAD / 8; j++)
+                o[j] = make_uint4(conv::pack_bf16(v[j * 8], v[j * 8 + 1]), conv::pack_bf16(v[j * 8 + 2], v[j * 8 + 3]),
+                                  conv::pack_bf16(v[j * 8 + 4], v[j * 8 + 5]), conv::pack_bf16(v[j * 8 + 6], v[j * 8 + 7]));
+        }
+    }
+}
+
+// ---- heads + legal-logit gather ------------------------------------------------------------------
+
+// network/repr.rs:49-71 `move_index` split into (channel, square)
+__device__ __forceinline__ int move_channel(int n, uint16_t m) {
+    const int kind = (m >> 6) & 3, pat = m >> 8;
+    if (pat == 0) return kind;  // flat 0, wall 1, cap 2
+    const int dir_off = kind == 0 ? 0 : kind == 1 ? 2 : kind == 2 ? 3 : 1;  // Up, Right, Down, Left order of repr.rs:61-66
+    return 3 + ((pat >> (8 - n)) - 1) + ((1 << n) - 2) * dir_off;
+}
+
+// One warp per position: value head (conv1x1 + ReLU + Linear + tanh), UBE head (same, no tanh),
+// uncertainty = clamp(max(exp(ube), local), 0, 4) with local = 4.0 (empty SimHash set, i.e. a
+// freshly initialised reference network), and logits[i] = policy[move_index(action_i)].
+__global__ void __launch_bounds__(32 * WPB) k_heads_gather(const __nv_bfloat16* act, const float* logits_full,
+                                                            const float* head_w, const float* head_misc,
+                                                            const uint16_t* actions, const int* n_actions,
+                                                            const int* count_ptr, int count_max, int n, int M, int guard,
+                                                            float* out_logits, float* out_value, float* out_variance) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * WPB + warp;
+    const int count = count_ptr ? *count_ptr : count_max;
+    if (q >= count) return;
+    const int nn = n * n, w1 = n + 1;
+    // lane owns channels lane*8 .. lane*8+7
+    float wv[8], wu[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        wv[j] = head_w[lane * 8 + j];
+        wu[j] = head_w[FILTERS + lane * 8 + j];
+    }
+    const float bv = head_misc[0], bu = head_misc[1];
+    const float* lin_v = head_misc + 2;
+    const float* lin_u = head_misc + 2 + 36;
+    float acc_v = 0.0f, acc_u = 0.0f;
+    for (int sq = 0; sq < nn; sq++) {
+        const int row = sq / n, col = sq % n;
+        const size_t r = (size_t)guard + (size_t)q * (w1 * w1) + (size_t)(row + 1) * w1 + col;
+        const uint4 x = *reinterpret_cast<const uint4*>(act + r * FILTERS + lane * 8);
+        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+        float dv = 0.0f, du = 0.0f;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
+            dv += lo * wv[e * 2] + hi * wv[e * 2 + 1];
+            du += lo * wu[e * 2] + hi * wu[e * 2 + 1];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            dv += __shfl_xor_sync(0xffffffffu, dv, o);
+            du += __shfl_xor_sync(0xffffffffu, du, o);
+        }
+        acc_v += fmaxf(dv + bv, 0.0f) * lin_v[sq];
+        acc_u += fmaxf(du + bu, 0.0f) * lin_u[sq];
+    }
+    if (lane == 0) {
+        out_value[q] = tanhf(acc_v + head_misc[2 + 72]);
+        const float ube = acc_u + head_misc[2 + 73];
+        const float local = 4.0f;  // MAXIMUM_VARIANCE when the SimHash bit is not set
+        out_variance[q] = fminf(fmaxf(fmaxf(expf(ube), local), 0.0f), 4.0f);
+    }
+    const int cnt = n_actions[q];
+    const uint16_t* a = actions + (size_t)q * M;
+    const float* lf = logits_full + (size_t)q * nn * FILTERS;
+    for (int i = lane; i < cnt; i += 32) {
+        const uint16_t m = a[i];
+        const int sq = ((m >> 3) & 7) * n + (m & 7);
+        out_logits[(size_t)q * M + i] = lf[(size_t)sq * FILTERS + move_channel(n, m)];
+    }
+}
+
+// ---- weights ------------------------------------------------------------------------------------------
+
+struct HostTensor {
+    std::string name;
+    const float* data;
+    std::vector<long long> shape;
+    size_t numel() const {
+        size_t k = 1;
+        for (long long s : shape) k *= (size_t)s;
+        return k;
+    }
+};
+
+static const HostTensor* find(const std::vector<HostTensor>& ts, const std::string& name) {
+    for (const HostTensor& t : ts)
+        if (t.name == name) return &t;
+    return nullptr;
+}
+
+static uint16_t f32_to_bf16(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+// conv [cout][cin][3][3] (+ BN, folded) -> bf16 blocks [cin_pad/64][9][8][256][8] + f32 bias[256]
+static int upload_conv(NnState* s, ConvLayer* L, const HostTensor* w, const HostTensor* conv_bias, const HostTensor* bn_w,
+                       const HostTensor* bn_b, const HostTensor* bn_m, const HostTensor* bn_v, int cin_pad) {
+    const int cout = (int)w->shape[0], cin = (int)w->shape[1];
+    if (cout > FILTERS || cin > cin_pad || w->shape[2] != 3 || w->shape[3] != 3) return TZ_EINVAL;
+    std::vector<float> scale(cout, 1.0f), bias(FILTERS, 0.0f);
+    for (int co = 0; co < cout; co++) {
+        if (bn_w) {
+            const float inv = 1.0f / sqrtf(bn_v->data[co] + 1e-5f);  // tch BatchNormConfig::default eps
+            scale[co] = bn_w->data[co] * inv;
+            bias[co] = bn_b->data[co] - bn_m->data[co] * scale[co];
+        }
+        if (conv_bias) bias[co] += conv_bias->data[co] * scale[co];
+    }
+    const int kblocks = cin_pad / 64;
+    std::vector<uint16_t> blk((size_t)kblocks * 9 * 8 * 256 * 8, 0);
+    for (int co = 0; co < cout; co++)
+        for (int ci = 0; ci < cin; ci++)
+            for (int tap = 0; tap < 9; tap++) {
+                const float v = w->data[((size_t)co * cin + ci) * 9 + tap] * scale[co];
+                const int kb = ci / 64, kc = (ci % 64) / 8, e = ci % 8;
+                blk[((((size_t)kb * 9 + tap) * 8 + kc) * 256 + co) * 8 + e] = f32_to_bf16(v);
+            }
+    void* dw = nullptr;
+    void* db = nullptr;
+    if (cudaMalloc(&dw, blk.size() * 2) != cudaSuccess) return TZ_ENOMEM;
+    s->allocs.push_back(dw);
+    if (cudaMalloc(&db, FILTERS * sizeof(float)) != cudaSuccess) return TZ_ENOMEM;
+    s->allocs.push_back(db);
+    if (cudaMemcpy(dw, blk.data(), blk.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) return TZ_ECUDA;
+    if (cudaMemcpy(db, bias.data(), FILTERS * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return TZ_ECUDA;
+    L->w = (__nv_bfloat16*)dw;
+    L->bias = (float*)db;
+    L->cin = cin_pad;
+    return TZ_OK;
+}
+
+static thread_local char g_nn_err[256] = "";
+const char* nn_last_error() { return g_nn_err; }
+#define NN_FAIL(code, ...)                              \
+    do {                                                \
+        snprintf(g_nn_err, sizeof(g_nn_err), __VA_ARGS__); \
+        return code;                                    \
+    } while (0)
+
+int nn_set_weights(tz_handle* h, const char* const* names, const float* const* data, const long long* const* shapes,
+                   const int* ndims, int count) {
+    cudaSetDevice(h->device);
+    std::vector<HostTensor> ts;
+    for (int i = 0; i < count; i++) {
+        HostTensor t;
+        t.name = names[i];
+        t.data = data[i];
+        t.shape.assign(shapes[i], shapes[i] + ndims[i]);
+        ts.push_back(t);
+    }
+    nn_free(h);
+    NnState* s = new NnState();
+    h->nn = s;
+    const int n = h->d.n, nn = n * n;
+    s->n = n;
+    s->in_channels = 2 * (2 * n + 3 + 2) + 2;
+    s->out_channels = 3 + 4 * ((1 << n) - 2);
+    cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, h->device);
+    auto need = [&](const std::string& name, std::vector<long long> shape) -> const HostTensor* {
+        const HostTensor* t = find(ts, name);
+        if (!t) {
+            snprintf(g_nn_err, sizeof(g_nn_err), "missing tensor %s", name.c_str());
+            return nullptr;
+        }
+        if (t->shape != shape) {
+            snprintf(g_nn_err, sizeof(g_nn_err), "tensor %s has the wrong shape", name.c_str());
+            return nullptr;
+        }
+        return t;
+    };
+    int rc;
+#define NEED(var, name, ...)                                  \
+    const HostTensor* var = need(name, std::vector<long long>{__VA_ARGS__}); \
+    if (!var) {                                               \
+        nn_free(h);                                           \
+        return TZ_EINVAL;                                     \
+    }
+    {
+        NEED(w, "core.input_conv2d.weight", FILTERS, s->in_channels, 3, 3);
+        NEED(bw, "core.batch_norm.weight", FILTERS);
+        NEED(bb, "core.batch_norm.bias", FILTERS);
+        NEED(bm, "core.batch_norm.running_mean", FILTERS);
+        NEED(bv, "core.batch_norm.running_var", FILTERS);
+        if ((rc = upload_conv(s, &s->input, w, nullptr, bw, bb, bm, bv, CIN_PAD)) != TZ_OK) {
+            nn_free(h);
+            NN_FAIL(rc, "input conv upload failed");
+        }
+    }
+    int blocks = 0;
+    while (find(ts, "core.res_block_" + std::to_string(blocks) + ".0.conv2d.weight")) blocks++;
+    if (blocks == 0) {
+        nn_free(h);
+        NN_FAIL(TZ_EINVAL, "no residual blocks (core.res_block_0.0.conv2d.weight) found");
+    }
+    s->blocks = blocks;
+    for (int b = 0; b < blocks; b++)
+        for (int j = 0; j < 2; j++) {
+            const std::string p = "core.res_block_" + std::to_string(b) + "." + std::to_string(j);
+            NEED(w, p + ".conv2d.weight", FILTERS, FILTERS, 3, 3);
+            NEED(bw, p + ".batch_norm.weight", FILTERS);
+            NEED(bb, p + ".batch_norm.bias", FILTERS);
+            NEED(bm, p + ".batch_norm.running_mean", FILTERS);
+            NEED(bv, p + ".batch_norm.running_var", FILTERS);
+            ConvLayer L;
+            if ((rc = upload_conv(s, &L, w, nullptr, bw, bb, bm, bv, FILTERS)) != TZ_OK) {
+                nn_free(h);
+                NN_FAIL(rc, "tower conv upload failed");
+            }
+            s->tower.push_back(L);
+        }
+    {
+        NEED(w, "policy.conv2d.weight", s->out_channels, FILTERS, 3, 3);
+        NEED(b, "policy.conv2d.bias", s->out_channels);
+        if ((rc = upload_conv(s, &s->policy, w, b, nullptr, nullptr, nullptr, nullptr, FILTERS)) != TZ_OK) {
+            nn_free(h);
+            NN_FAIL(rc, "policy conv upload failed");
+        }
+    }
+    {
+        NEED(vw, "value.conv2d.weight", 1, FILTERS, 1, 1);
+        NEED(vb, "value.conv2d.bias", 1);
+        NEED(vlw, "value.linear.weight", 1, nn);
+        NEED(vlb, "value.linear.bias", 1);
+        NEED(uw, "ube.conv2d.weight", 1, FILTERS, 1, 1);
+        NEED(ub, "ube.conv2d.bias", 1);
+        NEED(ulw, "ube.linear.weight", 1, nn);
+        NEED(ulb, "ube.linear.bias", 1);
+        std::vector<float> hw(2 * FILTERS), misc(2 + 72 + 2, 0.0f);
+        memcpy(hw.data(), vw->data, FILTERS * 4);
+        memcpy(hw.data() + FILTERS, uw->data, FILTERS * 4);
+        misc[0] = vb->data[0];
+        misc[1] = ub->data[0];
+        memcpy(misc.data() + 2, vlw->data, nn * 4);
+        memcpy(misc.data() + 2 + 36, ulw->data, nn * 4);
+        misc[2 + 72] = vlb->data[0];
+        misc[2 + 73] = ulb->data[0];
+        void *d1 = nullptr, *d2 = nullptr;
+        if (cudaMalloc(&d1, hw.size() * 4) != cudaSuccess || cudaMalloc(&d2, misc.size() * 4) != cudaSuccess) {
+            nn_free(h);
+            NN_FAIL(TZ_ENOMEM, "cudaMalloc heads");
+        }
+        s->allocs.push_back(d1);
+        s->allocs.push_back(d2);
+        cudaMemcpy(d1, hw.data(), hw.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(d2, misc.data(), misc.size() * 4, cudaMemcpyHostToDevice);
+        s->head_w = (float*)d1;
+        s->head_misc = (float*)d2;
+    }
+#undef NEED
+    // activation buffers: guard rows + all boards, rounded up to whole tiles, + halo
+    const int w1 = n + 1;
+    s->max_positions = h->d.G;
+    const size_t used = (size_t)s->max_positions * w1 * w1;
+    s->rows = conv::HALO + ((used + conv::TILE_M - 1) / conv::TILE_M) * conv::TILE_M + 2 * conv::HALO;
+    auto dalloc = [&](void** p, size_t bytes) -> bool {
+        if (cudaMalloc(p, bytes) != cudaSuccess) return false;
+        s->allocs.push_back(*p);
+        return cudaMemset(*p, 0, bytes) == cudaSuccess;
+    };
+    if (!dalloc((void**)&s->planes, s->rows * CIN_PAD * 2) || !dalloc((void**)&s->act_x, s->rows * FILTERS * 2) ||
+        !dalloc((void**)&s->act_t, s->rows * FILTERS * 2) ||
+        !dalloc((void**)&s->logits_full, (size_t)s->max_positions * nn * FILTERS * 4)) {
+        nn_free(h);
+        NN_FAIL(TZ_ENOMEM, "cudaMalloc activations");
+    }
+    if (cudaFuncSetAttribute(conv::k_conv3x3, cudaFuncAttributeMaxDynamicSharedMemorySize, conv::SMEM_BYTES) !=
+        cudaSuccess) {
+        nn_free(h);
+        NN_FAIL(TZ_ECUDA, "cudaFuncSetAttribute(k_conv3x3, %d B smem) failed", conv::SMEM_BYTES);
+    }
+    cudaDeviceSynchronize();
+    return TZ_OK;
+}
+
+void nn_set_layer_limit(tz_handle* h, int limit) {
+    if (h->nn) h->nn->layer_limit = limit;
+}
+
+// ---- forward ---------------------------------------------------------------------------------------------
+
+static void launch_conv(const tz_handle* h, const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* residual,
+                        __nv_bfloat16* out_act, float* out_f32, int relu, const int* count_ptr, int count_max) {
+    const NnState* s = h->nn;
+    conv::Params p;
+    p.in = in;
+    p.cin = L.cin;
+    p.w = L.w;
+    p.bias = L.bias;
+    p.residual = residual;
+    p.out_act = out_act;
+    p.out_f32 = out_f32;
+    p.relu = relu;
+    p.count_ptr = count_ptr;
+    p.count_max = count_max;
+    p.n = s->n;
+    p.guard = conv::HALO;
+    const int w1 = s->n + 1;
+    const int max_tiles = (count_max * w1 * w1 + conv::TILE_M - 1) / conv::TILE_M;
+    const int grid = max_tiles < s->sm_count ? max_tiles : s->sm_count;
+    conv::k_conv3x3<<<grid > 0 ? grid : 1, conv::THREADS, conv::SMEM_BYTES, h->stream>>>(p);
+}
+
+// states[count] (device), actions/n_actions by position -> logits/value/variance by position.
+// count_ptr (device) may be smaller than count_max; kernels size themselves from it.
+int nn_forward(tz_handle* h, const TzState* states, const int* count_ptr, int count_max, const uint16_t* actions,
+               const int* n_actions, float* logits, float* value, float* variance) {
+    NnState* s = h->nn;
+    if (!s) return TZ_ENOWEIGHTS;
+    if (count_max > s->max_positions) return TZ_EINVAL;
+    const TzDev& d = h->d;
+    const int wblocks = (count_max + WPB - 1) / WPB;
+    k_encode<<<wblocks, 32 * WPB, 0, h->stream>>>(states, count_ptr, count_max, d.n, d.half_komi, nullptr, s->planes,
+                                                  conv::HALO);
+    int done = 0;
+    const int limit = s->layer_limit;
+    auto more = [&]() { return limit < 0 || done < limit; };
+    if (more()) {
+        launch_conv(h, s->input, s->planes, nullptr, s->act_x, nullptr, 1, count_ptr, count_max);
+        done++;
+    }
+    for (int b = 0; b < s->blocks; b++) {
+        if (more()) {
+            launch_conv(h, s->tower[2 * b], s->act_x, nullptr, s->act_t, nullptr, 1, count_ptr, count_max);
+            done++;
+        }
+        if (more()) {
+            launch_conv(h, s->tower[2 * b + 1], s->act_t, s->act_x, s->act_x, nullptr, 1, count_ptr, count_max);
+            done++;
+        }
+    }
+    h->launches += 1 + done;
+    if (limit >= 0) return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
+    launch_conv(h, s->policy, s->act_x, nullptr, nullptr, s->logits_full, 0, count_ptr, count_max);
+    k_heads_gather<<<wblocks, 32 * WPB, 0, h->stream>>>(s->act_x, s->logits_full, s->head_w, s->head_misc, actions,
+                                                        n_actions, count_ptr, count_max, d.n, d.M, conv::HALO, logits,
+                                                        value, variance);
+    h->launches += 2;
+    return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
+}
+
+int nn_forward_queue(tz_handle* h) {
+    const TzDev& d = h->d;
+    return nn_forward(h, d.leaf_state, d.nn_count, d.G, d.actions, d.n_actions, d.logits, d.value, d.variance);
+}
+
+int nn_encode_planes(tz_handle* h, const TzState* states, int count, float* out_f32) {
+    const TzDev& d = h->d;
+    k_encode<<<(count + WPB - 1) / WPB, 32 * WPB, 0, h->stream>>>(states, nullptr, count, d.n, d.half_komi, out_f32,
+                                                                  nullptr, 0);
+    return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
+}
+
+// debug read-back: which = 0 act_x, 1 act_t, 2 planes; f32 [count][n*n][channels]
+__global__ void k_unpad(const __nv_bfloat16* buf, int channels, int count, int n, int guard, float* out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nn = n * n, w1 = n + 1;
+    if (idx >= (size_t)count * nn * channels) return;
+    const int c = (int)(idx % channels);
+    const size_t cell = idx / channels;
+    const int sq = (int)(cell % nn);
+    const size_t q = cell / nn;
+    const size_t r = (size_t)guard + q * (w1 * w1) + (size_t)(sq / n + 1) * w1 + sq % n;
+    out[idx] = __bfloat162float(buf[r * channels + c]);
+}
+
+int nn_debug_read(tz_handle* h, int which, int count, float* out_dev) {
+    NnState* s = h->nn;
+    if (!s) return TZ_ENOWEIGHTS;
+    const __nv_bfloat16* buf = which == 0 ? s->act_x : which == 1 ? s->act_t : s->planes;
+    const int channels = which == 2 ? CIN_PAD : FILTERS;
+    const size_t total = (size_t)count * s->n * s->n * channels;
+    k_unpad<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(buf, channels, count, s->n, conv::HALO, out_dev);
+    return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
+}

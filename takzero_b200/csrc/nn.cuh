@@ -4,5 +4,13 @@
 
 bool nn_ready(const tz_handle* h);
 void nn_free(tz_handle* h);
+const char* nn_last_error();
+int nn_set_weights(tz_handle* h, const char* const* names, const float* const* data, const long long* const* shapes,
+                   const int* ndims, int count);
 // policy/value/uncertainty of the queued leaf positions -> d.logits / d.value / d.variance
 int nn_forward_queue(tz_handle* h);
+int nn_forward(tz_handle* h, const TzState* states, const int* count_ptr, int count_max, const uint16_t* actions,
+               const int* n_actions, float* logits, float* value, float* variance);
+int nn_encode_planes(tz_handle* h, const TzState* states, int count, float* out_f32);
+void nn_set_layer_limit(tz_handle* h, int limit);
+int nn_debug_read(tz_handle* h, int which, int count, float* out_dev);

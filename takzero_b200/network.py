@@ -1,0 +1,86 @@
+"""Host-side mirror of the reference's `Network` / `Agent` surface for the device ResNet
+(takzero/src/network/mod.rs:10-45, net6_simhash.rs:259-324): weight upload and the
+evaluate / encode hooks of the C ABI.  All math happens in libtakzero_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Sequence
+
+import numpy as np
+
+from . import capi
+
+
+class _Tensor(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.POINTER(C.c_float)), ("shape", C.POINTER(C.c_int64)),
+                ("ndim", C.c_int)]
+
+
+_declared = False
+
+
+def _declare():
+    global _declared
+    if _declared:
+        return
+    vp, i32 = C.c_void_p, C.c_int
+    capi.declare("tz_set_weights", [vp, C.POINTER(_Tensor), i32], i32)
+    capi.declare("tz_evaluate", [vp, vp, i32, vp, vp, i32, vp, vp, vp], i32)
+    capi.declare("tz_encode_planes", [vp, vp, i32, vp], i32)
+    capi.declare("tz_debug_layer_limit", [vp, i32], i32)
+    capi.declare("tz_debug_activations", [vp, i32, i32, vp], i32)
+    _declared = True
+
+
+def set_weights(mcts: capi.BatchedMCTS, tensors: Dict[str, np.ndarray]) -> None:
+    """`Net::load`: upload named f32 tensors (PyTorch layout, names in include/takzero_b200.h)."""
+    _declare()
+    keep = []
+    arr = (_Tensor * len(tensors))()
+    for i, (name, t) in enumerate(tensors.items()):
+        a = np.ascontiguousarray(t, dtype=np.float32)
+        shape = (C.c_int64 * a.ndim)(*a.shape)
+        keep += [a, shape]
+        arr[i] = _Tensor(name.encode(), a.ctypes.data_as(C.POINTER(C.c_float)), shape, a.ndim)
+    capi._check(capi.lib().tz_set_weights(mcts.handle, arr, len(tensors)))
+
+
+def evaluate(mcts: capi.BatchedMCTS, states: np.ndarray, actions: Sequence[Sequence[int]]):
+    """`Agent::policy_value_uncertainty` for host positions: (logits list, values, variances)."""
+    _declare()
+    states = np.ascontiguousarray(states, dtype=capi.STATE_DTYPE)
+    count, M = len(states), mcts.move_stride
+    act = np.zeros((count, M), dtype=np.uint16)
+    nact = np.zeros(count, dtype=np.int32)
+    for i, a in enumerate(actions):
+        act[i, : len(a)] = a
+        nact[i] = len(a)
+    logits = np.zeros((count, M), dtype=np.float32)
+    values = np.zeros(count, dtype=np.float32)
+    variances = np.zeros(count, dtype=np.float32)
+    p = capi._ptr
+    capi._check(capi.lib().tz_evaluate(mcts.handle, p(states), count, p(act), p(nact), M, p(logits), p(values),
+                                       p(variances)))
+    return [logits[i, : nact[i]].copy() for i in range(count)], values, variances
+
+
+def encode_planes(mcts: capi.BatchedMCTS, states: np.ndarray) -> np.ndarray:
+    """`game_repr` (network/repr.rs:169-228): f32 [count, C, N, N]."""
+    _declare()
+    states = np.ascontiguousarray(states, dtype=capi.STATE_DTYPE)
+    out = np.zeros((len(states), mcts.input_channels, mcts.n, mcts.n), dtype=np.float32)
+    capi._check(capi.lib().tz_encode_planes(mcts.handle, capi._ptr(states), len(states), capi._ptr(out)))
+    return out
+
+
+def debug_layer_limit(mcts: capi.BatchedMCTS, limit: int) -> None:
+    _declare()
+    capi._check(capi.lib().tz_debug_layer_limit(mcts.handle, limit))
+
+
+def debug_activations(mcts: capi.BatchedMCTS, which: int, count: int) -> np.ndarray:
+    _declare()
+    ch = 64 if which == 2 else 256
+    out = np.zeros((count, mcts.n * mcts.n, ch), dtype=np.float32)
+    capi._check(capi.lib().tz_debug_activations(mcts.handle, which, count, capi._ptr(out)))
+    return out

@@ -1,0 +1,155 @@
+"""GPU parity: encoding (bit-exact) and the bf16 tcgen05 network vs the f32 PyTorch restatement.
+
+Tolerances (stated per BASELINE.json north_star): planes bit-exact; policy logits / value within
+|delta| <= 1e-2 of the f32 reference on random-init weights; argmax agreement >= 99%."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import net_ref
+from oracle import oracle as O
+from takzero_b200 import capi, network
+
+from helpers import games_to_states, random_playout_states
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-2
+
+
+def sample_positions(n, half_komi, count, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < count:
+        ps = random_playout_states(n, half_komi, int(rng.integers(1 << 30)), keep_terminal=False)
+        for i in rng.choice(len(ps), size=min(4, len(ps)), replace=False):
+            out.append(ps[int(i)])
+    return out[:count]
+
+
+@pytest.mark.parametrize("n,half_komi", [(3, 0), (4, 4), (5, 4), (6, 4)])
+def test_encode_planes_bit_exact(n, half_komi):
+    games = sample_positions(n, half_komi, 200, n)
+    m = capi.BatchedMCTS(n, half_komi, 4, arena_slots=4096)
+    got = network.encode_planes(m, games_to_states(games))
+    want = np.stack([O.game_repr(g) for g in games]).reshape(got.shape)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    m.close()
+
+
+def test_encode_golden_vector():
+    """repr.rs:303-360 `complicated_position` through the CUDA encoder."""
+    g = O.from_tps(5, 4, "x2,1221,x,1S/2,2C,2,1,x/x,212,21C,2S,2/2211S,2,21,1,1/x2,221S,2,x 2 23")
+    m = capi.BatchedMCTS(5, 4, 2, arena_slots=4096)
+    got = network.encode_planes(m, games_to_states([g]))[0]
+    assert np.array_equal(got.reshape(-1).view(np.uint32), O.game_repr(g).view(np.uint32))
+    assert got[-1, 0, 0] == np.float32(-3.0) / np.float32(25.0)  # FCD plane
+    m.close()
+
+
+def check_network(n, half_komi, count, blocks, seed, randomize_bn):
+    ref = net_ref.Net(n, seed=seed, blocks=blocks, randomize_bn=randomize_bn)
+    games = sample_positions(n, half_komi, count, seed)
+    actions = [O.possible_moves(g) for g in games]
+    m = capi.BatchedMCTS(n, half_komi, count, arena_slots=4096)
+    network.set_weights(m, ref.tensors())
+    logits, values, variances = network.evaluate(m, games_to_states(games), actions)
+    want_logits, want_values, want_var = ref.policy_value_uncertainty(games, actions)
+    worst = 0.0
+    agree = 0
+    for i in range(count):
+        assert logits[i].shape == want_logits[i].shape
+        worst = max(worst, float(np.abs(logits[i] - want_logits[i]).max()))
+        agree += int(np.argmax(logits[i]) == np.argmax(want_logits[i]))
+    dv = float(np.abs(values - want_values).max())
+    print(f"n={n} blocks={blocks}: max |dlogit| {worst:.4g}, max |dvalue| {dv:.4g}, argmax agreement {agree}/{count}")
+    assert worst <= TOL, f"policy logits differ by {worst}"
+    assert dv <= TOL, f"values differ by {dv}"
+    assert np.array_equal(variances, want_var)  # 4.0 everywhere with an empty SimHash set
+    assert agree >= 0.99 * count
+    m.close()
+
+
+def test_single_conv_layer_matches_torch():
+    """First convolution only (input planes -> 256 channels), compared element-wise."""
+    n, hk, count = 6, 4, 40
+    ref = net_ref.Net(n, seed=5, blocks=1, randomize_bn=True)
+    games = sample_positions(n, hk, count, 5)
+    actions = [O.possible_moves(g) for g in games]
+    m = capi.BatchedMCTS(n, hk, count, arena_slots=4096)
+    network.set_weights(m, ref.tensors())
+    network.debug_layer_limit(m, 1)
+    network.evaluate(m, games_to_states(games), actions)
+    got = network.debug_activations(m, 0, count)  # [count, 36, 256]
+    xs = torch.from_numpy(np.stack([O.game_repr(g).reshape(ref.cin, n, n) for g in games]))
+    with torch.no_grad():
+        want = torch.relu(ref.core.batch_norm(ref.core.input_conv2d(xs)))
+    want = want.permute(0, 2, 3, 1).reshape(count, n * n, 256).numpy()
+    err = np.abs(got - want).max()
+    print("first conv max abs err", err, "ref max", np.abs(want).max())
+    assert err <= 2e-2 * max(1.0, float(np.abs(want).max()))
+    network.debug_layer_limit(m, 3)
+    network.evaluate(m, games_to_states(games), actions)
+    got = network.debug_activations(m, 0, count)
+    with torch.no_grad():
+        want = ref.core.res_block_0(torch.relu(ref.core.batch_norm(ref.core.input_conv2d(xs))))
+    want = want.permute(0, 2, 3, 1).reshape(count, n * n, 256).numpy()
+    err = np.abs(got - want).max()
+    print("block 0 max abs err", err, "ref max", np.abs(want).max())
+    assert err <= 3e-2 * max(1.0, float(np.abs(want).max()))
+    m.close()
+
+
+def test_network_small_4x4():
+    check_network(4, 4, 64, 2, 11, True)
+
+
+def test_network_full_6x6():
+    check_network(6, 4, 96, 16, 123, False)
+
+
+def test_network_full_4x4():
+    check_network(4, 4, 128, 16, 123, False)
+
+
+def test_network_full_5x5():
+    check_network(5, 4, 48, 20, 123, False)
+
+
+def test_search_with_device_network_matches_injected_outputs():
+    """The search driven by the device network == the search with that network's own outputs
+    injected through the host callback (the tree code is identical; only the data path differs)."""
+    n, hk, G = 4, 4, 16
+    ref = net_ref.Net(n, seed=3, blocks=2)
+    a = capi.BatchedMCTS(n, hk, G, arena_slots=1 << 14)
+    b = capi.BatchedMCTS(n, hk, G, arena_slots=1 << 14)
+    evaluator = capi.BatchedMCTS(n, hk, G, arena_slots=4096)
+    for h in (a, b, evaluator):
+        network.set_weights(h, ref.tensors())
+    a.new_openings(seed=1)
+    b.new_openings(seed=1)
+    a.set_agent(capi.AGENT_NETWORK)
+
+    import ctypes as C
+
+    def cb(_ctx, batch, envs, actions, n_actions, stride, logits, values, variances):
+        st = np.ctypeslib.as_array(C.cast(envs, C.POINTER(C.c_uint8)), shape=(batch * 384,)).view(capi.STATE_DTYPE)
+        act = np.ctypeslib.as_array(actions, shape=(batch, stride))
+        na = np.ctypeslib.as_array(n_actions, shape=(batch,))
+        lg, v, u = network.evaluate(evaluator, st.copy(), [list(act[i, : na[i]]) for i in range(batch)])
+        lo = np.ctypeslib.as_array(logits, shape=(batch, stride))
+        for i in range(batch):
+            lo[i, : na[i]] = lg[i]
+        np.ctypeslib.as_array(values, shape=(batch,))[:] = v
+        np.ctypeslib.as_array(variances, shape=(batch,))[:] = u
+
+    b.set_agent(capi.AGENT_HOST, cb)
+    gum = np.random.default_rng(0).gumbel(size=(G, a.move_stride)).astype(np.float32)
+    ma = a.gumbel_sequential_halving(None, 8, 48, gum)
+    mb = b.gumbel_sequential_halving(None, 8, 48, gum)
+    assert np.array_equal(ma, mb)
+    ta, tb = a.root_children(), b.root_children()
+    assert np.array_equal(ta["visits"], tb["visits"])
+    assert np.array_equal(ta["eval_bits"], tb["eval_bits"])
+    for h in (a, b, evaluator):
+        h.close()
