@@ -186,6 +186,39 @@ TZ_API int tz_select_selfplay(tz_handle* h, int weighted_random_plies, uint32_t 
                        const uint64_t* randoms, uint64_t seed, tz_move_t* out_moves);
 TZ_API int tz_counters(tz_handle* h, tz_counters_t* out);
 
+/* One self-play move of every game without host buffers (the loop body of selfplay/src/main.rs:
+ * 138-153, 238-329 minus the file I/O): search with library-drawn Gumbel noise, improved-policy /
+ * UBE targets into device buffers, visit-weighted sampling on early plies, step, restart of finished
+ * games.  Asynchronous: returns once enqueued; tz_sync / tz_counters / tz_status wait. */
+typedef struct tz_selfplay_t {
+    int sampled_actions;        /* SAMPLED_ACTIONS */
+    uint32_t search_budget;     /* SEARCH_BUDGET */
+    float beta;                 /* BETA for the upper half of the batch (`exploration` feature), else 0 */
+    int weighted_random_plies;  /* WEIGHTED_RANDOM_PLIES (10) */
+    uint32_t sample_threshold;  /* 32 */
+    float allowed_eval_drop;    /* 0.5 */
+    float target_visitations;   /* IMPROVED_POLICY_VISITATIONS */
+    float target_beta;          /* ube_target beta (0.25) */
+    uint64_t seed;
+} tz_selfplay_t;
+TZ_API int tz_selfplay_move(tz_handle* h, const tz_selfplay_t* params);
+TZ_API int tz_launch_count(tz_handle* h, uint64_t* out);             /* kernels launched so far */
+
+/* Sampled per-kernel device timing: every `sample_every`-th lock-step simulation is bracketed with
+ * CUDA events on the library's stream.  Categories: 0 select(+movegen,+known backup), 1 encode,
+ * 2 input conv, 3 tower convs, 4 policy conv, 5 heads+gather, 6 expand(+softmax,+backup), 7 synthetic agent. */
+typedef struct tz_profile_t {
+    double ms[8];
+    uint64_t launches[8];
+    uint64_t locksteps; /* sampled lock-step simulations */
+    uint64_t positions; /* positions evaluated in the sampled lock-steps */
+} tz_profile_t;
+TZ_API int tz_profile_begin(tz_handle* h, int sample_every);
+TZ_API int tz_profile_end(tz_handle* h, tz_profile_t* out);
+/* CUDA-event stopwatch on the library's stream: start is asynchronous, stop waits and returns ms */
+TZ_API int tz_timer_start(tz_handle* h);
+TZ_API int tz_timer_stop(tz_handle* h, double* out_ms);
+
 /* ---- network (takzero/src/network/{net4_simhash,net5,net6_simhash,residual,repr}.rs) ----------- */
 /* Net::load (network/mod.rs:16-35): f32 tensors in PyTorch layout, named
  *   core.input_conv2d.weight [256,C,3,3]; core.batch_norm.{weight,bias,running_mean,running_var} [256];

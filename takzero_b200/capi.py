@@ -77,6 +77,23 @@ class Counters(C.Structure):
                 ("expansions", C.c_uint64)]
 
 
+class SelfplayParams(C.Structure):
+    """tz_selfplay_t: the compile-time constants of selfplay/src/main.rs:36-52 as runtime fields."""
+
+    _fields_ = [("sampled_actions", C.c_int), ("search_budget", C.c_uint32), ("beta", C.c_float),
+                ("weighted_random_plies", C.c_int), ("sample_threshold", C.c_uint32),
+                ("allowed_eval_drop", C.c_float), ("target_visitations", C.c_float), ("target_beta", C.c_float),
+                ("seed", C.c_uint64)]
+
+
+class Profile(C.Structure):
+    _fields_ = [("ms", C.c_double * 8), ("launches", C.c_uint64 * 8), ("locksteps", C.c_uint64),
+                ("positions", C.c_uint64)]
+
+
+PROFILE_CATEGORIES = ("select", "encode", "conv_input", "conv_tower", "conv_policy", "heads_gather", "expand",
+                      "agent_synthetic")
+
 ROOT_DTYPE = np.dtype([("eval_tag", "<u4"), ("eval_bits", "<u4"), ("visit_count", "<u4"),
                        ("std_dev_bits", "<u4"), ("n_children", "<u4"), ("arena_used", "<u4")])
 
@@ -133,6 +150,12 @@ def lib():
         "tz_select_best": ([vp, vp], i32),
         "tz_select_selfplay": ([vp, i32, u32, f32, vp, u64, vp], i32),
         "tz_counters": ([vp, P(Counters)], i32),
+        "tz_selfplay_move": ([vp, P(SelfplayParams)], i32),
+        "tz_launch_count": ([vp, P(u64)], i32),
+        "tz_profile_begin": ([vp, i32], i32),
+        "tz_profile_end": ([vp, P(Profile)], i32),
+        "tz_timer_start": ([vp], i32),
+        "tz_timer_stop": ([vp, P(C.c_double)], i32),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)
@@ -149,6 +172,18 @@ def declare(name, args, res):
     fn.argtypes = args
     fn.restype = res
     return fn
+
+
+def pinned_array(shape, dtype) -> np.ndarray:
+    """numpy view of pinned host memory from tz_host_alloc (kept alive by the returned array's base)."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    p = lib().tz_host_alloc(max(nbytes, 1))
+    if not p:
+        raise MemoryError("tz_host_alloc failed")
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    return arr
 
 
 def _ptr(a: Optional[np.ndarray]):
@@ -347,6 +382,31 @@ class BatchedMCTS:
         c = Counters()
         _check(lib().tz_counters(self._h, C.byref(c)))
         return c
+
+    def selfplay_move(self, params: SelfplayParams) -> None:
+        """One whole self-play move on the device, asynchronous (see tz_selfplay_move)."""
+        _check(lib().tz_selfplay_move(self._h, C.byref(params)))
+
+    def launch_count(self) -> int:
+        out = C.c_uint64()
+        _check(lib().tz_launch_count(self._h, C.byref(out)))
+        return out.value
+
+    def profile_begin(self, sample_every: int) -> None:
+        _check(lib().tz_profile_begin(self._h, sample_every))
+
+    def profile_end(self) -> Profile:
+        p = Profile()
+        _check(lib().tz_profile_end(self._h, C.byref(p)))
+        return p
+
+    def timer_start(self) -> None:
+        _check(lib().tz_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        _check(lib().tz_timer_stop(self._h, C.byref(ms)))
+        return ms.value
 
     def status(self) -> int:
         bits = C.c_uint32()

@@ -207,6 +207,10 @@ extern "C" TZ_API void tz_destroy(tz_handle* h) {
     nn_free(h);
     for (void* p : h->allocs) cudaFree(p);
     if (h->pin_small) cudaFreeHost(h->pin_small);
+    if (h->prof_counts) cudaFreeHost(h->prof_counts);
+    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+    if (h->timer_a) cudaEventDestroy(h->timer_a);
+    if (h->timer_b) cudaEventDestroy(h->timer_b);
     if (h->pin_states) cudaFreeHost(h->pin_states);
     if (h->pin_actions) cudaFreeHost(h->pin_actions);
     if (h->pin_nact) cudaFreeHost(h->pin_nact);
@@ -452,9 +456,18 @@ extern "C" TZ_API int tz_set_agent(tz_handle* h, int kind, tz_agent_fn fn, void*
 // one lock-step simulation of all games (batched.rs:63-128 / :266-333)
 static int lockstep(tz_handle* h, int phase, int halving_i, const float* dbetas) {
     const TzDev& d = h->d;
+    h->prof_active = h->prof_every > 0 && (h->prof_tick++ % (unsigned long long)h->prof_every) == 0 &&
+                     h->prof_locksteps < TZ_PROF_MAX_LOCKSTEPS && h->prof_used + 64 < TZ_PROF_MAX_PAIRS;
     CU(cudaMemsetAsync(d.nn_count, 0, sizeof(int), h->stream));
-    launch_select(d, phase, halving_i, dbetas, h->stream);
+    {
+        ProfScope ps(h, TZ_PROF_SELECT);
+        launch_select(d, phase, halving_i, dbetas, h->stream);
+    }
+    if (h->prof_active)
+        CU(cudaMemcpyAsync(h->prof_counts + h->prof_locksteps++, d.nn_count, sizeof(int), cudaMemcpyDeviceToHost,
+                           h->stream));
     if (h->agent_kind == TZ_AGENT_SYNTHETIC) {
+        ProfScope ps(h, TZ_PROF_SYNTH);
         launch_agent_synth(d, h->stream);
     } else if (h->agent_kind == TZ_AGENT_NETWORK) {
         int rc = nn_forward_queue(h);
@@ -476,7 +489,11 @@ static int lockstep(tz_handle* h, int phase, int halving_i, const float* dbetas)
             CU(cudaMemcpyAsync(d.variance, h->pin_variance, c * sizeof(float), cudaMemcpyHostToDevice, h->stream));
         }
     }
-    launch_expand(d, h->stream);
+    {
+        ProfScope ps(h, TZ_PROF_EXPAND);
+        launch_expand(d, h->stream);
+    }
+    h->prof_active = false;
     h->launches += 3;
     return TZ_OK;
 }
@@ -803,5 +820,102 @@ extern "C" TZ_API int tz_debug_activations(tz_handle* h, int which, int count, f
     CU(cudaMemcpyAsync(out, dout, total * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
+    return TZ_OK;
+}
+
+// ---- device-resident self-play move and sampled kernel timing ------------------------------------------
+
+extern "C" TZ_API int tz_selfplay_move(tz_handle* h, const tz_selfplay_t* sp) {
+    CHECK_H(h);
+    if (!sp) return fail(TZ_EINVAL, "null parameters");
+    if (sp->sampled_actions <= 0 || sp->sampled_actions > TZ_MAX_K)
+        return fail(TZ_EINVAL, "At least one action must be sampled (and at most %d)", TZ_MAX_K);
+    const uint32_t steps = ilog2_u32((uint32_t)sp->sampled_actions);
+    if (steps == 0 || sp->search_budget % (steps * (uint32_t)sp->sampled_actions) != 0)
+        return fail(TZ_EINVAL, "The search budget should be a multiple of k*log2(k) for clean visits");
+    const TzDev& d = h->d;
+    const float* dbetas = nullptr;
+    if (sp->beta != 0.0f) {
+        // `exploration` feature of selfplay (main.rs:81-87): beta for the upper half of the batch
+        std::vector<float> b((size_t)d.G, 0.0f);
+        for (int g = d.G / 2; g < d.G; g++) b[g] = sp->beta;
+        CU(cudaMemcpyAsync(h->betas, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        dbetas = h->betas;
+    }
+    launch_gumbel_noise(d, h->gumbel, d.M, sp->seed, h->move_counter, h->stream);
+    h->gumbel_stride = d.M;
+    int rc = tz_search_device(h, dbetas, sp->sampled_actions, sp->search_budget, h->gumbel, d.M);
+    if (rc) return rc;
+    // targets of this position (selfplay/src/main.rs:243-256) stay on the device
+    launch_targets(d, sp->target_visitations, sp->target_beta, d.M, h->tbl_f32a, h->ube, h->tbl_n, nullptr, h->stream);
+    // plies < weighted_random_plies sample proportionally to visits, the rest keep the halving winner
+    launch_select_actions(d, sp->weighted_random_plies, sp->sample_threshold, sp->allowed_eval_drop, nullptr, sp->seed,
+                          h->move_counter, h->tbl_moves, h->stream);
+    launch_merge_moves(d, sp->weighted_random_plies, h->tbl_moves, h->moves, h->stream);
+    launch_step(d, h->moves, h->stream);
+    launch_restart(d, nullptr, nullptr, sp->seed, h->opening_counter++, h->terminal, h->fin_start, h->fin_replay,
+                   h->fin_len, h->stream);
+    h->launches += 6;
+    CU(cudaGetLastError());
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_launch_count(tz_handle* h, uint64_t* out) {
+    if (!h || !out) return fail(TZ_EINVAL, "null argument");
+    *out = h->launches;
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_profile_begin(tz_handle* h, int sample_every) {
+    CHECK_H(h);
+    if (sample_every < 0) return fail(TZ_EINVAL, "sample_every must be >= 0");
+    CU(cudaStreamSynchronize(h->stream));
+    if (!h->prof_counts)
+        CU(cudaHostAlloc((void**)&h->prof_counts, TZ_PROF_MAX_LOCKSTEPS * sizeof(int), cudaHostAllocDefault));
+    h->prof_every = sample_every;
+    h->prof_tick = 0;
+    h->prof_used = 0;
+    h->prof_locksteps = 0;
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_profile_end(tz_handle* h, tz_profile_t* out) {
+    CHECK_H(h);
+    if (!out) return fail(TZ_EINVAL, "null out");
+    CU(cudaStreamSynchronize(h->stream));
+    memset(out, 0, sizeof(*out));
+    for (size_t i = 0; i < h->prof_used; i++) {
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, h->prof_events[2 * i], h->prof_events[2 * i + 1]));
+        const int c = h->prof_cat[i];
+        out->ms[c] += ms;
+        out->launches[c] += 1;
+    }
+    out->locksteps = (uint64_t)h->prof_locksteps;
+    for (int i = 0; i < h->prof_locksteps; i++) out->positions += (uint64_t)h->prof_counts[i];
+    h->prof_every = 0;
+    return TZ_OK;
+}
+
+// device-side stopwatch on the library's stream (CUDA events), for callers that time whole moves
+extern "C" TZ_API int tz_timer_start(tz_handle* h) {
+    CHECK_H(h);
+    if (!h->timer_a) {
+        CU(cudaEventCreate(&h->timer_a));
+        CU(cudaEventCreate(&h->timer_b));
+    }
+    CU(cudaEventRecord(h->timer_a, h->stream));
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_timer_stop(tz_handle* h, double* out_ms) {
+    CHECK_H(h);
+    if (!h->timer_a || !out_ms) return fail(TZ_EINVAL, "tz_timer_start first");
+    CU(cudaEventRecord(h->timer_b, h->stream));
+    CU(cudaEventSynchronize(h->timer_b));
+    float ms = 0.0f;
+    CU(cudaEventElapsedTime(&ms, h->timer_a, h->timer_b));
+    *out_ms = (double)ms;
     return TZ_OK;
 }

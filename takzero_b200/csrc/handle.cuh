@@ -48,4 +48,43 @@ struct tz_handle {
     unsigned long long move_counter = 0;
     unsigned long long opening_counter = 0;
     unsigned long long launches = 0;  // kernels launched by this handle
+    // sampled per-kernel timing (tz_profile_begin / tz_profile_end)
+    int prof_every = 0;
+    unsigned long long prof_tick = 0;
+    bool prof_active = false;  // the current lock-step simulation is being sampled
+    std::vector<cudaEvent_t> prof_events;  // pairs (start, stop)
+    std::vector<int> prof_cat;
+    size_t prof_used = 0;  // pairs in use
+    int* prof_counts = nullptr;  // pinned: evaluation-queue length of each sampled lock-step
+    int prof_locksteps = 0;
+    cudaEvent_t timer_a = nullptr, timer_b = nullptr;
+};
+
+enum { TZ_PROF_SELECT = 0, TZ_PROF_ENCODE, TZ_PROF_CONV_INPUT, TZ_PROF_CONV_TOWER, TZ_PROF_CONV_POLICY,
+       TZ_PROF_HEADS, TZ_PROF_EXPAND, TZ_PROF_SYNTH, TZ_PROF_CATS };
+#define TZ_PROF_MAX_PAIRS 16384
+#define TZ_PROF_MAX_LOCKSTEPS 1024
+
+// bracket one kernel launch with events when the current lock-step is sampled
+struct ProfScope {
+    tz_handle* h;
+    bool on;
+    ProfScope(tz_handle* h_, int cat) : h(h_), on(false) {
+        if (!h->prof_active || h->prof_used >= TZ_PROF_MAX_PAIRS) return;
+        if (h->prof_events.size() < 2 * (h->prof_used + 1)) {
+            cudaEvent_t a, b;
+            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+            h->prof_events.push_back(a);
+            h->prof_events.push_back(b);
+            h->prof_cat.push_back(cat);
+        }
+        h->prof_cat[h->prof_used] = cat;
+        cudaEventRecord(h->prof_events[2 * h->prof_used], h->stream);
+        on = true;
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(h->prof_events[2 * h->prof_used + 1], h->stream);
+        h->prof_used++;
+    }
 };

@@ -812,6 +812,13 @@ __global__ void __launch_bounds__(32 * WPB) k_select_actions(TzDev d, int weight
     if (lane == 0) out_moves[g] = (uint16_t)tz_meta_move(t.meta[first + (uint32_t)pick]);
 }
 
+// selfplay/src/main.rs:143-152: plies below WEIGHTED_RANDOM_PLIES take the sampled action
+__global__ void k_merge_moves(TzDev d, int weighted_random_plies, const uint16_t* sampled, uint16_t* moves) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= d.G) return;
+    if ((int)d.env[g].ply < weighted_random_plies) moves[g] = sampled[g];
+}
+
 // ---- rules parity hooks --------------------------------------------------------------------
 
 __global__ void __launch_bounds__(32 * WPB) k_rules_probe(TzDev d, const TzState* states, int count, int stride,
@@ -906,6 +913,10 @@ void launch_select_actions(const TzDev& d, int weighted_random_plies, uint32_t t
                            uint16_t* out_moves, cudaStream_t st) {
     k_select_actions<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, weighted_random_plies, threshold, allowed_drop, randoms,
                                                            seed, counter, out_moves);
+}
+void launch_merge_moves(const TzDev& d, int weighted_random_plies, const uint16_t* sampled, uint16_t* moves,
+                        cudaStream_t st) {
+    k_merge_moves<<<(d.G + 127) / 128, 128, 0, st>>>(d, weighted_random_plies, sampled, moves);
 }
 void launch_rules_probe(const TzDev& d, const TzState* states, int count, int stride, uint16_t* out_moves, int* out_n,
                         int* out_terminal, cudaStream_t st) {

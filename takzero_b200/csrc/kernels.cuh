@@ -29,3 +29,5 @@ void launch_rules_probe(const TzDev& d, const TzState* states, int count, int st
                         int* out_terminal, cudaStream_t st);
 void launch_apply_moves(const TzDev& d, TzState* states, const uint16_t* moves, int count, int* out_ok,
                         cudaStream_t st);
+void launch_merge_moves(const TzDev& d, int weighted_random_plies, const uint16_t* sampled, uint16_t* moves,
+                        cudaStream_t st);

@@ -399,7 +399,7 @@ void nn_set_layer_limit(tz_handle* h, int limit) {
 
 // ---- forward ---------------------------------------------------------------------------------------------
 
-static void launch_conv(const tz_handle* h, const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* residual,
+static void launch_conv(tz_handle* h, const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* residual,
                         __nv_bfloat16* out_act, float* out_f32, int relu, const int* count_ptr, int count_max) {
     const NnState* s = h->nn;
     conv::Params p;
@@ -430,31 +430,43 @@ int nn_forward(tz_handle* h, const TzState* states, const int* count_ptr, int co
     if (count_max > s->max_positions) return TZ_EINVAL;
     const TzDev& d = h->d;
     const int wblocks = (count_max + WPB - 1) / WPB;
-    k_encode<<<wblocks, 32 * WPB, 0, h->stream>>>(states, count_ptr, count_max, d.n, d.half_komi, nullptr, s->planes,
-                                                  conv::HALO);
+    {
+        ProfScope ps(h, TZ_PROF_ENCODE);
+        k_encode<<<wblocks, 32 * WPB, 0, h->stream>>>(states, count_ptr, count_max, d.n, d.half_komi, nullptr, s->planes,
+                                                      conv::HALO);
+    }
     int done = 0;
     const int limit = s->layer_limit;
     auto more = [&]() { return limit < 0 || done < limit; };
     if (more()) {
+        ProfScope ps(h, TZ_PROF_CONV_INPUT);
         launch_conv(h, s->input, s->planes, nullptr, s->act_x, nullptr, 1, count_ptr, count_max);
         done++;
     }
     for (int b = 0; b < s->blocks; b++) {
         if (more()) {
+            ProfScope ps(h, TZ_PROF_CONV_TOWER);
             launch_conv(h, s->tower[2 * b], s->act_x, nullptr, s->act_t, nullptr, 1, count_ptr, count_max);
             done++;
         }
         if (more()) {
+            ProfScope ps(h, TZ_PROF_CONV_TOWER);
             launch_conv(h, s->tower[2 * b + 1], s->act_t, s->act_x, s->act_x, nullptr, 1, count_ptr, count_max);
             done++;
         }
     }
     h->launches += 1 + done;
     if (limit >= 0) return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
-    launch_conv(h, s->policy, s->act_x, nullptr, nullptr, s->logits_full, 0, count_ptr, count_max);
-    k_heads_gather<<<wblocks, 32 * WPB, 0, h->stream>>>(s->act_x, s->logits_full, s->head_w, s->head_misc, actions,
-                                                        n_actions, count_ptr, count_max, d.n, d.M, conv::HALO, logits,
-                                                        value, variance);
+    {
+        ProfScope ps(h, TZ_PROF_CONV_POLICY);
+        launch_conv(h, s->policy, s->act_x, nullptr, nullptr, s->logits_full, 0, count_ptr, count_max);
+    }
+    {
+        ProfScope ps(h, TZ_PROF_HEADS);
+        k_heads_gather<<<wblocks, 32 * WPB, 0, h->stream>>>(s->act_x, s->logits_full, s->head_w, s->head_misc, actions,
+                                                            n_actions, count_ptr, count_max, d.n, d.M, conv::HALO, logits,
+                                                            value, variance);
+    }
     h->launches += 2;
     return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
 }
