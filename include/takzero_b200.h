@@ -238,6 +238,8 @@ TZ_API int tz_encode_planes(tz_handle* h, const tz_state_t* states, int count, f
  * buffer (0 block stream, 1 block middle, 2 input planes) of the last tz_evaluate as f32 [count][N*N][ch] */
 TZ_API int tz_debug_layer_limit(tz_handle* h, int limit);
 TZ_API int tz_debug_activations(tz_handle* h, int which, int count, float* out);
+/* tuning hook: mean ms per tower-convolution launch over `count` positions (CUDA events, `reps` blocks) */
+TZ_API int tz_debug_time_tower(tz_handle* h, int count, int reps, double* ms_per_conv);
 
 #ifdef __cplusplus
 }

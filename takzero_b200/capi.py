@@ -12,7 +12,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtakzero_b200.so")
+LIB_PATH = os.environ.get("TZ_LIB") or os.path.join(_HERE, "libtakzero_b200.so")
 
 MAX_SQ = 36
 MAX_MOVES = 1024

@@ -919,3 +919,11 @@ extern "C" TZ_API int tz_timer_stop(tz_handle* h, double* out_ms) {
     *out_ms = (double)ms;
     return TZ_OK;
 }
+
+extern "C" TZ_API int tz_debug_time_tower(tz_handle* h, int count, int reps, double* ms_per_conv) {
+    CHECK_H(h);
+    if (!ms_per_conv) return fail(TZ_EINVAL, "null out");
+    const int rc = nn_time_tower(h, count, reps, ms_per_conv);
+    if (rc) return fail(rc, "tz_debug_time_tower failed (weights set? count <= n_games?)");
+    return TZ_OK;
+}

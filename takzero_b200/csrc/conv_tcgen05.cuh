@@ -5,15 +5,18 @@
 // (takzero/src/network/residual.rs:13-63, net6_simhash.rs:43-86); BN is folded into the
 // weights / bias on the host (nn.cu), inference mode like `forward_t(xs, false)`.
 //
-// Data layout ("padded rows"): activations are channels-last bf16 [rows][C]; every board
-// owns (N+1)^2 consecutive rows: one zero row of N+1 entries, then N board rows of N squares
-// plus one zero column.  A 3x3 tap (dy,dx) of output row r is input row r + dy*(N+1) + dx,
-// and every out-of-board neighbour lands on a zero row/column, so the convolution is a GEMM
+// Data layout: activations are channels-last bf16 [rows][C] with DENSE rows, row = position *
+// N*N + square (no padding anywhere).  A 3x3 tap (dy,dx) of output row r is input row
+// r + dy*N + dx, so the convolution is the GEMM
 //   out[r, co] = sum_{tap, ci} act[r + off(tap), ci] * W[tap][co][ci]
-// whose A operand for each tap is the SAME shared-memory tile read at a shifted row:
-// the tile is stored K-chunk-major ([C/8][rows][8 ch], row pitch 16 B) in the no-swizzle
-// canonical UMMA layout, so a row shift is a +16 B/row change of the descriptor's start
-// address.  Zero rows are never written, so they stay zero from layer to layer.
+// whose A operand for each tap is the SAME shared-memory tile read at a shifted row: the tile is
+// stored K-chunk-major ([C/8][rows][8 ch], row pitch 16 B) in the no-swizzle canonical UMMA
+// layout, so a row shift is a +16 B/row change of the descriptor's start address.  Rows whose
+// neighbour (dy,dx) lies off the board (and would wrap to another board row / board) are
+// excluded with the `disable-output-lane` mask of tcgen05.mma: for that tap their accumulator
+// lanes are simply not updated, which is exactly "add zero padding".  The masks depend only on
+// (first row of the tile) mod N*N and come from a small host-built table.  No tensor-core work
+// is spent on padding.
 //
 // One CTA = 128 output rows x 256 output channels (one UMMA M128 N256 accumulator of 256
 // TMEM columns, double buffered), persistent over row tiles.  Warp roles:
@@ -29,31 +32,40 @@
 namespace conv {
 
 constexpr int TILE_M = 128;
-constexpr int HALO = 8;                       // >= (N+1)+1 for N <= 6
+constexpr int HALO = 8;                       // >= N+1 for N <= 6
 constexpr int A_ROWS = TILE_M + 2 * HALO;     // 144
 constexpr int A_KC_PITCH = (A_ROWS + 1) * 16; // 2320 B: +1 row keeps cp.async writes bank-conflict free
 constexpr int A_STAGE_BYTES = 8 * A_KC_PITCH; // 18560 B = one 64-channel block
-constexpr int A_STAGES = 6;
+#ifndef TZ_A_STAGES
+#define TZ_A_STAGES 4
+#endif
+#ifndef TZ_B_STAGES
+#define TZ_B_STAGES 4
+#endif
+constexpr int A_STAGES = TZ_A_STAGES;
 constexpr int B_KC_PITCH = 256 * 16;          // 4096 B
 constexpr int B_STAGE_BYTES = 8 * B_KC_PITCH; // 32768 B = 64 K x 256 N
-constexpr int B_STAGES = 3;
+constexpr int B_STAGES = TZ_B_STAGES;
 constexpr int N_OUT = 256;
 constexpr int THREADS = 256;
-constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + 1024 /*bias*/ + 256 /*barriers*/;
+constexpr int MASK_BYTES = 36 * 9 * 16;         // [N*N][9 taps] 128-bit lane masks
+constexpr int SMEM_BYTES =
+    A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + 1024 /*bias*/ + 256 /*barriers*/ + MASK_BYTES;
 
 struct Params {
-    const __nv_bfloat16* in;        // [rows][cin] activations, padded-row layout
+    const __nv_bfloat16* in;        // [rows][cin] activations, dense rows
     int cin;                        // channels of `in` (multiple of 64)
     const __nv_bfloat16* w;         // [cin/64][9][8][256][8] pre-arranged weight blocks
     const float* bias;              // [256]
     const __nv_bfloat16* residual;  // [rows][256] or null
     __nv_bfloat16* out_act;         // [rows][256] or null
-    float* out_f32;                 // [positions * n*n][256] compact rows, or null
+    float* out_f32;                 // [positions * n*n][256] (no guard rows), or null
     int relu;
     const int* count_ptr;           // number of positions (device), or null: use count_max
     int count_max;
     int n;                          // board size
     int guard;                      // leading guard rows of the buffers (= HALO)
+    const uint4* masks;             // [n*n][9] disable-output-lane masks by (first tile row) mod n*n
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -100,14 +112,16 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+// `mask`: disable-output-lane, bit i of the 128-bit vector = do not update TMEM lane (= tile row) i
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc,
+                                       const uint4& mask) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
         "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(mask.x), "r"(mask.y), "r"(mask.z), "r"(mask.w)
         : "memory");
 }
 // K-major, no swizzle: 8x8 core matrices of 128 contiguous bytes; LBO = byte distance of the
@@ -148,10 +162,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3(const Params p) {
     const uint32_t b_full = a_empty + 8 * A_STAGES, b_empty = b_full + 8 * B_STAGES;
     const uint32_t t_full = b_empty + 8 * B_STAGES, t_empty = t_full + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * A_STAGES + 2 * B_STAGES + 4);
+    uint4* s_masks = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
     const int count = p.count_ptr ? *p.count_ptr : p.count_max;
-    const int w1 = p.n + 1, sb = w1 * w1;
-    const int rows_used = count * sb;
+    const int nn = p.n * p.n;
+    const int rows_used = count * nn;
     const int tiles = (rows_used + TILE_M - 1) / TILE_M;
     const int kblocks = p.cin >> 6;
 
@@ -177,6 +192,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3(const Params p) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (int i = threadIdx.x; i < N_OUT; i += THREADS) s_bias[i] = p.bias[i];
+    for (int i = threadIdx.x; i < nn * 9; i += THREADS) s_masks[i] = p.masks[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -250,20 +266,24 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3(const Params p) {
                 mbar_wait(t_empty + 8 * acc, ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * N_OUT;
+                const uint4* tile_masks = s_masks + ((size_t)t * TILE_M % nn) * 9;
                 for (int kb = 0; kb < kblocks; kb++) {
                     mbar_wait(a_full + 8 * a_stage, a_phase);
                     const uint32_t a_base = smem_u32(a_smem + a_stage * A_STAGE_BYTES);
-                    for (int tap = 0; tap < 9; tap++) {
+                    // tap order: the centre tap first (no mask, it initialises every lane), then the rest
+                    for (int ti = 0; ti < 9; ti++) {
+                        const int tap = ti == 0 ? 4 : (ti <= 4 ? ti - 1 : ti);
                         mbar_wait(b_full + 8 * b_stage, b_phase);
                         tc_fence_after();
-                        const int off = (tap / 3 - 1) * w1 + (tap % 3 - 1);
+                        const int off = (tap / 3 - 1) * p.n + (tap % 3 - 1);
+                        const uint4 mask = tile_masks[tap];
                         const uint32_t a_tap = a_base + (HALO + off) * 16;
                         const uint32_t b_base = smem_u32(b_smem + b_stage * B_STAGE_BYTES);
 #pragma unroll
                         for (int ks = 0; ks < 4; ks++) {
                             const uint64_t adesc = make_desc(a_tap + ks * 2 * A_KC_PITCH, A_KC_PITCH);
                             const uint64_t bdesc = make_desc(b_base + ks * 2 * B_KC_PITCH, B_KC_PITCH);
-                            tc_mma(tmem_d, adesc, bdesc, idesc, (kb | tap | ks) != 0);
+                            tc_mma(tmem_d, adesc, bdesc, idesc, (kb | ti | ks) != 0, mask);
                         }
                         tc_commit(b_empty + 8 * b_stage);
                         if (++b_stage == B_STAGES) {
@@ -287,12 +307,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3(const Params p) {
         for (int t = blockIdx.x; t < tiles; t += gridDim.x, it++) {
             const int acc = it & 1;
             const int tr = wq * 32 + lane;
-            const int rel = t * TILE_M + tr;  // row relative to the first board
-            const int b = rel / sb, idx = rel - b * sb;
-            const int yy = idx / w1, xx = idx - yy * w1;
-            const bool valid = rel < rows_used && yy >= 1 && xx < p.n;
+            const int rel = t * TILE_M + tr;  // row = position * n*n + square
+            const bool valid = rel < rows_used;
             const size_t grow = (size_t)(p.guard + rel);
-            const size_t crow = (size_t)b * (p.n * p.n) + (size_t)(yy - 1) * p.n + xx;
+            const size_t crow = (size_t)rel;
             mbar_wait(t_full + 8 * acc, (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * N_OUT;

@@ -39,6 +39,7 @@ struct NnState {
     __nv_bfloat16* act_x = nullptr;   // [rows][256]
     __nv_bfloat16* act_t = nullptr;   // [rows][256]
     float* logits_full = nullptr;     // [max_positions * n*n][256]
+    uint4* masks = nullptr;           // [n*n][9] disable-output-lane masks (conv_tcgen05.cuh)
     int layer_limit = -1;             // debug: stop the tower after this many convolutions
     std::vector<void*> allocs;
     int sm_count = 148;
@@ -56,7 +57,7 @@ void nn_free(tz_handle* h) {
 // ---- input planes (network/repr.rs:169-228) ----------------------------------------------------
 
 // One warp per position.  out_f32: [count][C][N][N] exactly like `game_repr` (parity hook);
-// out_bf16: padded-row layout [rows][64] feeding the first convolution.
+// out_bf16: dense rows [guard + position * N*N + square][64] feeding the first convolution.
 __global__ void __launch_bounds__(32 * WPB) k_encode(const TzState* states, const int* count_ptr, int count_max, int n,
                                                       int half_komi, float* out_f32, __nv_bfloat16* out_bf16,
                                                       int guard) {
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(32 * WPB) k_encode(const TzState* states, cons
     if (q >= count) return;
     TzState* st = &s_state[warp];
     warp_load_state(st, &states[q], lane);
-    const int nn = n * n, ss = 2 * n + 3, C = 2 * (ss + 2) + 2, w1 = n + 1;
+    const int nn = n * n, ss = 2 * n + 3, C = 2 * (ss + 2) + 2;
     const int me = st->to_move, other = me ^ 1;
     const TzBoards b = warp_boards(st, nn, lane);
     const int s0 = n == 3 ? 10 : n == 4 ? 15 : n == 5 ? 21 : 30;
@@ -105,8 +106,7 @@ __global__ void __launch_bounds__(32 * WPB) k_encode(const TzState* states, cons
             for (int c = 0; c < C; c++) o[(size_t)c * nn] = v[c];
         }
         if (out_bf16) {
-            const int row = sq / n, col = sq % n;
-            const size_t r = (size_t)guard + (size_t)q * (w1 * w1) + (size_t)(row + 1) * w1 + col;
+            const size_t r = (size_t)guard + (size_t)q * nn + sq;
             uint4* o = reinterpret_cast<uint4*>(out_bf16 + r * CIN_PAD);
 #pragma unroll
             for (int j = 0; j < CIN_PAD / 8; j++)
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(32 * WPB) k_heads_gather(const __nv_bfloat16* 
     const int q = blockIdx.x * WPB + warp;
     const int count = count_ptr ? *count_ptr : count_max;
     if (q >= count) return;
-    const int nn = n * n, w1 = n + 1;
+    const int nn = n * n;
     // lane owns channels lane*8 .. lane*8+7
     float wv[8], wu[8];
 #pragma unroll
@@ -151,8 +151,7 @@ __global__ void __launch_bounds__(32 * WPB) k_heads_gather(const __nv_bfloat16* 
     const float* lin_u = head_misc + 2 + 36;
     float acc_v = 0.0f, acc_u = 0.0f;
     for (int sq = 0; sq < nn; sq++) {
-        const int row = sq / n, col = sq % n;
-        const size_t r = (size_t)guard + (size_t)q * (w1 * w1) + (size_t)(row + 1) * w1 + col;
+        const size_t r = (size_t)guard + (size_t)q * nn + sq;
         const uint4 x = *reinterpret_cast<const uint4*>(act + r * FILTERS + lane * 8);
         const uint32_t w[4] = {x.x, x.y, x.z, x.w};
         float dv = 0.0f, du = 0.0f;
@@ -229,12 +228,14 @@ static int upload_conv(NnState* s, ConvLayer* L, const HostTensor* w, const Host
     }
     const int kblocks = cin_pad / 64;
     std::vector<uint16_t> blk((size_t)kblocks * 9 * 8 * 256 * 8, 0);
+    // blocks are stored in the order the kernel consumes the taps: centre first, then the rest
     for (int co = 0; co < cout; co++)
         for (int ci = 0; ci < cin; ci++)
-            for (int tap = 0; tap < 9; tap++) {
+            for (int ti = 0; ti < 9; ti++) {
+                const int tap = ti == 0 ? 4 : (ti <= 4 ? ti - 1 : ti);  // tap = ky * 3 + kx
                 const float v = w->data[((size_t)co * cin + ci) * 9 + tap] * scale[co];
                 const int kb = ci / 64, kc = (ci % 64) / 8, e = ci % 8;
-                blk[((((size_t)kb * 9 + tap) * 8 + kc) * 256 + co) * 8 + e] = f32_to_bf16(v);
+                blk[((((size_t)kb * 9 + ti) * 8 + kc) * 256 + co) * 8 + e] = f32_to_bf16(v);
             }
     void* dw = nullptr;
     void* db = nullptr;
@@ -369,9 +370,8 @@ int nn_set_weights(tz_handle* h, const char* const* names, const float* const* d
     }
 #undef NEED
     // activation buffers: guard rows + all boards, rounded up to whole tiles, + halo
-    const int w1 = n + 1;
     s->max_positions = h->d.G;
-    const size_t used = (size_t)s->max_positions * w1 * w1;
+    const size_t used = (size_t)s->max_positions * nn;
     s->rows = conv::HALO + ((used + conv::TILE_M - 1) / conv::TILE_M) * conv::TILE_M + 2 * conv::HALO;
     auto dalloc = [&](void** p, size_t bytes) -> bool {
         if (cudaMalloc(p, bytes) != cudaSuccess) return false;
@@ -383,6 +383,25 @@ int nn_set_weights(tz_handle* h, const char* const* names, const float* const* d
         !dalloc((void**)&s->logits_full, (size_t)s->max_positions * nn * FILTERS * 4)) {
         nn_free(h);
         NN_FAIL(TZ_ENOMEM, "cudaMalloc activations");
+    }
+    {
+        // lane masks: bit i of mask[start][tap] is set when tile row i (board square (start + i) mod nn)
+        // has no (dy,dx) neighbour on the board
+        std::vector<uint32_t> mk((size_t)nn * 9 * 4, 0);
+        for (int start = 0; start < nn; start++)
+            for (int tap = 0; tap < 9; tap++) {
+                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                for (int i = 0; i < conv::TILE_M; i++) {
+                    const int sq = (start + i) % nn, y = sq / n, x = sq % n;
+                    const bool off = y + dy < 0 || y + dy >= n || x + dx < 0 || x + dx >= n;
+                    if (off) mk[((size_t)start * 9 + tap) * 4 + i / 32] |= 1u << (i % 32);
+                }
+            }
+        if (!dalloc((void**)&s->masks, mk.size() * 4) ||
+            cudaMemcpy(s->masks, mk.data(), mk.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+            nn_free(h);
+            NN_FAIL(TZ_ENOMEM, "cudaMalloc masks");
+        }
     }
     if (cudaFuncSetAttribute(conv::k_conv3x3, cudaFuncAttributeMaxDynamicSharedMemorySize, conv::SMEM_BYTES) !=
         cudaSuccess) {
@@ -415,8 +434,8 @@ static void launch_conv(tz_handle* h, const ConvLayer& L, const __nv_bfloat16* i
     p.count_max = count_max;
     p.n = s->n;
     p.guard = conv::HALO;
-    const int w1 = s->n + 1;
-    const int max_tiles = (count_max * w1 * w1 + conv::TILE_M - 1) / conv::TILE_M;
+    p.masks = s->masks;
+    const int max_tiles = (count_max * s->n * s->n + conv::TILE_M - 1) / conv::TILE_M;
     const int grid = max_tiles < s->sm_count ? max_tiles : s->sm_count;
     conv::k_conv3x3<<<grid > 0 ? grid : 1, conv::THREADS, conv::SMEM_BYTES, h->stream>>>(p);
 }
@@ -486,14 +505,11 @@ int nn_encode_planes(tz_handle* h, const TzState* states, int count, float* out_
 // debug read-back: which = 0 act_x, 1 act_t, 2 planes; f32 [count][n*n][channels]
 __global__ void k_unpad(const __nv_bfloat16* buf, int channels, int count, int n, int guard, float* out) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int nn = n * n, w1 = n + 1;
+    const int nn = n * n;
     if (idx >= (size_t)count * nn * channels) return;
     const int c = (int)(idx % channels);
-    const size_t cell = idx / channels;
-    const int sq = (int)(cell % nn);
-    const size_t q = cell / nn;
-    const size_t r = (size_t)guard + q * (w1 * w1) + (size_t)(sq / n + 1) * w1 + sq % n;
-    out[idx] = __bfloat162float(buf[r * channels + c]);
+    const size_t cell = idx / channels;  // position * nn + square
+    out[idx] = __bfloat162float(buf[((size_t)guard + cell) * channels + c]);
 }
 
 int nn_debug_read(tz_handle* h, int which, int count, float* out_dev) {
@@ -503,5 +519,33 @@ int nn_debug_read(tz_handle* h, int which, int count, float* out_dev) {
     const int channels = which == 2 ? CIN_PAD : FILTERS;
     const size_t total = (size_t)count * s->n * s->n * channels;
     k_unpad<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(buf, channels, count, s->n, conv::HALO, out_dev);
+    return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
+}
+
+// test / tuning hook: time `reps` repetitions of one residual block (2 tower convolutions) over
+// `count` positions with CUDA events; returns the mean milliseconds per convolution launch
+int nn_time_tower(tz_handle* h, int count, int reps, double* ms_per_conv) {
+    NnState* s = h->nn;
+    if (!s) return TZ_ENOWEIGHTS;
+    if (count <= 0 || count > s->max_positions || reps <= 0) return TZ_EINVAL;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    for (int i = 0; i < 2; i++) {
+        launch_conv(h, s->tower[0], s->act_x, nullptr, s->act_t, nullptr, 1, nullptr, count);
+        launch_conv(h, s->tower[1], s->act_t, s->act_x, s->act_x, nullptr, 1, nullptr, count);
+    }
+    cudaEventRecord(a, h->stream);
+    for (int i = 0; i < reps; i++) {
+        launch_conv(h, s->tower[0], s->act_x, nullptr, s->act_t, nullptr, 1, nullptr, count);
+        launch_conv(h, s->tower[1], s->act_t, s->act_x, s->act_x, nullptr, 1, nullptr, count);
+    }
+    cudaEventRecord(b, h->stream);
+    cudaEventSynchronize(b);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *ms_per_conv = (double)ms / (2.0 * reps);
     return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
 }

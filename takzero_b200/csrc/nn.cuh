@@ -14,3 +14,4 @@ int nn_forward(tz_handle* h, const TzState* states, const int* count_ptr, int co
 int nn_encode_planes(tz_handle* h, const TzState* states, int count, float* out_f32);
 void nn_set_layer_limit(tz_handle* h, int limit);
 int nn_debug_read(tz_handle* h, int which, int count, float* out_dev);
+int nn_time_tower(tz_handle* h, int count, int reps, double* ms_per_conv);

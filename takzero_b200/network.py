@@ -29,6 +29,7 @@ def _declare():
     capi.declare("tz_encode_planes", [vp, vp, i32, vp], i32)
     capi.declare("tz_debug_layer_limit", [vp, i32], i32)
     capi.declare("tz_debug_activations", [vp, i32, i32, vp], i32)
+    capi.declare("tz_debug_time_tower", [vp, i32, i32, C.POINTER(C.c_double)], i32)
     _declared = True
 
 
@@ -84,3 +85,11 @@ def debug_activations(mcts: capi.BatchedMCTS, which: int, count: int) -> np.ndar
     out = np.zeros((count, mcts.n * mcts.n, ch), dtype=np.float32)
     capi._check(capi.lib().tz_debug_activations(mcts.handle, which, count, capi._ptr(out)))
     return out
+
+
+def time_tower(mcts: capi.BatchedMCTS, count: int, reps: int = 20) -> float:
+    """Mean milliseconds per tower-convolution launch over `count` positions (tuning hook)."""
+    _declare()
+    ms = C.c_double()
+    capi._check(capi.lib().tz_debug_time_tower(mcts.handle, count, reps, C.byref(ms)))
+    return ms.value
