@@ -154,7 +154,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(1),
+        "config": workload_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "restated CPU baseline (oracle port), not the reference binary: no Rust toolchain in the image",
@@ -193,6 +193,7 @@ def main():
 
     from takzero_b200 import build as tz_build
     from takzero_b200 import capi, network, weights
+    from takzero_b200 import distributed as tzd
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -210,24 +211,16 @@ def main():
     tz_build.build()
 
     G, k, budget = GAMES_PER_GPU, SAMPLED_ACTIONS, SEARCH_BUDGET
-    m = capi.BatchedMCTS(BOARD_N, HALF_KOMI, G, device=local_rank, game_base=rank * G)
+    game_base, _ = tzd.shard(rank, world, G)
+    m = capi.BatchedMCTS(BOARD_N, HALF_KOMI, G, device=local_rank, game_base=game_base)
     M = m.move_stride
+    cuda_dev = torch.device("cuda", local_rank)
 
-    # weights: rank 0 initialises, NCCL broadcasts the blob (one "generation")
+    # weights: every rank builds the tensor list, rank 0's values are broadcast over NCCL (one "generation")
     t_w = time.perf_counter()
-    tensors = weights.random_init(BOARD_N, seed=123)
+    tensors = weights.random_init(BOARD_N, seed=123 + rank)
     if world > 1:
-        names = list(tensors)
-        flat = torch.from_numpy(np.concatenate([tensors[n].ravel() for n in names])).cuda()
-        if rank != 0:
-            flat.zero_()
-        dist.broadcast(flat, src=0)
-        host = flat.cpu().numpy()
-        off = 0
-        for n in names:
-            size = tensors[n].size
-            tensors[n] = host[off:off + size].reshape(tensors[n].shape).copy()
-            off += size
+        tensors = tzd.broadcast_weights(tensors, src=0, device=cuda_dev)
     network.set_weights(m, tensors)
     weight_load_s = time.perf_counter() - t_w
     m.set_agent(capi.AGENT_NETWORK)
@@ -269,12 +262,9 @@ def main():
     known = c1.known - c0.known
     positions = G * args.steps
     if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        tot = torch.tensor([sims, evals, known, positions, launches], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        sims, evals, known, positions, launches = (int(x) for x in tot.tolist())
+        ms = tzd.max_over_ranks([ms], cuda_dev)[0]
+        sims, evals, known, positions, launches = (
+            int(x) for x in tzd.sum_counters([sims, evals, known, positions, launches], cuda_dev))
     value = sims / (ms / 1000.0)
 
     # ---- roofline of the dominant kernel (tower convolution, tcgen05) ---------------------------------
@@ -344,12 +334,8 @@ def main():
         ce1 = m.counters()
         esims = ce1.simulations - ce0.simulations
         if dist is not None:
-            t = torch.tensor([ems, wall_ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ems, wall_ms = (float(x) for x in t.tolist())
-            tot = torch.tensor([esims], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-            esims = int(tot.item())
+            ems, wall_ms = tzd.max_over_ranks([ems, wall_ms], cuda_dev)
+            esims = int(tzd.sum_counters([esims], cuda_dev)[0])
         e2e = {"value": esims / (ems / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": ems / args.steps, "wall_ms_per_step": wall_ms / args.steps,
                "api": "tz_gumbel_sequential_halving + tz_targets + tz_select_selfplay + tz_step + tz_restart_terminal "
