@@ -27,6 +27,7 @@
 //   warps 4-7 epilogue    tcgen05.ld -> bias (+ residual) (+ ReLU) -> bf16 / f32 stores
 #pragma once
 #include <cuda_bf16.h>
+#include <stdio.h>
 #include <stdint.h>
 
 namespace conv {
@@ -36,6 +37,18 @@ constexpr int HALO = 8;                       // >= N+1 for N <= 6
 constexpr int A_ROWS = TILE_M + 2 * HALO;     // 144
 constexpr int A_KC_PITCH = (A_ROWS + 1) * 16; // 2320 B: +1 row keeps cp.async writes bank-conflict free
 constexpr int A_STAGE_BYTES = 8 * A_KC_PITCH; // 18560 B = one 64-channel block
+#ifndef TZ_DEBUG_SKIP_RES
+#define TZ_DEBUG_SKIP_RES 0
+#endif
+#ifndef TZ_DEBUG_SKIP_STORE
+#define TZ_DEBUG_SKIP_STORE 0
+#endif
+#ifndef TZ_EPI_STAGED
+#define TZ_EPI_STAGED 0
+#endif
+#ifndef TZ_ROLE_SWAP
+#define TZ_ROLE_SWAP 1
+#endif
 #ifndef TZ_A_STAGES
 #define TZ_A_STAGES 4
 #endif
@@ -48,9 +61,19 @@ constexpr int B_STAGE_BYTES = 8 * B_KC_PITCH; // 32768 B = 64 K x 256 N
 constexpr int B_STAGES = TZ_B_STAGES;
 constexpr int N_OUT = 256;
 constexpr int THREADS = 256;
+// Warp roles.  The SM sub-partition arbiter favours the highest warp id, so the single-thread producer /
+// MMA roles sit on warps 4-7 and the instruction-heavy epilogue on warps 0-3 (warp w may only touch TMEM
+// lanes 32*(w%4)..+31, so any four warps with distinct w%4 can be the epilogue).
+#if TZ_ROLE_SWAP
+constexpr int W_EPI0 = 0, W_APROD = 4, W_BPROD = 5, W_MMA = 6, W_ALLOC = 7;
+#else
+constexpr int W_EPI0 = 4, W_APROD = 0, W_BPROD = 1, W_MMA = 2, W_ALLOC = 3;
+#endif
 constexpr int MASK_BYTES = 36 * 9 * 16;         // [N*N][9 taps] 128-bit lane masks
-constexpr int SMEM_BYTES =
-    A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + 1024 /*bias*/ + 256 /*barriers*/ + MASK_BYTES;
+constexpr int EPI_PITCH = 36;                   // floats per staged row (32 + 4: conflict-free 16-B accesses)
+constexpr int EPI_BYTES = TILE_M * EPI_PITCH * 4;  // f32 staging of one 32-column chunk of the tile
+constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + 1024 /*bias*/ +
+                           256 /*barriers*/ + MASK_BYTES + EPI_BYTES;
 
 struct Params {
     const __nv_bfloat16* in;        // [rows][cin] activations, dense rows
@@ -86,6 +109,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+#ifdef TZ_DEBUG_TIMING
+#define TWAIT(acc, stmt)                 \
+    do {                                 \
+        const long long t0_ = clock64(); \
+        stmt;                            \
+        acc += clock64() - t0_;          \
+    } while (0)
+#else
+#define TWAIT(acc, stmt) stmt
+#endif
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -163,6 +196,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3(const Params p) {
     const uint32_t t_full = b_empty + 8 * B_STAGES, t_empty = t_full + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * A_STAGES + 2 * B_STAGES + 4);
     uint4* s_masks = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(bars) + 256);
+    float* s_epi = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_masks) + MASK_BYTES);
 
     const int count = p.count_ptr ? *p.count_ptr : p.count_max;
     const int nn = p.n * p.n;
@@ -185,7 +219,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3(const Params p) {
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 3) {
+    if (warp == W_ALLOC) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(512)
                      : "memory");
@@ -198,7 +232,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3(const Params p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == W_APROD) {
         // ---- A producer: halo tile rows [guard + 128 t - 8, +144), one 64-channel block per stage
         int stage = 0, phase = 0, pending = -1;
         const size_t row_bytes = (size_t)p.cin * 2;
@@ -209,12 +243,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3(const Params p) {
                 mbar_wait(a_empty + 8 * stage, phase ^ 1);
                 const uint32_t dst = smem_u32(a_smem + stage * A_STAGE_BYTES);
                 const uint8_t* src = src_tile + kb * 128;
+#ifndef TZ_DEBUG_NO_A_LOAD  // tuning experiment
 #pragma unroll 4
                 for (int it = 0; it < A_ROWS * 8 / 32; it++) {
                     const int piece = it * 32 + lane;
                     const int row = piece >> 3, kc = piece & 7;
                     cp_async16(dst + kc * A_KC_PITCH + row * 16, src + (size_t)row * row_bytes + kc * 16);
                 }
+#endif
                 cp_async_commit();
                 if (pending >= 0) {
                     // the previous block has landed: publish it to the async proxy (tcgen05 reads)
@@ -236,7 +272,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3(const Params p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(a_full + 8 * pending);
         }
-    } else if (warp == 1) {
+    } else if (warp == W_BPROD) {
         // ---- B producer: weight blocks stream from L2 in exactly the order the MMA consumes them
         if (lane == 0) {
             int stage = 0, phase = 0;
@@ -244,9 +280,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3(const Params p) {
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w);
                 for (int blk = 0; blk < kblocks * 9; blk++) {
                     mbar_wait(b_empty + 8 * stage, phase ^ 1);
+#ifdef TZ_DEBUG_NO_B_LOAD  // tuning experiment: no weight traffic (results are garbage)
+                    mbar_arrive(b_full + 8 * stage);
+#else
                     mbar_arrive_expect_tx(b_full + 8 * stage, B_STAGE_BYTES);
                     bulk_g2s(smem_u32(b_smem + stage * B_STAGE_BYTES), src + (size_t)blk * B_STAGE_BYTES, B_STAGE_BYTES,
                              b_full + 8 * stage);
+#endif
                     if (++stage == B_STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -254,26 +294,29 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3(const Params p) {
                 }
             }
         }
-    } else if (warp == 2) {
+    } else if (warp == W_MMA) {
         // ---- MMA issuer
         if (lane == 0) {
             // kind::f16: D = f32, A = B = bf16, both K-major, N = 256, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_OUT >> 3) << 17) |
                                    ((uint32_t)(TILE_M >> 4) << 24);
             int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0, it = 0;
+            long long w_t = 0, w_a = 0, w_b = 0;
+            (void)w_t, (void)w_a, (void)w_b;
+            const long long mma_start = clock64();
             for (int t = blockIdx.x; t < tiles; t += gridDim.x, it++) {
                 const int acc = it & 1;
-                mbar_wait(t_empty + 8 * acc, ((it >> 1) & 1) ^ 1);
+                TWAIT(w_t, mbar_wait(t_empty + 8 * acc, ((it >> 1) & 1) ^ 1));
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * N_OUT;
                 const uint4* tile_masks = s_masks + ((size_t)t * TILE_M % nn) * 9;
                 for (int kb = 0; kb < kblocks; kb++) {
-                    mbar_wait(a_full + 8 * a_stage, a_phase);
+                    TWAIT(w_a, mbar_wait(a_full + 8 * a_stage, a_phase));
                     const uint32_t a_base = smem_u32(a_smem + a_stage * A_STAGE_BYTES);
                     // tap order: the centre tap first (no mask, it initialises every lane), then the rest
                     for (int ti = 0; ti < 9; ti++) {
                         const int tap = ti == 0 ? 4 : (ti <= 4 ? ti - 1 : ti);
-                        mbar_wait(b_full + 8 * b_stage, b_phase);
+                        TWAIT(w_b, mbar_wait(b_full + 8 * b_stage, b_phase));
                         tc_fence_after();
                         const int off = (tap / 3 - 1) * p.n + (tap % 3 - 1);
                         const uint4 mask = tile_masks[tap];
@@ -283,7 +326,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3(const Params p) {
                         for (int ks = 0; ks < 4; ks++) {
                             const uint64_t adesc = make_desc(a_tap + ks * 2 * A_KC_PITCH, A_KC_PITCH);
                             const uint64_t bdesc = make_desc(b_base + ks * 2 * B_KC_PITCH, B_KC_PITCH);
+#ifndef TZ_DEBUG_NO_MMA  // tuning experiment: data movement only
                             tc_mma(tmem_d, adesc, bdesc, idesc, (kb | ti | ks) != 0, mask);
+#endif
                         }
                         tc_commit(b_empty + 8 * b_stage);
                         if (++b_stage == B_STAGES) {
@@ -299,11 +344,98 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3(const Params p) {
                 }
                 tc_commit(t_full + 8 * acc);
             }
+#ifdef TZ_DEBUG_TIMING
+            if (blockIdx.x == 0 || blockIdx.x == 77)
+                printf("cta %d mma: tiles %d total %lld wait_tmem %lld wait_a %lld wait_b %lld\n", blockIdx.x, it,
+                       clock64() - mma_start, w_t, w_a, w_b);
+#endif
         }
-    } else if (warp >= 4) {
-        // ---- epilogue: TMEM lane = tile row; warp w reads lanes 32*(w%4)..+31
+    } else if (warp >= W_EPI0 && warp < W_EPI0 + 4) {
+        // ---- epilogue: TMEM lane = tile row; warp w reads lanes 32*(w%4)..+31.
+        // Each 32-column chunk goes TMEM -> registers (+bias) -> a per-warp f32 staging tile in shared
+        // memory -> coalesced copy-out (4 lanes per row for bf16, 8 for f32), where the residual is
+        // loaded with the same coalesced pattern, added in f32, and ReLU / rounding are applied.  A warp
+        // store then touches 8 (or 4) 128-B lines instead of 32.
+#if TZ_EPI_STAGED
+        const int wq = warp & 3;
+        float* stg = s_epi + wq * 32 * EPI_PITCH;
+        int it = 0;
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x, it++) {
+            const int acc = it & 1;
+            const int rel0 = t * TILE_M + wq * 32;  // first row of this warp (row = position * n*n + square)
+            mbar_wait(t_full + 8 * acc, (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * N_OUT;
+#ifndef TZ_DEBUG_NO_EPILOGUE  // tuning experiment
+#pragma unroll 1
+            for (int c0 = 0; c0 < N_OUT; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+                tmem_ld_wait();
+                float4* srow = reinterpret_cast<float4*>(stg + lane * EPI_PITCH);
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    srow[j] = make_float4(__uint_as_float(v[4 * j]) + s_bias[c0 + 4 * j],
+                                          __uint_as_float(v[4 * j + 1]) + s_bias[c0 + 4 * j + 1],
+                                          __uint_as_float(v[4 * j + 2]) + s_bias[c0 + 4 * j + 2],
+                                          __uint_as_float(v[4 * j + 3]) + s_bias[c0 + 4 * j + 3]);
+                __syncwarp();
+                if (p.out_act) {
+                    const int piece = lane & 3;  // 8 channels
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int r = (lane >> 2) + 8 * k;
+                        const int rel = rel0 + r;
+                        if (rel < rows_used) {
+                            const size_t goff = (size_t)(p.guard + rel) * N_OUT + c0 + piece * 8;
+                            const float4 a0 = *reinterpret_cast<const float4*>(stg + r * EPI_PITCH + piece * 8);
+                            const float4 a1 = *reinterpret_cast<const float4*>(stg + r * EPI_PITCH + piece * 8 + 4);
+                            float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                            if (p.residual && !TZ_DEBUG_SKIP_RES) {
+                                const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + goff);
+                                const uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                                for (int e = 0; e < 4; e++) {
+                                    f[e * 2] += __uint_as_float(w[e] << 16);
+                                    f[e * 2 + 1] += __uint_as_float(w[e] & 0xffff0000u);
+                                }
+                            }
+                            if (p.relu) {
+#pragma unroll
+                                for (int e = 0; e < 8; e++) f[e] = fmaxf(f[e], 0.0f);
+                            }
+                            if (!TZ_DEBUG_SKIP_STORE)
+                                *reinterpret_cast<uint4*>(p.out_act + goff) =
+                                    make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                                               pack_bf16(f[6], f[7]));
+                        }
+                    }
+                }
+                if (p.out_f32) {
+                    const int piece = lane & 7;  // 4 channels
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const int r = (lane >> 3) + 4 * k;
+                        const int rel = rel0 + r;
+                        if (rel < rows_used) {
+                            float4 a = *reinterpret_cast<const float4*>(stg + r * EPI_PITCH + piece * 4);
+                            if (p.relu) a = make_float4(fmaxf(a.x, 0.0f), fmaxf(a.y, 0.0f), fmaxf(a.z, 0.0f), fmaxf(a.w, 0.0f));
+                            *reinterpret_cast<float4*>(p.out_f32 + (size_t)rel * N_OUT + c0 + piece * 4) = a;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+#endif
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty + 8 * acc);
+        }
+#else
         const int wq = warp & 3;
         int it = 0;
+        long long e_wait = 0, e_busy = 0;
+        (void)e_wait, (void)e_busy;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x, it++) {
             const int acc = it & 1;
             const int tr = wq * 32 + lane;
@@ -311,8 +443,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3(const Params p) {
             const bool valid = rel < rows_used;
             const size_t grow = (size_t)(p.guard + rel);
             const size_t crow = (size_t)rel;
-            mbar_wait(t_full + 8 * acc, (it >> 1) & 1);
+            TWAIT(e_wait, mbar_wait(t_full + 8 * acc, (it >> 1) & 1));
             tc_fence_after();
+#ifdef TZ_DEBUG_TIMING
+            const long long e0 = clock64();
+#endif
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * N_OUT;
 #pragma unroll 1
             for (int c0 = 0; c0 < N_OUT; c0 += 32) {
@@ -357,11 +492,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3(const Params p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(t_empty + 8 * acc);
+#ifdef TZ_DEBUG_TIMING
+            e_busy += clock64() - e0;
+#endif
         }
+#ifdef TZ_DEBUG_TIMING
+        if ((blockIdx.x == 0 || blockIdx.x == 77) && lane == 0 && wq == 1)
+            printf("cta %d epi warp %d: tiles %d wait_full %lld busy %lld\n", blockIdx.x, warp, it, e_wait, e_busy);
+#endif
+#endif
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 3) {
+    if (warp == W_ALLOC) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }

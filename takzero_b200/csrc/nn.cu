@@ -38,6 +38,7 @@ struct NnState {
     __nv_bfloat16* planes = nullptr;  // [rows][64]
     __nv_bfloat16* act_x = nullptr;   // [rows][256]
     __nv_bfloat16* act_t = nullptr;   // [rows][256]
+    __nv_bfloat16* act_scratch = nullptr;  // tuning hook only
     float* logits_full = nullptr;     // [max_positions * n*n][256]
     uint4* masks = nullptr;           // [n*n][9] disable-output-lane masks (conv_tcgen05.cuh)
     int layer_limit = -1;             // debug: stop the tower after this many convolutions
@@ -523,22 +524,29 @@ int nn_debug_read(tz_handle* h, int which, int count, float* out_dev) {
 }
 
 // test / tuning hook: time `reps` repetitions of one residual block (2 tower convolutions) over
-// `count` positions with CUDA events; returns the mean milliseconds per convolution launch
+// `count` positions with CUDA events; returns the mean milliseconds per convolution launch.  The block
+// stream X is only read (the second convolution writes to a scratch buffer), so the data stay whatever
+// the last tz_evaluate left there -- realistic activations, which matters under the power cap.
 int nn_time_tower(tz_handle* h, int count, int reps, double* ms_per_conv) {
     NnState* s = h->nn;
     if (!s) return TZ_ENOWEIGHTS;
     if (count <= 0 || count > s->max_positions || reps <= 0) return TZ_EINVAL;
+    if (!s->act_scratch) {
+        if (cudaMalloc((void**)&s->act_scratch, s->rows * FILTERS * 2) != cudaSuccess) return TZ_ENOMEM;
+        s->allocs.push_back(s->act_scratch);
+        cudaMemset(s->act_scratch, 0, s->rows * FILTERS * 2);
+    }
     cudaEvent_t a, b;
     cudaEventCreate(&a);
     cudaEventCreate(&b);
     for (int i = 0; i < 2; i++) {
         launch_conv(h, s->tower[0], s->act_x, nullptr, s->act_t, nullptr, 1, nullptr, count);
-        launch_conv(h, s->tower[1], s->act_t, s->act_x, s->act_x, nullptr, 1, nullptr, count);
+        launch_conv(h, s->tower[1], s->act_t, s->act_x, s->act_scratch, nullptr, 1, nullptr, count);
     }
     cudaEventRecord(a, h->stream);
     for (int i = 0; i < reps; i++) {
         launch_conv(h, s->tower[0], s->act_x, nullptr, s->act_t, nullptr, 1, nullptr, count);
-        launch_conv(h, s->tower[1], s->act_t, s->act_x, s->act_x, nullptr, 1, nullptr, count);
+        launch_conv(h, s->tower[1], s->act_t, s->act_x, s->act_scratch, nullptr, 1, nullptr, count);
     }
     cudaEventRecord(b, h->stream);
     cudaEventSynchronize(b);
