@@ -319,7 +319,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3(const Params p) {
                         TWAIT(w_b, mbar_wait(b_full + 8 * b_stage, b_phase));
                         tc_fence_after();
                         const int off = (tap / 3 - 1) * p.n + (tap % 3 - 1);
+#ifdef TZ_DEBUG_NO_MASK
+                        const uint4 mask = make_uint4(0, 0, 0, 0);
+#else
                         const uint4 mask = tile_masks[tap];
+#endif
                         const uint32_t a_tap = a_base + (HALO + off) * 16;
                         const uint32_t b_base = smem_u32(b_smem + b_stage * B_STAGE_BYTES);
 #pragma unroll
@@ -449,6 +453,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3(const Params p) {
             const long long e0 = clock64();
 #endif
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * N_OUT;
+#ifndef TZ_DEBUG_NO_EPILOGUE
 #pragma unroll 1
             for (int c0 = 0; c0 < N_OUT; c0 += 32) {
                 uint32_t v[32];
@@ -489,6 +494,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3(const Params p) {
                     }
                 }
             }
+#endif
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(t_empty + 8 * acc);

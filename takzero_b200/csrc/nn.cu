@@ -7,11 +7,13 @@
 // The 3x3 convolutions run on tcgen05 (conv_tcgen05.cuh); everything else here is small.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
 #include <vector>
 
+#include "conv_pair_tcgen05.cuh"
 #include "conv_tcgen05.cuh"
 #include "nn.cuh"
 #include "rules.cuh"
@@ -42,6 +44,7 @@ struct NnState {
     float* logits_full = nullptr;     // [max_positions * n*n][256]
     uint4* masks = nullptr;           // [n*n][9] disable-output-lane masks (conv_tcgen05.cuh)
     int layer_limit = -1;             // debug: stop the tower after this many convolutions
+    bool pair = true;                 // CTA-pair kernel (cta_group::2); TZ_CONV_MODE=single selects the 1-CTA kernel
     std::vector<void*> allocs;
     int sm_count = 148;
 };
@@ -236,7 +239,11 @@ static int upload_conv(NnState* s, ConvLayer* L, const HostTensor* w, const Host
                 const int tap = ti == 0 ? 4 : (ti <= 4 ? ti - 1 : ti);  // tap = ky * 3 + kx
                 const float v = w->data[((size_t)co * cin + ci) * 9 + tap] * scale[co];
                 const int kb = ci / 64, kc = (ci % 64) / 8, e = ci % 8;
-                blk[((((size_t)kb * 9 + ti) * 8 + kc) * 256 + co) * 8 + e] = f32_to_bf16(v);
+                // one 32 KB block per (kb, tap): [8 k-chunks][256 n][8]; the CTA-pair kernel wants the two
+                // N halves as separate contiguous 16 KB images: [2][8][128][8]
+                const size_t in_blk = s->pair ? (((size_t)(co / 128) * 8 + kc) * 128 + co % 128) * 8 + e
+                                              : ((size_t)kc * 256 + co) * 8 + e;
+                blk[((size_t)kb * 9 + ti) * (8 * 256 * 8) + in_blk] = f32_to_bf16(v);
             }
     void* dw = nullptr;
     void* db = nullptr;
@@ -274,6 +281,7 @@ int nn_set_weights(tz_handle* h, const char* const* names, const float* const* d
     nn_free(h);
     NnState* s = new NnState();
     h->nn = s;
+    if (const char* mode = getenv("TZ_CONV_MODE")) s->pair = strcmp(mode, "single") != 0;
     const int n = h->d.n, nn = n * n;
     s->n = n;
     s->in_channels = 2 * (2 * n + 3 + 2) + 2;
@@ -373,7 +381,7 @@ int nn_set_weights(tz_handle* h, const char* const* names, const float* const* d
     // activation buffers: guard rows + all boards, rounded up to whole tiles, + halo
     s->max_positions = h->d.G;
     const size_t used = (size_t)s->max_positions * nn;
-    s->rows = conv::HALO + ((used + conv::TILE_M - 1) / conv::TILE_M) * conv::TILE_M + 2 * conv::HALO;
+    s->rows = conv::HALO + ((used + 2 * conv::TILE_M - 1) / (2 * conv::TILE_M)) * (2 * conv::TILE_M) + 2 * conv::HALO;
     auto dalloc = [&](void** p, size_t bytes) -> bool {
         if (cudaMalloc(p, bytes) != cudaSuccess) return false;
         s->allocs.push_back(*p);
@@ -405,7 +413,9 @@ int nn_set_weights(tz_handle* h, const char* const* names, const float* const* d
         }
     }
     if (cudaFuncSetAttribute(conv::k_conv3x3, cudaFuncAttributeMaxDynamicSharedMemorySize, conv::SMEM_BYTES) !=
-        cudaSuccess) {
+            cudaSuccess ||
+        cudaFuncSetAttribute(conv::k_conv3x3_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, conv::P_SMEM_BYTES) !=
+            cudaSuccess) {
         nn_free(h);
         NN_FAIL(TZ_ECUDA, "cudaFuncSetAttribute(k_conv3x3, %d B smem) failed", conv::SMEM_BYTES);
     }
@@ -437,8 +447,14 @@ static void launch_conv(tz_handle* h, const ConvLayer& L, const __nv_bfloat16* i
     p.guard = conv::HALO;
     p.masks = s->masks;
     const int max_tiles = (count_max * s->n * s->n + conv::TILE_M - 1) / conv::TILE_M;
-    const int grid = max_tiles < s->sm_count ? max_tiles : s->sm_count;
-    conv::k_conv3x3<<<grid > 0 ? grid : 1, conv::THREADS, conv::SMEM_BYTES, h->stream>>>(p);
+    if (s->pair) {
+        const int pairs = (max_tiles + 1) / 2, max_pairs = s->sm_count / 2;
+        const int grid = 2 * (pairs < max_pairs ? (pairs > 0 ? pairs : 1) : max_pairs);
+        conv::k_conv3x3_pair<<<grid, conv::THREADS, conv::P_SMEM_BYTES, h->stream>>>(p);
+    } else {
+        const int grid = max_tiles < s->sm_count ? max_tiles : s->sm_count;
+        conv::k_conv3x3<<<grid > 0 ? grid : 1, conv::THREADS, conv::SMEM_BYTES, h->stream>>>(p);
+    }
 }
 
 // states[count] (device), actions/n_actions by position -> logits/value/variance by position.
