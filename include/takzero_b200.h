@@ -232,6 +232,11 @@ TZ_API int tz_set_weights(tz_handle* h, const tz_tensor_t* tensors, int count);
  * count <= n_games positions, actions [count][stride] -> logits [count][stride], values, variances */
 TZ_API int tz_evaluate(tz_handle* h, const tz_state_t* states, int count, const tz_move_t* actions,
                 const int* n_actions, int stride, float* logits, float* values, float* variances);
+/* SimHash novelty (net6_simhash.rs:136-139,203-256): matrix [C*N*N][32] f32 and the optional 2^32-bit set
+ * (the 512 MiB `bitvec.bin` sidecar of the model, LSB-first); bitset NULL = empty set (fresh network), for
+ * which the local uncertainty is MAXIMUM_VARIANCE = 4.0.  tz_simhash_indices = `get_indices` (parity hook). */
+TZ_API int tz_set_simhash(tz_handle* h, const float* matrix, const uint8_t* bitset);
+TZ_API int tz_simhash_indices(tz_handle* h, const tz_state_t* states, int count, uint32_t* out);
 /* game_repr (repr.rs:169-228): f32 planes [count][C][N][N] */
 TZ_API int tz_encode_planes(tz_handle* h, const tz_state_t* states, int count, float* out);
 /* test hooks: stop the tower after `limit` convolutions (-1 = full network); read back an activation

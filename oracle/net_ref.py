@@ -92,6 +92,9 @@ class Net(nn.Module):
         self.policy = Policy(self.cout)
         self.value = Head(n, True)
         self.ube = Head(n, False)
+        # root.randn_standard("simhash_matrix", [input_size, HASH_BITS]) (net6_simhash.rs:136-139)
+        self.simhash_matrix = torch.randn(self.cin * n * n, 32, generator=torch.Generator().manual_seed(seed + 7))
+        self.simhash_set: set = set()  # indices whose bit is set (the reference keeps a 2^32-bit BitBox)
         if randomize_bn:  # exercise the BN folding with non-trivial statistics
             g = torch.Generator().manual_seed(seed + 1)
             for m in self.modules():
@@ -106,6 +109,25 @@ class Net(nn.Module):
     def forward(self, xs):  # forward_t(xs, false), net6_simhash.rs:194-201
         core = self.core(xs)
         return self.policy(core), self.value(core), self.ube(core)
+
+    @torch.no_grad()
+    def simhash_dots(self, xs):
+        """get_indices (net6_simhash.rs:203-234) up to the sign test: the side-to-move plane is zeroed."""
+        xs = xs.clone()
+        xs[:, self.cin - 2] = 0.0
+        return xs.reshape(xs.shape[0], -1) @ self.simhash_matrix
+
+    def get_indices(self, xs) -> np.ndarray:
+        dots = self.simhash_dots(xs).numpy()
+        bits = (~(dots < 0.0)).astype(np.uint64)
+        return (bits << np.arange(32, dtype=np.uint64)).sum(axis=1).astype(np.uint32)
+
+    def bitset_bytes(self) -> np.ndarray:
+        """The reference's bitvec.bin image: 2^29 bytes, bit i of the set = byte i/8, bit i%8."""
+        b = np.zeros(1 << 29, dtype=np.uint8)
+        for i in self.simhash_set:
+            b[i >> 3] |= 1 << (i & 7)
+        return b
 
     def tensors(self) -> Dict[str, np.ndarray]:
         """Named f32 tensors in the layout tz_set_weights documents."""
@@ -124,7 +146,7 @@ class Net(nn.Module):
         for i, acts in enumerate(actions):
             idx = torch.tensor([O.move_index(n, a) for a in acts], dtype=torch.long)
             out_logits.append(policy[i, idx].numpy().astype(np.float32))
-        local = torch.full((len(envs),), MAXIMUM_VARIANCE)
+        local = torch.tensor([0.0 if int(i) in self.simhash_set else MAXIMUM_VARIANCE for i in self.get_indices(xs)])
         unc = torch.clamp(torch.maximum(torch.exp(ube.view(-1)), local), 0.0, MAXIMUM_VARIANCE)
         return out_logits, values.view(-1).numpy().astype(np.float32), unc.numpy().astype(np.float32)
 

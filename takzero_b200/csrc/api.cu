@@ -927,3 +927,29 @@ extern "C" TZ_API int tz_debug_time_tower(tz_handle* h, int count, int reps, dou
     if (rc) return fail(rc, "tz_debug_time_tower failed (weights set? count <= n_games?)");
     return TZ_OK;
 }
+
+extern "C" TZ_API int tz_set_simhash(tz_handle* h, const float* matrix, const uint8_t* bitset) {
+    CHECK_H(h);
+    if (!matrix) return fail(TZ_EINVAL, "null matrix");
+    CU(cudaStreamSynchronize(h->stream));
+    const int rc = nn_set_simhash(h, matrix, bitset);
+    if (rc) return fail(rc, "tz_set_simhash failed (tz_set_weights first; the set needs 512 MiB of HBM)");
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_simhash_indices(tz_handle* h, const tz_state_t* states, int count, uint32_t* out) {
+    CHECK_H(h);
+    if (!states || !out || count <= 0) return fail(TZ_EINVAL, "bad argument");
+    Scratch s;
+    TzState* ds;
+    uint32_t* dout;
+    CU(s.get(&ds, (size_t)count));
+    CU(s.get(&dout, (size_t)count));
+    CU(cudaMemcpyAsync(ds, states, (size_t)count * sizeof(TzState), cudaMemcpyHostToDevice, h->stream));
+    const int rc = nn_simhash_indices(h, ds, count, dout);
+    if (rc) return fail(rc, "tz_simhash_indices needs tz_set_simhash first");
+    CU(cudaMemcpyAsync(out, dout, (size_t)count * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return TZ_OK;
+}

@@ -43,6 +43,9 @@ struct NnState {
     __nv_bfloat16* act_scratch = nullptr;  // tuning hook only
     float* logits_full = nullptr;     // [max_positions * n*n][256]
     uint4* masks = nullptr;           // [n*n][9] disable-output-lane masks (conv_tcgen05.cuh)
+    float* simhash_matrix = nullptr;  // [C*N*N][32] (net6_simhash.rs:136-139), optional
+    uint32_t* simhash_set = nullptr;  // 2^32-bit set (bitvec.bin), optional; absent = empty set
+    uint32_t* simhash_idx = nullptr;  // [max_positions] hash index of each queued position
     int layer_limit = -1;             // debug: stop the tower after this many convolutions
     bool pair = true;                 // CTA-pair kernel (cta_group::2); TZ_CONV_MODE=single selects the 1-CTA kernel
     std::vector<void*> allocs;
@@ -120,6 +123,61 @@ __global__ void __launch_bounds__(32 * WPB) k_encode(const TzState* states, cons
     }
 }
 
+// ---- SimHash novelty index (net6_simhash.rs:203-234 `get_indices`) ---------------------------------
+
+// One warp per position, lane = hash bit: dot of the f32 planes (side-to-move plane zeroed) with column
+// `lane` of the [C*N*N][32] matrix; bit set when the dot is >= 0; index = sum of 2^bit.
+__global__ void __launch_bounds__(32 * WPB) k_simhash(const TzState* states, const int* count_ptr, int count_max, int n,
+                                                       int half_komi, const float* matrix, uint32_t* out_idx) {
+    __shared__ TzState s_state[WPB];
+    __shared__ float s_planes[WPB][36 * 36];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * WPB + warp;
+    const int count = count_ptr ? *count_ptr : count_max;
+    if (q >= count) return;
+    TzState* st = &s_state[warp];
+    warp_load_state(st, &states[q], lane);
+    const int nn = n * n, ss = 2 * n + 3, C = 2 * (ss + 2) + 2;
+    float* x = s_planes[warp];
+    for (int i = lane; i < C * nn; i += 32) x[i] = 0.0f;
+    __syncwarp();
+    const int me = st->to_move, other = me ^ 1;
+    const TzBoards b = warp_boards(st, nn, lane);
+    const int s0 = n == 3 ? 10 : n == 4 ? 15 : n == 5 ? 21 : 30;
+    const int c0 = n >= 5 ? 1 : 0;
+    const float r0 = __fdiv_rn((float)st->stones[me], (float)s0);
+    const float r1 = c0 ? __fdiv_rn((float)st->caps[me], (float)c0) : 0.0f;
+    const float r2 = __fdiv_rn((float)st->stones[other], (float)s0);
+    const float r3 = c0 ? __fdiv_rn((float)st->caps[other], (float)c0) : 0.0f;
+    const float fcd = __fsub_rn((float)(__popcll(b.flat[0]) - __popcll(b.flat[1])), __fdiv_rn((float)half_komi, 2.0f));
+    const float fcd_sq = __fdiv_rn(fcd, (float)nn);
+    for (int sq = lane; sq < nn; sq += 32) {
+        const int h = st->height[sq];
+        if (h > 0) {
+            const uint64_t stack = st->stack[sq];
+            const int top_col = (int)((stack >> (h - 1)) & 1ull);
+            x[(st->top[sq] + (top_col != me ? ss : 0)) * nn + sq] = 1.0f;
+            for (int i = 0; i < ss - 3 && h - 2 - i >= 0; i++) {
+                const int col = (int)((stack >> (h - 2 - i)) & 1ull);
+                x[(3 + i + (col != me ? ss : 0)) * nn + sq] = 1.0f;
+            }
+        }
+        const int base = 2 * ss;
+        x[(base + 0) * nn + sq] = r0;
+        x[(base + 1) * nn + sq] = r1;
+        x[(base + 2) * nn + sq] = r2;
+        x[(base + 3) * nn + sq] = r3;
+        // plane base + 4 (black to move) is zeroed for the hash (net6_simhash.rs:209-222)
+        x[(base + 5) * nn + sq] = fcd_sq;
+    }
+    __syncwarp();
+    float dot = 0.0f;
+    const int total = C * nn;
+    for (int j = 0; j < total; j++) dot = fmaf(x[j], matrix[(size_t)j * 32 + lane], dot);
+    const uint32_t bits = __ballot_sync(0xffffffffu, !(dot < 0.0f));
+    if (lane == 0) out_idx[q] = bits;
+}
+
 // ---- heads + legal-logit gather ------------------------------------------------------------------
 
 // network/repr.rs:49-71 `move_index` split into (channel, square)
@@ -137,6 +195,7 @@ __global__ void __launch_bounds__(32 * WPB) k_heads_gather(const __nv_bfloat16* 
                                                             const float* head_w, const float* head_misc,
                                                             const uint16_t* actions, const int* n_actions,
                                                             const int* count_ptr, int count_max, int n, int M, int guard,
+                                                            const uint32_t* simhash_set, const uint32_t* simhash_idx,
                                                             float* out_logits, float* out_value, float* out_variance) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * WPB + warp;
@@ -176,7 +235,12 @@ __global__ void __launch_bounds__(32 * WPB) k_heads_gather(const __nv_bfloat16* 
     if (lane == 0) {
         out_value[q] = tanhf(acc_v + head_misc[2 + 72]);
         const float ube = acc_u + head_misc[2 + 73];
-        const float local = 4.0f;  // MAXIMUM_VARIANCE when the SimHash bit is not set
+        // forward_hash (net6_simhash.rs:243-256): 0 when the position's SimHash bit is set, else 4.0
+        float local = 4.0f;
+        if (simhash_set) {
+            const uint32_t idx = simhash_idx[q];
+            if ((simhash_set[idx >> 5] >> (idx & 31)) & 1u) local = 0.0f;
+        }
         out_variance[q] = fminf(fmaxf(fmaxf(expf(ube), local), 0.0f), 4.0f);
     }
     const int cnt = n_actions[q];
@@ -497,11 +561,14 @@ int nn_forward(tz_handle* h, const TzState* states, const int* count_ptr, int co
         ProfScope ps(h, TZ_PROF_CONV_POLICY);
         launch_conv(h, s->policy, s->act_x, nullptr, nullptr, s->logits_full, 0, count_ptr, count_max);
     }
+    if (s->simhash_set)
+        k_simhash<<<wblocks, 32 * WPB, 0, h->stream>>>(states, count_ptr, count_max, d.n, d.half_komi, s->simhash_matrix,
+                                                       s->simhash_idx);
     {
         ProfScope ps(h, TZ_PROF_HEADS);
         k_heads_gather<<<wblocks, 32 * WPB, 0, h->stream>>>(s->act_x, s->logits_full, s->head_w, s->head_misc, actions,
-                                                            n_actions, count_ptr, count_max, d.n, d.M, conv::HALO, logits,
-                                                            value, variance);
+                                                            n_actions, count_ptr, count_max, d.n, d.M, conv::HALO,
+                                                            s->simhash_set, s->simhash_idx, logits, value, variance);
     }
     h->launches += 2;
     return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
@@ -571,5 +638,38 @@ int nn_time_tower(tz_handle* h, int count, int reps, double* ms_per_conv) {
     cudaEventDestroy(a);
     cudaEventDestroy(b);
     *ms_per_conv = (double)ms / (2.0 * reps);
+    return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
+}
+
+// SimHash matrix ([C*N*N][32] f32) and the optional 2^32-bit set (512 MiB, the reference's bitvec.bin)
+int nn_set_simhash(tz_handle* h, const float* matrix, const unsigned char* bitset) {
+    NnState* s = h->nn;
+    if (!s) return TZ_ENOWEIGHTS;
+    const size_t rows = (size_t)s->in_channels * s->n * s->n;
+    if (!s->simhash_matrix) {
+        if (cudaMalloc((void**)&s->simhash_matrix, rows * 32 * 4) != cudaSuccess) return TZ_ENOMEM;
+        s->allocs.push_back(s->simhash_matrix);
+        if (cudaMalloc((void**)&s->simhash_idx, (size_t)s->max_positions * 4) != cudaSuccess) return TZ_ENOMEM;
+        s->allocs.push_back(s->simhash_idx);
+    }
+    if (cudaMemcpy(s->simhash_matrix, matrix, rows * 32 * 4, cudaMemcpyHostToDevice) != cudaSuccess) return TZ_ECUDA;
+    if (bitset) {
+        const size_t bytes = (size_t)1 << 29;
+        if (!s->simhash_set) {
+            if (cudaMalloc((void**)&s->simhash_set, bytes) != cudaSuccess) return TZ_ENOMEM;
+            s->allocs.push_back(s->simhash_set);
+        }
+        if (cudaMemcpy(s->simhash_set, bitset, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return TZ_ECUDA;
+    } else {
+        s->simhash_set = nullptr;  // empty set: local uncertainty is MAXIMUM_VARIANCE everywhere
+    }
+    return TZ_OK;
+}
+
+int nn_simhash_indices(tz_handle* h, const TzState* states, int count, uint32_t* out_dev) {
+    NnState* s = h->nn;
+    if (!s || !s->simhash_matrix) return TZ_ENOWEIGHTS;
+    k_simhash<<<(count + WPB - 1) / WPB, 32 * WPB, 0, h->stream>>>(states, nullptr, count, h->d.n, h->d.half_komi,
+                                                                   s->simhash_matrix, out_dev);
     return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
 }

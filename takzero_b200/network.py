@@ -27,6 +27,8 @@ def _declare():
     capi.declare("tz_set_weights", [vp, C.POINTER(_Tensor), i32], i32)
     capi.declare("tz_evaluate", [vp, vp, i32, vp, vp, i32, vp, vp, vp], i32)
     capi.declare("tz_encode_planes", [vp, vp, i32, vp], i32)
+    capi.declare("tz_set_simhash", [vp, vp, vp], i32)
+    capi.declare("tz_simhash_indices", [vp, vp, i32, vp], i32)
     capi.declare("tz_debug_layer_limit", [vp, i32], i32)
     capi.declare("tz_debug_activations", [vp, i32, i32, vp], i32)
     capi.declare("tz_debug_time_tower", [vp, i32, i32, C.POINTER(C.c_double)], i32)
@@ -93,3 +95,23 @@ def time_tower(mcts: capi.BatchedMCTS, count: int, reps: int = 20) -> float:
     ms = C.c_double()
     capi._check(capi.lib().tz_debug_time_tower(mcts.handle, count, reps, C.byref(ms)))
     return ms.value
+
+
+def set_simhash(mcts: capi.BatchedMCTS, matrix: np.ndarray, bitset: np.ndarray | None = None) -> None:
+    """SimHash matrix [C*N*N, 32] and optionally the 2^32-bit set as 2^29 bytes (`bitvec.bin`)."""
+    _declare()
+    m = np.ascontiguousarray(matrix, dtype=np.float32)
+    assert m.shape == (mcts.input_channels * mcts.n * mcts.n, 32)
+    b = None
+    if bitset is not None:
+        b = np.ascontiguousarray(bitset, dtype=np.uint8)
+        assert b.size == 1 << 29
+    capi._check(capi.lib().tz_set_simhash(mcts.handle, capi._ptr(m), capi._ptr(b)))
+
+
+def simhash_indices(mcts: capi.BatchedMCTS, states: np.ndarray) -> np.ndarray:
+    _declare()
+    states = np.ascontiguousarray(states, dtype=capi.STATE_DTYPE)
+    out = np.zeros(len(states), dtype=np.uint32)
+    capi._check(capi.lib().tz_simhash_indices(mcts.handle, capi._ptr(states), len(states), capi._ptr(out)))
+    return out

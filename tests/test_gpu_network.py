@@ -153,3 +153,39 @@ def test_search_with_device_network_matches_injected_outputs():
     assert np.array_equal(ta["eval_bits"], tb["eval_bits"])
     for h in (a, b, evaluator):
         h.close()
+
+
+def test_simhash_indices_and_uncertainty():
+    """SimHash novelty (net6_simhash.rs:203-256,309-317): hash index per position, set lookup and the
+    uncertainty combine clamp(max(exp(ube), local), 0, 4)."""
+    n, hk, count = 6, 4, 64
+    ref = net_ref.Net(n, seed=9, blocks=1)
+    games = sample_positions(n, hk, count, 9)
+    actions = [O.possible_moves(g) for g in games]
+    states = games_to_states(games)
+    m = capi.BatchedMCTS(n, hk, count, arena_slots=4096)
+    network.set_weights(m, ref.tensors())
+    network.set_simhash(m, ref.simhash_matrix.numpy())
+    got = network.simhash_indices(m, states)
+    xs = torch.from_numpy(np.stack([O.game_repr(g).reshape(ref.cin, n, n) for g in games]))
+    dots = ref.simhash_dots(xs).numpy()
+    want = ref.get_indices(xs)
+    # bits may only differ where the f32 dot product is within rounding of zero (summation order)
+    diff = got ^ want
+    for i in range(count):
+        for b in range(32):
+            if (int(diff[i]) >> b) & 1:
+                assert abs(dots[i, b]) < 1e-3, f"position {i} bit {b}: dot {dots[i, b]}"
+    assert (diff == 0).mean() > 0.9
+    # half of the positions are "seen": their local uncertainty drops to 0, so variance = clamp(exp(ube))
+    ref.simhash_set = {int(x) for x in got[::2]}
+    network.set_simhash(m, ref.simhash_matrix.numpy(), ref.bitset_bytes())
+    _, _, variances = network.evaluate(m, states, actions)
+    with torch.no_grad():
+        ube = ref.ube(ref.core(xs)).view(-1)
+    seen = np.array([int(x) in ref.simhash_set for x in got])
+    want_var = np.where(seen, np.clip(np.exp(ube.numpy()), 0.0, 4.0), 4.0)
+    assert seen.sum() >= count // 2
+    assert np.abs(variances - want_var).max() <= 2e-2
+    assert (variances[~seen] == 4.0).all()
+    m.close()
