@@ -144,6 +144,9 @@ TZ_API int tz_legal_moves(tz_handle* h, const tz_state_t* states, int count, int
 TZ_API int tz_apply(tz_handle* h, tz_state_t* states, const tz_move_t* moves, int count, int* out_ok);
 /* Environment::terminal (env.rs:47-59): 0 none, 1 win, 2 loss, 3 draw for the side to move */
 TZ_API int tz_result(tz_handle* h, const tz_state_t* states, int count, int* out_terminal);
+/* Game::result in absolute terms (the suffix of a Replay line, target.rs:226-230):
+ * 0 ongoing, 1 "R-0", 2 "0-R", 3 "F-0", 4 "0-F", 5 "1/2-1/2" */
+TZ_API int tz_game_result(tz_handle* h, const tz_state_t* states, int count, int* out_result);
 
 /* ---- positions ------------------------------------------------------------------------- */
 /* BatchedMCTS::from_envs / nodes_and_envs_mut writes (reanalyze/src/main.rs:159-165); roots reset */
@@ -193,7 +196,7 @@ TZ_API int tz_counters(tz_handle* h, tz_counters_t* out);
 typedef struct tz_selfplay_t {
     int sampled_actions;        /* SAMPLED_ACTIONS */
     uint32_t search_budget;     /* SEARCH_BUDGET */
-    float beta;                 /* BETA for the upper half of the batch (`exploration` feature), else 0 */
+    float beta;                 /* BETA for the first half of the batch (`exploration` feature), else 0 */
     int weighted_random_plies;  /* WEIGHTED_RANDOM_PLIES (10) */
     uint32_t sample_threshold;  /* 32 */
     float allowed_eval_drop;    /* 0.5 */

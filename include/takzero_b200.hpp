@@ -1,0 +1,477 @@
+// takzero_b200.hpp -- C++17 host-side mirror of the reference's search surface on top of the C ABI
+// (include/takzero_b200.h).  Header only; link against libtakzero_b200.so.
+//
+// The reference is Rust; its toolchain is not available where this was built, so the host layer that a
+// `selfplay` / `reanalyze` style program needs is provided in C++ with the reference's names and semantics:
+//   takzero::BatchedMCTS      takzero/src/search/node/batched.rs:24-409
+//   takzero::Eval             takzero/src/search/eval.rs:8-163 (negate, f32::from; used for value targets)
+//   takzero::Target / Replay  takzero/src/target.rs:25-30,56-73,167-170,215-232 (text formats of the files
+//                             `learn` consumes), takzero::tps / move_to_string (takparse `Tps`, `Move` Display)
+// All search / rules / network math happens in the CUDA library; this header only marshals and formats.
+#pragma once
+
+#include <charconv>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "takzero_b200.h"
+
+namespace takzero {
+
+inline void check(int rc) {
+    if (rc < 0) throw std::runtime_error(std::string(tz_last_error()) + " (code " + std::to_string(rc) + ")");
+}
+
+// ---- notation -----------------------------------------------------------------------------------------
+
+using Move = tz_move_t;
+
+// takparse `Move` Display: "a1", "Sa1", "Ca1", "a1+", "3a1>12" (drop counts omitted for a single drop)
+inline std::string move_to_string(Move m) {
+    std::string s;
+    const int col = m & 7, row = (m >> 3) & 7, kind = (m >> 6) & 3, pat = m >> 8;
+    if (pat == 0) {
+        if (kind == 1) s += 'S';
+        if (kind == 2) s += 'C';
+        s += char('a' + col);
+        s += char('1' + row);
+        return s;
+    }
+    const int c = 8 - __builtin_ctz((unsigned)pat);
+    if (c > 1) s += char('0' + c);
+    s += char('a' + col);
+    s += char('1' + row);
+    s += "+-<>"[kind];
+    int drops[8], nd = 0;
+    for (int i = 0; i < c; i++) {
+        if ((pat >> (8 - c + i)) & 1) drops[nd++] = 0;
+        drops[nd - 1]++;
+    }
+    if (nd > 1)
+        for (int i = 0; i < nd; i++) s += char('0' + drops[i]);
+    return s;
+}
+
+// takparse `Tps` Display of a position: ranks from N down to 1, "x"/"xK" for empties, stacks bottom-up as
+// 1/2 with S/C suffix, then the player to move (1/2) and the move number
+inline std::string tps(const tz_state_t& g, int n) {
+    std::string s;
+    for (int row = n - 1; row >= 0; row--) {
+        int empties = 0;
+        bool first = true;
+        for (int col = 0; col <= n; col++) {
+            const int sq = row * n + col;
+            if (col < n && g.height[sq] == 0) {
+                empties++;
+                continue;
+            }
+            if (empties) {
+                if (!first) s += ',';
+                s += 'x';
+                if (empties > 1) s += char('0' + empties);
+                empties = 0;
+                first = false;
+            }
+            if (col == n) break;
+            if (!first) s += ',';
+            first = false;
+            for (int i = 0; i < g.height[sq]; i++) s += char('1' + ((g.stack[sq] >> i) & 1));
+            if (g.top[sq] == 1) s += 'S';
+            if (g.top[sq] == 2) s += 'C';
+        }
+        if (row > 0) s += '/';
+    }
+    s += ' ';
+    s += char('1' + g.to_move);
+    s += ' ';
+    s += std::to_string(g.ply / 2 + 1);
+    return s;
+}
+
+// takparse `Move` FromStr (PTN): the inverse of move_to_string; returns false on malformed input
+inline bool parse_move(const std::string& str, Move* out) {
+    const char* s = str.c_str();
+    int kind = 0, c = 0;
+    if (*s == 'S') { kind = 1; s++; } else if (*s == 'C') { kind = 2; s++; } else if (*s == 'F') { s++; }
+    if (*s >= '1' && *s <= '8') c = *s++ - '0';
+    if (*s < 'a' || *s > 'h') return false;
+    const int col = *s++ - 'a';
+    if (*s < '1' || *s > '8') return false;
+    const int row = *s++ - '1';
+    if (*s == 0) {
+        if (c != 0) return false;
+        *out = (Move)(col | (row << 3) | (kind << 6));
+        return true;
+    }
+    int dir;
+    switch (*s++) {
+        case '+': dir = 0; break;
+        case '-': dir = 1; break;
+        case '<': dir = 2; break;
+        case '>': dir = 3; break;
+        default: return false;
+    }
+    if (c == 0) c = 1;
+    int drops[8], nd = 0, total = 0;
+    while (*s >= '1' && *s <= '8' && nd < 8) {
+        drops[nd] = *s++ - '0';
+        total += drops[nd++];
+    }
+    while (*s == '*' || *s == '\'' || *s == '!' || *s == '?') s++;
+    if (*s != 0) return false;
+    if (nd == 0) { drops[nd++] = c; total = c; }
+    if (total != c || c > 8) return false;
+    int pat = 0, i = 0;
+    for (int d = 0; d < nd; d++) {
+        pat |= 1 << (8 - c + i);
+        i += drops[d];
+    }
+    *out = (Move)(col | (row << 3) | (dir << 6) | (pat << 8));
+    return true;
+}
+
+// takparse `Tps` FromStr into a tz_state_t (reserves are what is left of the standard piece counts;
+// reversible_plies is not part of TPS and starts at 0, like `Game::from(tps)` in the reference)
+inline bool parse_tps(const std::string& text, int n, tz_state_t* g) {
+    static const int STONES[9] = {0, 0, 0, 10, 15, 21, 30, 40, 50}, CAPS[9] = {0, 0, 0, 0, 0, 1, 1, 2, 2};
+    std::memset(g, 0, sizeof(*g));
+    g->stones[0] = g->stones[1] = (uint8_t)STONES[n];
+    g->caps[0] = g->caps[1] = (uint8_t)CAPS[n];
+    const char* s = text.c_str();
+    int row = n - 1, col = 0;
+    while (*s && *s != ' ') {
+        if (*s == '/') {
+            if (col != n) return false;
+            row--; col = 0; s++;
+        } else if (*s == ',') {
+            s++;
+        } else if (*s == 'x') {
+            s++;
+            int k = 1;
+            if (*s >= '1' && *s <= '8') k = *s++ - '0';
+            col += k;
+        } else if (*s == '1' || *s == '2') {
+            if (row < 0 || col >= n) return false;
+            const int sq = row * n + col;
+            int h = 0;
+            uint64_t bits = 0;
+            while (*s == '1' || *s == '2') { bits |= (uint64_t)(*s - '1') << h; h++; s++; }
+            int type = 0;
+            if (*s == 'S') { type = 1; s++; } else if (*s == 'C') { type = 2; s++; }
+            g->stack[sq] = bits;
+            g->height[sq] = (uint8_t)h;
+            g->top[sq] = (uint8_t)type;
+            for (int i = 0; i < h; i++) {
+                const int cl = (int)((bits >> i) & 1);
+                uint8_t& pool = (i == h - 1 && type == 2) ? g->caps[cl] : g->stones[cl];
+                if (pool == 0) return false;
+                pool--;
+            }
+            col++;
+        } else {
+            return false;
+        }
+    }
+    if (row != 0 || col != n) return false;
+    int player = 1, move_no = 1;
+    if (std::sscanf(s, " %d %d", &player, &move_no) != 2) return false;
+    g->to_move = (uint8_t)(player - 1);
+    g->ply = (uint16_t)((move_no - 1) * 2 + (player - 1));
+    return true;
+}
+
+// Rust `{}` of an f32: shortest decimal that round-trips, never in exponent form ("1", "0.5", "-0.0009")
+inline std::string format_f32(float v) {
+    if (std::isnan(v)) return "NaN";
+    if (std::isinf(v)) return v > 0 ? "inf" : "-inf";
+    char buf[128];
+    auto r = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::fixed);
+    return std::string(buf, r.ptr);
+}
+
+inline const char* result_string(int game_result) {  // tz_game_result codes
+    static const char* names[] = {"", "R-0", "0-R", "F-0", "0-F", "1/2-1/2"};
+    return names[game_result];
+}
+
+// ---- Eval (search/eval.rs) ------------------------------------------------------------------------------
+
+struct Eval {
+    uint32_t tag = 0;  // 0 Value, 1 Win, 2 Loss, 3 Draw
+    union {
+        float value;
+        uint32_t ply;
+    };
+    Eval() : value(0.0f) {}
+    static Eval from_terminal(int terminal) {  // eval.rs:118-126; terminal: 1 win, 2 loss, 3 draw
+        Eval e;
+        e.tag = (uint32_t)terminal;
+        e.ply = 0;
+        return e;
+    }
+    Eval negate() const {  // eval.rs:40-47
+        Eval e = *this;
+        switch (tag) {
+            case 0: e.value = -value; break;
+            case 1: e.tag = 2; e.ply = ply + 1; break;
+            case 2: e.tag = 1; e.ply = ply + 1; break;
+            default: e.ply = ply + 1; break;
+        }
+        return e;
+    }
+    float to_f32() const {  // eval.rs:95-105, `0.997f32.powi(ply)` by square-and-multiply like compiler-rt
+        if (tag == 0) return value;
+        float a = 0.997f, r = 1.0f;
+        for (uint32_t b = ply;;) {
+            if (b & 1) r *= a;
+            b >>= 1;
+            if (b == 0) break;
+            a *= a;
+        }
+        return r * (tag == 1 ? 1.0f : tag == 2 ? -1.0f : 0.0f);
+    }
+};
+
+// ---- Target / Replay (target.rs) ---------------------------------------------------------------------------
+
+struct Target {
+    tz_state_t env;
+    std::vector<std::pair<Move, float>> policy;
+    float value = 0.0f;
+    float ube = 0.0f;
+    // "{tps};{value};{ube};{move:p,move:p,...}\n" (target.rs:56-73)
+    std::string to_string(int n) const {
+        std::string s = tps(env, n) + ';' + format_f32(value) + ';' + format_f32(ube) + ';';
+        for (size_t i = 0; i < policy.size(); i++) {
+            if (i) s += ',';
+            s += move_to_string(policy[i].first) + ':' + format_f32(policy[i].second);
+        }
+        s += '\n';
+        return s;
+    }
+};
+
+struct Replay {
+    tz_state_t env;
+    std::vector<Move> actions;
+    // "[TPS \"{tps}\"] m1 m2 ... {result}\n" (target.rs:215-232); game_result from tz_game_result (0 = none)
+    std::string to_string(int n, int game_result) const {
+        std::string s = "[TPS \"" + tps(env, n) + "\"]";
+        for (Move m : actions) s += ' ' + move_to_string(m);
+        if (game_result) s += std::string(" ") + result_string(game_result);
+        s += '\n';
+        return s;
+    }
+    // Replay FromStr (target.rs:243-272): `[TPS "..."] m1 m2 ... [result]`
+    static bool parse(const std::string& line, int n, Replay* out) {
+        const size_t a = line.find('"'), b = line.find('"', a + 1);
+        if (a == std::string::npos || b == std::string::npos) return false;
+        if (!parse_tps(line.substr(a + 1, b - a - 1), n, &out->env)) return false;
+        out->actions.clear();
+        size_t pos = line.find(']', b);
+        if (pos == std::string::npos) return false;
+        pos++;
+        while (pos < line.size()) {
+            while (pos < line.size() && line[pos] == ' ') pos++;
+            size_t end = line.find(' ', pos);
+            if (end == std::string::npos) end = line.size();
+            const std::string tok = line.substr(pos, end - pos);
+            pos = end;
+            if (tok.empty()) continue;
+            Move m;
+            if (parse_move(tok, &m)) out->actions.push_back(m);
+            else if (tok.find('-') == std::string::npos) return false;  // not a result token either
+        }
+        return true;
+    }
+};
+
+// ---- weights file (our own container: "TZW1", count, then per tensor name / shape / f32 data) ----------------
+
+struct Weights {
+    std::vector<std::string> names;
+    std::vector<std::vector<int64_t>> shapes;
+    std::vector<std::vector<float>> data;
+    static Weights load(const std::string& path) {
+        std::ifstream f(path, std::ios::binary);
+        if (!f) throw std::runtime_error("cannot open " + path);
+        char magic[4];
+        uint32_t count = 0;
+        f.read(magic, 4);
+        f.read(reinterpret_cast<char*>(&count), 4);
+        if (std::memcmp(magic, "TZW1", 4) != 0) throw std::runtime_error(path + ": not a TZW1 file");
+        Weights w;
+        for (uint32_t i = 0; i < count; i++) {
+            uint32_t len = 0, ndim = 0;
+            f.read(reinterpret_cast<char*>(&len), 4);
+            std::string name(len, '\0');
+            f.read(name.data(), len);
+            f.read(reinterpret_cast<char*>(&ndim), 4);
+            std::vector<int64_t> shape(ndim);
+            f.read(reinterpret_cast<char*>(shape.data()), 8 * ndim);
+            size_t numel = 1;
+            for (int64_t d : shape) numel *= (size_t)d;
+            std::vector<float> v(numel);
+            f.read(reinterpret_cast<char*>(v.data()), 4 * numel);
+            if (!f) throw std::runtime_error(path + ": truncated");
+            w.names.push_back(std::move(name));
+            w.shapes.push_back(std::move(shape));
+            w.data.push_back(std::move(v));
+        }
+        return w;
+    }
+};
+
+// ---- BatchedMCTS (search/node/batched.rs) --------------------------------------------------------------------
+
+class BatchedMCTS {
+  public:
+    BatchedMCTS(int board_n, int half_komi, int n_games, int device = 0, int game_base = 0, uint32_t arena_slots = 0)
+        : n_(board_n), games_(n_games) {
+        tz_config_t cfg{};
+        cfg.board_n = board_n;
+        cfg.half_komi = half_komi;
+        cfg.n_games = n_games;
+        cfg.device = device;
+        cfg.game_base = game_base;
+        cfg.arena_slots = arena_slots;
+        check(tz_create(&cfg, &h_));
+        check(tz_info(h_, &stride_, nullptr, nullptr, nullptr));
+    }
+    ~BatchedMCTS() { tz_destroy(h_); }
+    BatchedMCTS(const BatchedMCTS&) = delete;
+    BatchedMCTS& operator=(const BatchedMCTS&) = delete;
+
+    tz_handle* handle() const { return h_; }
+    int board_n() const { return n_; }
+    int games() const { return games_; }
+    int move_stride() const { return stride_; }
+
+    void set_weights(const Weights& w) {  // Net::load
+        std::vector<tz_tensor_t> t(w.names.size());
+        for (size_t i = 0; i < t.size(); i++)
+            t[i] = tz_tensor_t{w.names[i].c_str(), w.data[i].data(), w.shapes[i].data(), (int)w.shapes[i].size()};
+        check(tz_set_weights(h_, t.data(), (int)t.size()));
+    }
+    void set_agent(int kind, tz_agent_fn fn = nullptr, void* ctx = nullptr) { check(tz_set_agent(h_, kind, fn, ctx)); }
+    void new_openings(uint64_t seed) { check(tz_new_openings(h_, nullptr, nullptr, nullptr, seed)); }
+    void set_positions(const std::vector<tz_state_t>& envs) { check(tz_set_positions(h_, envs.data(), nullptr)); }
+    std::vector<tz_state_t> envs() const {
+        std::vector<tz_state_t> out(games_);
+        check(tz_get_positions(h_, out.data()));
+        return out;
+    }
+    void simulate(const std::vector<float>& betas) { check(tz_simulate(h_, betas.data())); }
+    // noise drawn by the library from `seed` (the reference draws from its rng, whose stream is not pinned)
+    std::vector<Move> gumbel_sequential_halving(const std::vector<float>& betas, int sampled_actions,
+                                                uint32_t search_budget, uint64_t seed) {
+        std::vector<Move> out(games_);
+        check(tz_gumbel_sequential_halving(h_, betas.data(), sampled_actions, search_budget, nullptr, 0, seed, out.data()));
+        return out;
+    }
+    std::vector<Move> select_actions_in_selfplay(int weighted_random_plies, uint64_t seed, uint32_t threshold = 32,
+                                                 float allowed_eval_drop = 0.5f) {
+        std::vector<Move> out(games_);
+        check(tz_select_selfplay(h_, weighted_random_plies, threshold, allowed_eval_drop, nullptr, seed, out.data()));
+        return out;
+    }
+    std::vector<Move> select_best_actions() {
+        std::vector<Move> out(games_);
+        check(tz_select_best(h_, out.data()));
+        return out;
+    }
+    void step(const std::vector<Move>& actions) { check(tz_step(h_, actions.data())); }
+    // Replay::states (target.rs:205-212): the position before every action, by applying the moves on the device
+    std::vector<tz_state_t> replay_states(const Replay& r) {
+        std::vector<tz_state_t> out;
+        tz_state_t cur = r.env;
+        for (Move m : r.actions) {
+            out.push_back(cur);
+            int ok = 0;
+            check(tz_apply(h_, &cur, &m, 1, &ok));
+            if (!ok) throw std::runtime_error("Action should be valid: " + move_to_string(m));
+        }
+        return out;
+    }
+
+    struct RootTargets {
+        std::vector<float> policy;  // [games][stride]
+        std::vector<Move> moves;    // [games][stride]
+        std::vector<int> n;
+        std::vector<float> ube;
+    };
+    // Node::improved_policy + Node::ube_target of every root (visitations < 0: most_visited_count())
+    RootTargets targets(float visitations, float beta) {
+        RootTargets t;
+        t.policy.resize((size_t)games_ * stride_);
+        t.moves.resize((size_t)games_ * stride_);
+        t.n.resize(games_);
+        t.ube.resize(games_);
+        check(tz_targets(h_, visitations, beta, stride_, t.policy.data(), t.ube.data(), t.n.data(), t.moves.data()));
+        return t;
+    }
+    struct RootStats {
+        std::vector<tz_root_t> roots;
+    };
+    std::vector<tz_root_t> root_stats() {
+        std::vector<tz_root_t> out(games_);
+        check(tz_root_stats(h_, out.data()));
+        return out;
+    }
+    struct Children {
+        int stride;
+        std::vector<int> n;
+        std::vector<Move> moves;
+        std::vector<uint32_t> visits, eval_tag, eval_bits;
+        std::vector<float> logit, prob, std_dev;
+    };
+    Children root_children() {
+        Children c;
+        c.stride = stride_;
+        const size_t cells = (size_t)games_ * stride_;
+        c.n.resize(games_);
+        c.moves.resize(cells);
+        c.visits.resize(cells);
+        c.eval_tag.resize(cells);
+        c.eval_bits.resize(cells);
+        c.logit.resize(cells);
+        c.prob.resize(cells);
+        c.std_dev.resize(cells);
+        check(tz_root_children(h_, stride_, c.n.data(), c.moves.data(), c.visits.data(), c.eval_tag.data(),
+                               c.eval_bits.data(), c.logit.data(), c.prob.data(), c.std_dev.data()));
+        return c;
+    }
+    // restart_terminal_envs: terminal[g] (0 none, 1 win, 2 loss, 3 draw for the side to move) and, for finished
+    // games, the replay that just ended
+    std::vector<int> restart_terminal_envs(uint64_t seed) {
+        std::vector<int> term(games_);
+        check(tz_restart_terminal(h_, nullptr, nullptr, seed, term.data()));
+        return term;
+    }
+    Replay finished_replay(int game) {
+        Replay r;
+        std::vector<Move> buf(TZ_MAX_PLIES);
+        const int len = tz_finished_replay(h_, game, &r.env, buf.data(), TZ_MAX_PLIES);
+        check(len);
+        r.actions.assign(buf.begin(), buf.begin() + len);
+        return r;
+    }
+    tz_counters_t counters() {
+        tz_counters_t c;
+        check(tz_counters(h_, &c));
+        return c;
+    }
+
+  private:
+    tz_handle* h_ = nullptr;
+    int n_, games_, stride_ = 0;
+};
+
+}  // namespace takzero

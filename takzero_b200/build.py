@@ -30,8 +30,10 @@ def _stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
-        os.path.join(HERE, "..", "include", "takzero_b200.h"), os.path.abspath(__file__)]
+    hostdir = os.path.join(HERE, "..", "host")
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(hostdir, f) for f in os.listdir(hostdir)] + [
+        os.path.join(HERE, "..", "include", "takzero_b200.h"), os.path.join(HERE, "..", "include", "takzero_b200.hpp"),
+        os.path.abspath(__file__)]
     return any(os.path.getmtime(p) > t for p in deps)
 
 
@@ -58,7 +60,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [nvcc(), "-shared", "-o", LIB, *objs, "--cudart", "static",
            "-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
+    build_hosts()
     return LIB
+
+
+HOSTS = ["selfplay", "reanalyze"]
+
+
+def build_hosts() -> None:
+    """C++ host programs over the C ABI (host/*.cpp) -> takzero_b200/bin/."""
+    bindir = os.path.join(HERE, "bin")
+    os.makedirs(bindir, exist_ok=True)
+    for name in HOSTS:
+        src = os.path.join(HERE, "..", "host", f"{name}.cpp")
+        if not os.path.exists(src):
+            continue
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", src, "-o", os.path.join(bindir, name),
+                               f"-L{HERE}", "-ltakzero_b200", "-Wl,-rpath,$ORIGIN/.."])
 
 
 if __name__ == "__main__":

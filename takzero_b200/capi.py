@@ -132,6 +132,7 @@ def lib():
         "tz_legal_moves": ([vp, vp, i32, i32, vp, vp], i32),
         "tz_apply": ([vp, vp, vp, i32, vp], i32),
         "tz_result": ([vp, vp, i32, vp], i32),
+        "tz_game_result": ([vp, vp, i32, vp], i32),
         "tz_set_positions": ([vp, vp, vp], i32),
         "tz_get_positions": ([vp, vp], i32),
         "tz_new_openings": ([vp, vp, vp, vp, u64], i32),
@@ -255,6 +256,13 @@ class BatchedMCTS:
         states = _arr(states, STATE_DTYPE)
         out = np.zeros(len(states), dtype=np.int32)
         _check(lib().tz_result(self._h, _ptr(states), len(states), _ptr(out)))
+        return out
+
+    def game_result(self, states: np.ndarray):
+        """0 ongoing, 1 R-0, 2 0-R, 3 F-0, 4 0-F, 5 draw."""
+        states = _arr(states, STATE_DTYPE)
+        out = np.zeros(len(states), dtype=np.int32)
+        _check(lib().tz_game_result(self._h, _ptr(states), len(states), _ptr(out)))
         return out
 
     # ---- positions --------------------------------------------------------------------

@@ -310,7 +310,7 @@ extern "C" TZ_API int tz_legal_moves(tz_handle* h, const tz_state_t* states, int
     CU(s.get(&dm, (size_t)count * stride));
     CU(s.get(&dn, (size_t)count));
     CU(cudaMemcpyAsync(ds, states, (size_t)count * sizeof(TzState), cudaMemcpyHostToDevice, h->stream));
-    launch_rules_probe(h->d, ds, count, stride, dm, dn, nullptr, h->stream);
+    launch_rules_probe(h->d, ds, count, stride, dm, dn, nullptr, nullptr, h->stream);
     CU(cudaMemcpyAsync(out_moves, dm, (size_t)count * stride * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(out_n, dn, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -328,8 +328,25 @@ extern "C" TZ_API int tz_result(tz_handle* h, const tz_state_t* states, int coun
     CU(s.get(&ds, (size_t)count));
     CU(s.get(&dt, (size_t)count));
     CU(cudaMemcpyAsync(ds, states, (size_t)count * sizeof(TzState), cudaMemcpyHostToDevice, h->stream));
-    launch_rules_probe(h->d, ds, count, 0, nullptr, nullptr, dt, h->stream);
+    launch_rules_probe(h->d, ds, count, 0, nullptr, nullptr, dt, nullptr, h->stream);
     CU(cudaMemcpyAsync(out_terminal, dt, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_game_result(tz_handle* h, const tz_state_t* states, int count, int* out_result) {
+    CHECK_H(h);
+    if (!states || count < 0 || !out_result) return fail(TZ_EINVAL, "bad argument");
+    if (count == 0) return TZ_OK;
+    Scratch s;
+    TzState* ds;
+    int* dt;
+    CU(s.get(&ds, (size_t)count));
+    CU(s.get(&dt, (size_t)count));
+    CU(cudaMemcpyAsync(ds, states, (size_t)count * sizeof(TzState), cudaMemcpyHostToDevice, h->stream));
+    launch_rules_probe(h->d, ds, count, 0, nullptr, nullptr, nullptr, dt, h->stream);
+    CU(cudaMemcpyAsync(out_result, dt, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
     return TZ_OK;
@@ -836,9 +853,9 @@ extern "C" TZ_API int tz_selfplay_move(tz_handle* h, const tz_selfplay_t* sp) {
     const TzDev& d = h->d;
     const float* dbetas = nullptr;
     if (sp->beta != 0.0f) {
-        // `exploration` feature of selfplay (main.rs:81-87): beta for the upper half of the batch
+        // `exploration` feature of selfplay (main.rs:81-87): beta for the first half of the batch
         std::vector<float> b((size_t)d.G, 0.0f);
-        for (int g = d.G / 2; g < d.G; g++) b[g] = sp->beta;
+        for (int g = 0; g < d.G / 2; g++) b[g] = sp->beta;
         CU(cudaMemcpyAsync(h->betas, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
         CU(cudaStreamSynchronize(h->stream));
         dbetas = h->betas;

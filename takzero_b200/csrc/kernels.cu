@@ -822,7 +822,8 @@ __global__ void k_merge_moves(TzDev d, int weighted_random_plies, const uint16_t
 // ---- rules parity hooks --------------------------------------------------------------------
 
 __global__ void __launch_bounds__(32 * WPB) k_rules_probe(TzDev d, const TzState* states, int count, int stride,
-                                                          uint16_t* out_moves, int* out_n, int* out_terminal) {
+                                                          uint16_t* out_moves, int* out_n, int* out_terminal,
+                                                          int* out_result) {
     __shared__ TzState s_state[WPB];
     __shared__ uint16_t s_moves[WPB][TZ_MAX_MOVES];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -833,6 +834,10 @@ __global__ void __launch_bounds__(32 * WPB) k_rules_probe(TzDev d, const TzState
     if (out_terminal) {
         const int term = warp_terminal(st, d.n, d.half_komi, d.rev_limit, lane);
         if (lane == 0) out_terminal[i] = term;
+    }
+    if (out_result) {
+        const int res = warp_game_result(st, d.n, d.half_komi, d.rev_limit, lane);
+        if (lane == 0) out_result[i] = res;
     }
     if (out_moves) {
         const int cnt = warp_movegen(st, d.n, s_moves[warp], lane);
@@ -919,8 +924,9 @@ void launch_merge_moves(const TzDev& d, int weighted_random_plies, const uint16_
     k_merge_moves<<<(d.G + 127) / 128, 128, 0, st>>>(d, weighted_random_plies, sampled, moves);
 }
 void launch_rules_probe(const TzDev& d, const TzState* states, int count, int stride, uint16_t* out_moves, int* out_n,
-                        int* out_terminal, cudaStream_t st) {
-    k_rules_probe<<<blocks_for(count), 32 * WPB, 0, st>>>(d, states, count, stride, out_moves, out_n, out_terminal);
+                        int* out_terminal, int* out_result, cudaStream_t st) {
+    k_rules_probe<<<blocks_for(count), 32 * WPB, 0, st>>>(d, states, count, stride, out_moves, out_n, out_terminal,
+                                                          out_result);
 }
 void launch_apply_moves(const TzDev& d, TzState* states, const uint16_t* moves, int count, int* out_ok,
                         cudaStream_t st) {

@@ -26,7 +26,7 @@ void launch_select_actions(const TzDev& d, int weighted_random_plies, uint32_t t
                            const unsigned long long* randoms, unsigned long long seed, unsigned long long counter,
                            uint16_t* out_moves, cudaStream_t st);
 void launch_rules_probe(const TzDev& d, const TzState* states, int count, int stride, uint16_t* out_moves, int* out_n,
-                        int* out_terminal, cudaStream_t st);
+                        int* out_terminal, int* out_result, cudaStream_t st);
 void launch_apply_moves(const TzDev& d, TzState* states, const uint16_t* moves, int count, int* out_ok,
                         cudaStream_t st);
 void launch_merge_moves(const TzDev& d, int weighted_random_plies, const uint16_t* sampled, uint16_t* moves,

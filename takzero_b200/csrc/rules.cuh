@@ -85,11 +85,11 @@ __device__ __forceinline__ bool bb_connects(uint64_t road, uint64_t from, uint64
     return false;
 }
 
-// `Environment::terminal` (env.rs:47-59) over fast-tak's `Game::result`: road for the
-// player who just moved first, then the other player, then flat count (komi) when the
-// board is full or a player is out of pieces, then the reversible-ply draw.
-__device__ __forceinline__ int warp_terminal(const TzState* s, int n, int half_komi, int rev_limit,
-                                             int lane) {
+// fast-tak's `Game::result` as consumed by env.rs:47-59 and target.rs:226-230: road for the player who
+// just moved first, then the other player, then flat count (komi) when the board is full or a player is
+// out of pieces, then the reversible-ply draw.
+// Returns 0 ongoing, 1 white road, 2 black road, 3 white flat win, 4 black flat win, 5 draw.
+__device__ __forceinline__ int warp_game_result(const TzState* s, int n, int half_komi, int rev_limit, int lane) {
     const int nn = n * n;
     const TzBoards b = warp_boards(s, nn, lane);
     const uint64_t c0 = col_mask(n, 0), cN = col_mask(n, n - 1);
@@ -104,27 +104,28 @@ __device__ __forceinline__ int warp_terminal(const TzState* s, int n, int half_k
     const uint32_t roads = __ballot_sync(FULL_MASK, mine);
     const bool road_w = roads & 3u, road_b = roads & 12u;
     const int to_move = s->to_move, mover = to_move ^ 1;
-    int winner = -1;  // 0 white, 1 black, 2 draw
     const bool road_mover = mover == 0 ? road_w : road_b;
     const bool road_other = mover == 0 ? road_b : road_w;
-    if (road_mover) {
-        winner = mover;
-    } else if (road_other) {
-        winner = to_move;
-    } else {
-        const bool full = __popcll(b.occ) == nn;
-        const bool w_out = s->stones[0] == 0 && s->caps[0] == 0;
-        const bool b_out = s->stones[1] == 0 && s->caps[1] == 0;
-        if (full || w_out || b_out) {
-            const int score2 = 2 * (__popcll(b.flat[0]) - __popcll(b.flat[1])) - half_komi;
-            winner = score2 > 0 ? 0 : (score2 < 0 ? 1 : 2);
-        } else if ((int)s->reversible_plies >= rev_limit) {
-            winner = 2;
-        }
+    if (road_mover) return 1 + mover;
+    if (road_other) return 1 + to_move;
+    const bool full = __popcll(b.occ) == nn;
+    const bool w_out = s->stones[0] == 0 && s->caps[0] == 0;
+    const bool b_out = s->stones[1] == 0 && s->caps[1] == 0;
+    if (full || w_out || b_out) {
+        const int score2 = 2 * (__popcll(b.flat[0]) - __popcll(b.flat[1])) - half_komi;
+        return score2 > 0 ? 3 : (score2 < 0 ? 4 : 5);
     }
-    if (winner < 0) return TZ_T_NONE;
-    if (winner == 2) return TZ_T_DRAW;
-    return winner == to_move ? TZ_T_WIN : TZ_T_LOSS;
+    if ((int)s->reversible_plies >= rev_limit) return 5;
+    return 0;
+}
+
+// `Environment::terminal` (env.rs:47-59): the result relative to the side to move
+__device__ __forceinline__ int warp_terminal(const TzState* s, int n, int half_komi, int rev_limit, int lane) {
+    const int r = warp_game_result(s, n, half_komi, rev_limit, lane);
+    if (r == 0) return TZ_T_NONE;
+    if (r == 5) return TZ_T_DRAW;
+    const int winner = (r == 1 || r == 3) ? 0 : 1;
+    return winner == (int)s->to_move ? TZ_T_WIN : TZ_T_LOSS;
 }
 
 // ---- move generation -----------------------------------------------------------

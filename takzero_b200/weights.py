@@ -65,3 +65,17 @@ def flops_per_position(n: int, blocks: int | None = None) -> float:
     mac = nn_ * 9 * cin * FILTERS + blocks * 2 * nn_ * 9 * FILTERS * FILTERS + nn_ * 9 * FILTERS * cout
     mac += 2 * (nn_ * FILTERS + nn_)
     return 2.0 * mac
+
+
+def save_tzw(path: str, tensors: Dict[str, np.ndarray]) -> None:
+    """Write the TZW1 container the C++ hosts read (include/takzero_b200.hpp `Weights::load`)."""
+    import struct
+
+    with open(path, "wb") as f:
+        f.write(b"TZW1" + struct.pack("<I", len(tensors)))
+        for name, t in tensors.items():
+            a = np.ascontiguousarray(t, dtype=np.float32)
+            nb = name.encode()
+            f.write(struct.pack("<I", len(nb)) + nb + struct.pack("<I", a.ndim))
+            f.write(struct.pack(f"<{a.ndim}q", *a.shape))
+            f.write(a.tobytes())
