@@ -222,6 +222,14 @@ TZ_API int tz_profile_end(tz_handle* h, tz_profile_t* out);
 TZ_API int tz_timer_start(tz_handle* h);
 TZ_API int tz_timer_stop(tz_handle* h, double* out_ms);
 
+/* ---- single tree (tei/src/main.rs:139-290, analysis/src/main.rs): the tree and position are game 0 of the
+ * handle (tz_set_positions / tz_reset_roots); batch_size <= n_games. ------------------------------------------ */
+TZ_API int tz_tree_simulate_simple(tz_handle* h, float beta);                 /* Node::simulate_simple (mcts.rs:235-266) */
+TZ_API int tz_tree_simulate_batch(tz_handle* h, float beta, int batch_size);  /* Node::simulate_batch (mcts.rs:268-328) */
+TZ_API int tz_tree_descend(tz_handle* h, tz_move_t move);                     /* Node::descend + env.step (tree reuse) */
+/* Node::principal_variation (node/mod.rs:40-62); returns the length written to out_moves */
+TZ_API int tz_tree_principal_variation(tz_handle* h, tz_move_t* out_moves, int cap);
+
 /* ---- network (takzero/src/network/{net4_simhash,net5,net6_simhash,residual,repr}.rs) ----------- */
 /* Net::load (network/mod.rs:16-35): f32 tensors in PyTorch layout, named
  *   core.input_conv2d.weight [256,C,3,3]; core.batch_norm.{weight,bias,running_mean,running_var} [256];

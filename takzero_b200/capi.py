@@ -151,6 +151,10 @@ def lib():
         "tz_select_best": ([vp, vp], i32),
         "tz_select_selfplay": ([vp, i32, u32, f32, vp, u64, vp], i32),
         "tz_counters": ([vp, P(Counters)], i32),
+        "tz_tree_simulate_simple": ([vp, f32], i32),
+        "tz_tree_simulate_batch": ([vp, f32, i32], i32),
+        "tz_tree_descend": ([vp, C.c_uint16], i32),
+        "tz_tree_principal_variation": ([vp, vp, i32], i32),
         "tz_selfplay_move": ([vp, P(SelfplayParams)], i32),
         "tz_launch_count": ([vp, P(u64)], i32),
         "tz_profile_begin": ([vp, i32], i32),
@@ -390,6 +394,21 @@ class BatchedMCTS:
         c = Counters()
         _check(lib().tz_counters(self._h, C.byref(c)))
         return c
+
+    # ---- single tree (game 0): the reference's Node::simulate_simple / simulate_batch / descend / PV ----
+    def tree_simulate_simple(self, beta: float = 0.0) -> None:
+        _check(lib().tz_tree_simulate_simple(self._h, beta))
+
+    def tree_simulate_batch(self, beta: float, batch_size: int) -> None:
+        _check(lib().tz_tree_simulate_batch(self._h, beta, batch_size))
+
+    def tree_descend(self, move: int) -> None:
+        _check(lib().tz_tree_descend(self._h, int(move)))
+
+    def tree_principal_variation(self, cap: int = 64) -> np.ndarray:
+        out = np.zeros(cap, dtype=np.uint16)
+        n = _check(lib().tz_tree_principal_variation(self._h, _ptr(out), cap))
+        return out[:n].copy()
 
     def selfplay_move(self, params: SelfplayParams) -> None:
         """One whole self-play move on the device, asynchronous (see tz_selfplay_move)."""

@@ -470,19 +470,9 @@ extern "C" TZ_API int tz_set_agent(tz_handle* h, int kind, tz_agent_fn fn, void*
     return TZ_OK;
 }
 
-// one lock-step simulation of all games (batched.rs:63-128 / :266-333)
-static int lockstep(tz_handle* h, int phase, int halving_i, const float* dbetas) {
+// Agent::policy_value_uncertainty over the evaluation queue -> d.logits / d.value / d.variance
+static int run_agent(tz_handle* h) {
     const TzDev& d = h->d;
-    h->prof_active = h->prof_every > 0 && (h->prof_tick++ % (unsigned long long)h->prof_every) == 0 &&
-                     h->prof_locksteps < TZ_PROF_MAX_LOCKSTEPS && h->prof_used + 64 < TZ_PROF_MAX_PAIRS;
-    CU(cudaMemsetAsync(d.nn_count, 0, sizeof(int), h->stream));
-    {
-        ProfScope ps(h, TZ_PROF_SELECT);
-        launch_select(d, phase, halving_i, dbetas, h->stream);
-    }
-    if (h->prof_active)
-        CU(cudaMemcpyAsync(h->prof_counts + h->prof_locksteps++, d.nn_count, sizeof(int), cudaMemcpyDeviceToHost,
-                           h->stream));
     if (h->agent_kind == TZ_AGENT_SYNTHETIC) {
         ProfScope ps(h, TZ_PROF_SYNTH);
         launch_agent_synth(d, h->stream);
@@ -505,6 +495,26 @@ static int lockstep(tz_handle* h, int phase, int halving_i, const float* dbetas)
             CU(cudaMemcpyAsync(d.value, h->pin_value, c * sizeof(float), cudaMemcpyHostToDevice, h->stream));
             CU(cudaMemcpyAsync(d.variance, h->pin_variance, c * sizeof(float), cudaMemcpyHostToDevice, h->stream));
         }
+    }
+    return TZ_OK;
+}
+
+// one lock-step simulation of all games (batched.rs:63-128 / :266-333)
+static int lockstep(tz_handle* h, int phase, int halving_i, const float* dbetas) {
+    const TzDev& d = h->d;
+    h->prof_active = h->prof_every > 0 && (h->prof_tick++ % (unsigned long long)h->prof_every) == 0 &&
+                     h->prof_locksteps < TZ_PROF_MAX_LOCKSTEPS && h->prof_used + 64 < TZ_PROF_MAX_PAIRS;
+    CU(cudaMemsetAsync(d.nn_count, 0, sizeof(int), h->stream));
+    {
+        ProfScope ps(h, TZ_PROF_SELECT);
+        launch_select(d, phase, halving_i, dbetas, h->stream);
+    }
+    if (h->prof_active)
+        CU(cudaMemcpyAsync(h->prof_counts + h->prof_locksteps++, d.nn_count, sizeof(int), cudaMemcpyDeviceToHost,
+                           h->stream));
+    {
+        const int rc = run_agent(h);
+        if (rc) return rc;
     }
     {
         ProfScope ps(h, TZ_PROF_EXPAND);
@@ -969,4 +979,55 @@ extern "C" TZ_API int tz_simhash_indices(tz_handle* h, const tz_state_t* states,
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
     return TZ_OK;
+}
+
+// ---- single tree (tei / analysis): Node::simulate_simple, simulate_batch, descend, principal_variation ----
+// The tree is game 0 of the handle; batch_size <= n_games because the per-leaf paths reuse the per-game buffers.
+
+static int tree_simulate(tz_handle* h, float beta, int batch_size, int max_forwards) {
+    const TzDev& d = h->d;
+    if (batch_size <= 0 || batch_size > d.G) return fail(TZ_EINVAL, "batch_size must be 1..n_games (%d)", d.G);
+    h->prof_active = false;
+    launch_tree_forward(d, beta, batch_size, max_forwards, h->stream);
+    int rc = run_agent(h);
+    if (rc) return rc;
+    launch_tree_backward(d, h->stream);
+    h->launches += 2;
+    return finish(h);
+}
+
+extern "C" TZ_API int tz_tree_simulate_simple(tz_handle* h, float beta) {
+    CHECK_H(h);
+    return tree_simulate(h, beta, 1, 1);  // mcts.rs:235-266
+}
+
+extern "C" TZ_API int tz_tree_simulate_batch(tz_handle* h, float beta, int batch_size) {
+    CHECK_H(h);
+    return tree_simulate(h, beta, batch_size, 4 * batch_size);  // mcts.rs:268-328
+}
+
+extern "C" TZ_API int tz_tree_descend(tz_handle* h, tz_move_t move) {
+    CHECK_H(h);
+    std::vector<uint16_t> mv((size_t)h->d.G, 0);
+    mv[0] = move;
+    CU(cudaMemcpyAsync(h->moves, mv.data(), mv.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
+    launch_step(h->d, h->moves, h->stream, 0);
+    h->launches += 1;
+    return finish(h);
+}
+
+extern "C" TZ_API int tz_tree_principal_variation(tz_handle* h, tz_move_t* out_moves, int cap) {
+    CHECK_H(h);
+    if (!out_moves || cap <= 0) return fail(TZ_EINVAL, "bad argument");
+    if (cap > h->d.M) cap = h->d.M;
+    launch_tree_pv(h->d, h->tbl_moves, cap, h->tbl_n, h->stream);
+    int* len = (int*)(h->pin_small + 192);
+    CU(cudaMemcpyAsync(len, h->tbl_n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (*len > 0) {
+        CU(cudaMemcpyAsync(out_moves, h->tbl_moves, (size_t)*len * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    CU(cudaGetLastError());
+    return *len;
 }

@@ -26,6 +26,73 @@ __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b)
 
 // ---- one lock-step simulation: selection -----------------------------------------
 
+// Node::forward (mcts.rs:107-138) from node `slot` with the position in `st` (shared memory):
+// visit counts are incremented on the way down, the path is written to `traj`.
+// Returns 1 when the result is known (*known_ev), 0 when the leaf needs the network, -1 on error.
+__device__ __forceinline__ int warp_forward(const TzDev& d, const GameTree& t, TzState* st, uint32_t* traj,
+                                            uint32_t slot, float beta, int lane, int* out_len, Ev* known_ev) {
+    int len = 0;
+    while (true) {
+        if (len >= TZ_MAX_DEPTH) {
+            flag_error(d, TZ_ERR_DEPTH, lane);
+            return -1;
+        }
+        if (lane == 0) {
+            t.visits[slot] += 1;
+            traj[len] = slot;
+        }
+        len++;
+        __syncwarp();
+        const uint32_t meta = t.meta[slot];
+        const uint32_t tag = tz_meta_tag(meta);
+        if (tag != TZ_E_VALUE && t.eval[slot] == 0) {  // is_terminal
+            *known_ev = ev_make(tag, 0);
+            *out_len = len;
+            return 1;
+        }
+        if (tz_meta_nchild(meta) == 0 && tag == TZ_E_VALUE) {  // needs_initialization
+            const int term = warp_terminal(st, d.n, d.half_komi, d.rev_limit, lane);
+            *out_len = len;
+            if (term != TZ_T_NONE) {
+                *known_ev = ev_make(term == TZ_T_WIN ? TZ_E_WIN : (term == TZ_T_LOSS ? TZ_E_LOSS : TZ_E_DRAW), 0);
+                if (lane == 0) {
+                    node_set_eval(t, slot, *known_ev);
+                    t.std_dev[slot] = 0.0f;
+                }
+                __syncwarp();
+                return 1;
+            }
+            return 0;
+        }
+        bool nan_seen;
+        const int idx = warp_select_puct(t, slot, beta, d.ln_table, lane, &nan_seen);
+        if (nan_seen) flag_error(d, TZ_ERR_NAN, lane);
+        if (idx < 0) {
+            flag_error(d, TZ_ERR_NO_CHILD, lane);
+            return -1;
+        }
+        slot = t.first[slot] + (uint32_t)idx;
+        if (!warp_apply(st, d.n, (uint16_t)tz_meta_move(t.meta[slot]), lane)) flag_error(d, TZ_ERR_BAD_MOVE, lane);
+    }
+}
+
+// Forward::NeedsNetwork: legal moves + leaf position into evaluation-queue slot q
+__device__ __forceinline__ bool warp_enqueue(const TzDev& d, int g, int q, TzState* st, uint16_t* moves, int lane) {
+    const int cnt = warp_movegen(st, d.n, moves, lane);
+    if (cnt < 0 || cnt > d.M) {
+        flag_error(d, TZ_ERR_TOO_MANY_MOVES, lane);
+        return false;
+    }
+    if (lane == 0) {
+        d.nn_queue[q] = g;
+        d.n_actions[q] = cnt;
+    }
+    warp_store_state(&d.leaf_state[q], st, lane);
+    uint16_t* out = d.actions + (size_t)q * d.M;
+    for (int i = lane; i < cnt; i += 32) out[i] = moves[i];
+    return true;
+}
+
 __global__ void __launch_bounds__(32 * WPB) k_select(TzDev d, int phase, int halving_i, const float* betas) {
     __shared__ TzState s_state[WPB];
     __shared__ uint16_t s_moves[WPB][TZ_MAX_MOVES];
@@ -54,53 +121,11 @@ __global__ void __launch_bounds__(32 * WPB) k_select(TzDev d, int phase, int hal
         if (!warp_apply(st, d.n, (uint16_t)tz_meta_move(t.meta[slot]), lane)) flag_error(d, TZ_ERR_BAD_MOVE, lane);
     }
     if (lane == 0) ctr[0] += 1;
-
     int len = 0;
-    bool known = false;
     Ev known_ev = ev_value(0.0f);
-    while (true) {
-        if (len >= TZ_MAX_DEPTH) {
-            flag_error(d, TZ_ERR_DEPTH, lane);
-            return;
-        }
-        if (lane == 0) {
-            t.visits[slot] += 1;
-            traj[len] = slot;
-        }
-        len++;
-        __syncwarp();
-        const uint32_t meta = t.meta[slot];
-        const uint32_t tag = tz_meta_tag(meta);
-        if (tag != TZ_E_VALUE && t.eval[slot] == 0) {  // is_terminal
-            known = true;
-            known_ev = ev_make(tag, 0);
-            break;
-        }
-        if (tz_meta_nchild(meta) == 0 && tag == TZ_E_VALUE) {  // needs_initialization
-            const int term = warp_terminal(st, d.n, d.half_komi, d.rev_limit, lane);
-            if (term != TZ_T_NONE) {
-                known = true;
-                known_ev = ev_make(term == TZ_T_WIN ? TZ_E_WIN : (term == TZ_T_LOSS ? TZ_E_LOSS : TZ_E_DRAW), 0);
-                if (lane == 0) {
-                    node_set_eval(t, slot, known_ev);
-                    t.std_dev[slot] = 0.0f;
-                }
-                __syncwarp();
-            }
-            break;
-        }
-        bool nan_seen;
-        const int idx = warp_select_puct(t, slot, beta, d.ln_table, lane, &nan_seen);
-        if (nan_seen) flag_error(d, TZ_ERR_NAN, lane);
-        if (idx < 0) {
-            flag_error(d, TZ_ERR_NO_CHILD, lane);
-            return;
-        }
-        slot = t.first[slot] + (uint32_t)idx;
-        if (!warp_apply(st, d.n, (uint16_t)tz_meta_move(t.meta[slot]), lane)) flag_error(d, TZ_ERR_BAD_MOVE, lane);
-    }
-
-    if (known) {
+    const int res = warp_forward(d, t, st, traj, slot, beta, lane, &len, &known_ev);
+    if (res < 0) return;
+    if (res == 1) {
         if (lane == 0) ctr[2] += 1;
         Propagated p;
         p.eval = known_ev;
@@ -108,24 +133,14 @@ __global__ void __launch_bounds__(32 * WPB) k_select(TzDev d, int phase, int hal
         warp_backup(t, traj, len, p, lane);
         return;
     }
-    // Forward::NeedsNetwork: legal moves + leaf position go to the evaluation queue
-    const int cnt = warp_movegen(st, d.n, s_moves[warp], lane);
-    if (cnt < 0 || cnt > d.M) {
-        flag_error(d, TZ_ERR_TOO_MANY_MOVES, lane);
-        return;
-    }
     int q = 0;
     if (lane == 0) {
         q = atomicAdd(d.nn_count, 1);
-        d.nn_queue[q] = g;
-        d.n_actions[q] = cnt;
         d.traj_len[g] = len;
         ctr[1] += 1;
     }
     q = __shfl_sync(FULL_MASK, q, 0);
-    warp_store_state(&d.leaf_state[q], st, lane);
-    uint16_t* out = d.actions + (size_t)q * d.M;
-    for (int i = lane; i < cnt; i += 32) out[i] = s_moves[warp][i];
+    warp_enqueue(d, g, q, st, s_moves[warp], lane);
 }
 
 // ---- synthetic agent (oracle/tak_search.c `tk_agent_synthetic`) ----------------------
@@ -175,19 +190,14 @@ __device__ __forceinline__ bool warp_softmax_inplace(float* buf, int n, int lane
     return !__any_sync(FULL_MASK, bad);
 }
 
-__global__ void __launch_bounds__(32 * WPB) k_expand(TzDev d) {
-    __shared__ float s_p[WPB][TZ_MAX_MOVES];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = blockIdx.x * WPB + warp;
-    if (q >= *d.nn_count) return;
-    const int g = d.nn_queue[q];
+// softmax + backward_network_eval (mcts.rs:171-225) of evaluation-queue entry q of game g whose selection
+// path is traj[0..len)
+__device__ __forceinline__ void warp_expand(const TzDev& d, int g, int q, const uint32_t* traj, int len, float* p,
+                                            int lane) {
     const int n = d.n_actions[q];
     const GameTree t = game_tree(d.arena, g);
-    const uint32_t* traj = d.traj + (size_t)g * TZ_MAX_DEPTH;
-    const int len = d.traj_len[g];
     const float* lg = d.logits + (size_t)q * d.M;
     const uint16_t* act = d.actions + (size_t)q * d.M;
-    float* p = s_p[warp];
     for (int i = lane; i < n; i += 32) p[i] = lg[i];
     __syncwarp();
     const float value = d.value[q], variance = d.variance[q];
@@ -239,6 +249,66 @@ __global__ void __launch_bounds__(32 * WPB) k_expand(TzDev d) {
     pr.eval = ev_value(fmul(value, 0.997f));
     pr.variance = fmul(fmul(variance, 0.997f), 0.997f);
     warp_backup(t, traj, len, pr, lane);
+}
+
+__global__ void __launch_bounds__(32 * WPB) k_expand(TzDev d) {
+    __shared__ float s_p[WPB][TZ_MAX_MOVES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * WPB + warp;
+    if (q >= *d.nn_count) return;
+    const int g = d.nn_queue[q];
+    warp_expand(d, g, q, d.traj + (size_t)g * TZ_MAX_DEPTH, d.traj_len[g], s_p[warp], lane);
+}
+
+// ---- single tree: Node::simulate_simple / simulate_batch (mcts.rs:235-328) on game 0 -------------------------
+
+// Up to `max_forwards` sequential descents of ONE tree by one warp: the visit increments of earlier
+// descents steer later ones (the reference's only "virtual loss"); known results are backed up at once,
+// leaves that need the network fill queue slots 0..batch_size-1 in order, their paths go to traj[q].
+__global__ void __launch_bounds__(32) k_tree_forward(TzDev d, float beta, int batch_size, int max_forwards) {
+    __shared__ TzState s_state;
+    __shared__ uint16_t s_moves[TZ_MAX_MOVES];
+    const int lane = threadIdx.x & 31;
+    const GameTree t = game_tree(d.arena, 0);
+    unsigned long long* ctr = d.counters;
+    int filled = 0;
+    for (int it = 0; it < max_forwards && filled < batch_size; it++) {
+        __syncwarp();
+        warp_load_state(&s_state, &d.env[0], lane);
+        uint32_t* traj = d.traj + (size_t)filled * TZ_MAX_DEPTH;
+        if (lane == 0) ctr[0] += 1;
+        int len = 0;
+        Ev known_ev = ev_value(0.0f);
+        const int res = warp_forward(d, t, &s_state, traj, 0, beta, lane, &len, &known_ev);
+        if (res < 0) break;
+        if (res == 1) {
+            if (lane == 0) ctr[2] += 1;
+            Propagated p;
+            p.eval = known_ev;
+            p.variance = 0.0f;
+            warp_backup(t, traj, len, p, lane);
+            continue;
+        }
+        if (lane == 0) {
+            d.traj_len[filled] = len;
+            ctr[1] += 1;
+        }
+        if (!warp_enqueue(d, 0, filled, &s_state, s_moves, lane)) break;
+        filled++;
+        __syncwarp();
+    }
+    if (lane == 0) *d.nn_count = filled;
+}
+
+// backward_network_eval of the queued leaves, in queue order (the order matters: they share one tree)
+__global__ void __launch_bounds__(32) k_tree_backward(TzDev d) {
+    __shared__ float s_p[TZ_MAX_MOVES];
+    const int lane = threadIdx.x & 31;
+    const int count = *d.nn_count;
+    for (int q = 0; q < count; q++) {
+        warp_expand(d, 0, q, d.traj + (size_t)q * TZ_MAX_DEPTH, d.traj_len[q], s_p, lane);
+        __syncwarp();
+    }
 }
 
 // ---- Gumbel top-k and sequential halving -----------------------------------------------
@@ -416,11 +486,11 @@ __device__ __forceinline__ void copy_node(const GameTree& dst, uint32_t to, cons
     dst.first[to] = src.first[from];
 }
 
-__global__ void __launch_bounds__(32 * WPB) k_step(TzDev d, const uint16_t* moves) {
+__global__ void __launch_bounds__(32 * WPB) k_step(TzDev d, const uint16_t* moves, int only_game) {
     __shared__ TzState s_state[WPB];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.x * WPB + warp;
-    if (g >= d.G) return;
+    if (g >= d.G || (only_game >= 0 && g != only_game)) return;
     const int half = d.arena.half[g];
     const GameTree src = game_tree_half(d.arena, g, half);
     const uint32_t rmeta = src.meta[0];
@@ -706,11 +776,11 @@ __global__ void __launch_bounds__(32 * WPB) k_targets(TzDev d, float visitations
     }
 }
 
-// select_best_action (node/mod.rs:132-163); returns the child index, -1 without children
-__device__ __forceinline__ int warp_select_best(const GameTree& t, int lane) {
-    const uint32_t meta = t.meta[0];
+// select_best_action (node/mod.rs:132-163) of node `slot`; returns the child index, -1 without children
+__device__ __forceinline__ int warp_select_best(const GameTree& t, int lane, uint32_t slot = 0) {
+    const uint32_t meta = t.meta[slot];
     const int n = (int)tz_meta_nchild(meta);
-    const uint32_t first = t.first[0];
+    const uint32_t first = t.first[slot];
     if (n == 0) return -1;
     if (tz_meta_tag(meta) != TZ_E_VALUE) {
         Ev m;
@@ -819,6 +889,27 @@ __global__ void k_merge_moves(TzDev d, int weighted_random_plies, const uint16_t
     if ((int)d.env[g].ply < weighted_random_plies) moves[g] = sampled[g];
 }
 
+// Node::principal_variation (node/mod.rs:40-62) of game 0's tree
+__global__ void __launch_bounds__(32) k_tree_pv(TzDev d, uint16_t* out_moves, int cap, int* out_len) {
+    const int lane = threadIdx.x & 31;
+    const GameTree t = game_tree(d.arena, 0);
+    uint32_t slot = 0;
+    int len = 0;
+    while (len < cap) {
+        const uint32_t meta = t.meta[slot];
+        const uint32_t tag = tz_meta_tag(meta);
+        const bool needs_init = tz_meta_nchild(meta) == 0 && tag == TZ_E_VALUE;
+        const bool terminal = tag != TZ_E_VALUE && t.eval[slot] == 0;
+        if (needs_init || terminal) break;
+        const int idx = warp_select_best(t, lane, slot);
+        if (idx < 0) break;
+        slot = t.first[slot] + (uint32_t)idx;
+        if (lane == 0) out_moves[len] = (uint16_t)tz_meta_move(t.meta[slot]);
+        len++;
+    }
+    if (lane == 0) *out_len = len;
+}
+
 // ---- rules parity hooks --------------------------------------------------------------------
 
 __global__ void __launch_bounds__(32 * WPB) k_rules_probe(TzDev d, const TzState* states, int count, int stride,
@@ -883,8 +974,15 @@ void launch_halve(const TzDev& d, const float* betas, float visits, int remainin
 void launch_finalize(const TzDev& d, uint16_t* out_moves, cudaStream_t st) {
     k_finalize<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, out_moves);
 }
-void launch_step(const TzDev& d, const uint16_t* moves, cudaStream_t st) {
-    k_step<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, moves);
+void launch_step(const TzDev& d, const uint16_t* moves, cudaStream_t st, int only_game) {
+    k_step<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, moves, only_game);
+}
+void launch_tree_forward(const TzDev& d, float beta, int batch_size, int max_forwards, cudaStream_t st) {
+    k_tree_forward<<<1, 32, 0, st>>>(d, beta, batch_size, max_forwards);
+}
+void launch_tree_backward(const TzDev& d, cudaStream_t st) { k_tree_backward<<<1, 32, 0, st>>>(d); }
+void launch_tree_pv(const TzDev& d, uint16_t* out_moves, int cap, int* out_len, cudaStream_t st) {
+    k_tree_pv<<<1, 32, 0, st>>>(d, out_moves, cap, out_len);
 }
 void launch_new_openings(const TzDev& d, const uint8_t* mask, const int* sym, const int* adj, unsigned long long seed,
                          unsigned long long counter, cudaStream_t st) {
