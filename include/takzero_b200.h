@@ -83,6 +83,7 @@ typedef struct tz_config_t {
     int reversible_limit;  /* reversible-ply draw threshold; 0 = default 100 (unpinned) */
     int move_stride;       /* row stride of per-game move/logit tables; 0 = default for board_n */
     uint32_t arena_slots;  /* node slots per game per arena half; 0 = sized from free HBM */
+    int tree_batch;        /* single-tree use (tz_tree_*): leaves per network batch; 0 = n_games */
 } tz_config_t;
 
 typedef struct tz_handle tz_handle;

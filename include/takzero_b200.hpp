@@ -333,7 +333,8 @@ struct Weights {
 
 class BatchedMCTS {
   public:
-    BatchedMCTS(int board_n, int half_komi, int n_games, int device = 0, int game_base = 0, uint32_t arena_slots = 0)
+    BatchedMCTS(int board_n, int half_komi, int n_games, int device = 0, int game_base = 0, uint32_t arena_slots = 0,
+                int tree_batch = 0)
         : n_(board_n), games_(n_games) {
         tz_config_t cfg{};
         cfg.board_n = board_n;
@@ -342,6 +343,7 @@ class BatchedMCTS {
         cfg.device = device;
         cfg.game_base = game_base;
         cfg.arena_slots = arena_slots;
+        cfg.tree_batch = tree_batch;
         check(tz_create(&cfg, &h_));
         check(tz_info(h_, &stride_, nullptr, nullptr, nullptr));
     }
@@ -462,6 +464,17 @@ class BatchedMCTS {
         check(len);
         r.actions.assign(buf.begin(), buf.begin() + len);
         return r;
+    }
+    // ---- single tree = game 0 (tei / analysis): Node::simulate_simple / simulate_batch / descend / PV ----
+    void tree_simulate_simple(float beta) { check(tz_tree_simulate_simple(h_, beta)); }
+    void tree_simulate_batch(float beta, int batch_size) { check(tz_tree_simulate_batch(h_, beta, batch_size)); }
+    void tree_descend(Move m) { check(tz_tree_descend(h_, m)); }
+    std::vector<Move> principal_variation(int cap = 64) {
+        std::vector<Move> pv(cap);
+        const int len = tz_tree_principal_variation(h_, pv.data(), cap);
+        check(len);
+        pv.resize(len);
+        return pv;
     }
     tz_counters_t counters() {
         tz_counters_t c;

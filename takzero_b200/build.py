@@ -64,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
-HOSTS = ["selfplay", "reanalyze"]
+HOSTS = ["selfplay", "reanalyze", "tei"]
 
 
 def build_hosts() -> None:

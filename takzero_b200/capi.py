@@ -69,6 +69,7 @@ class Config(C.Structure):
         ("reversible_limit", C.c_int),
         ("move_stride", C.c_int),
         ("arena_slots", C.c_uint32),
+        ("tree_batch", C.c_int),
     ]
 
 
@@ -212,9 +213,10 @@ class BatchedMCTS:
     """Host mirror of `BatchedMCTS<BATCH_SIZE, Env>`; all state lives on the device."""
 
     def __init__(self, board_n: int, half_komi: int, n_games: int, device: int = 0, game_base: int = 0,
-                 reversible_limit: int = 0, move_stride: int = 0, arena_slots: int = 0):
+                 reversible_limit: int = 0, move_stride: int = 0, arena_slots: int = 0, tree_batch: int = 0):
         self._h = C.c_void_p()
-        cfg = Config(board_n, half_komi, n_games, device, game_base, reversible_limit, move_stride, arena_slots)
+        cfg = Config(board_n, half_komi, n_games, device, game_base, reversible_limit, move_stride, arena_slots,
+                     tree_batch)
         _check(lib().tz_create(C.byref(cfg), C.byref(self._h)))
         self.n = board_n
         self.half_komi = half_komi

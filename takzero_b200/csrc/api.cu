@@ -83,10 +83,11 @@ extern "C" TZ_API int tz_create(const tz_config_t* cfg, tz_handle** out) {
     d.half_komi = cfg->half_komi;
     d.rev_limit = cfg->reversible_limit > 0 ? cfg->reversible_limit : 100;
     d.G = cfg->n_games;
+    d.Q = cfg->tree_batch > cfg->n_games ? cfg->tree_batch : cfg->n_games;
     d.M = cfg->move_stride > 0 ? cfg->move_stride : default_stride(d.n);
     if (d.M > TZ_MAX_MOVES) return fail(TZ_EINVAL, "move_stride > %d", TZ_MAX_MOVES);
     d.game_base = cfg->game_base;
-    const size_t G = (size_t)d.G;
+    const size_t G = (size_t)d.G, Q = (size_t)d.Q;
 
     uint32_t cap = cfg->arena_slots;
     if (cap == 0) {
@@ -115,16 +116,16 @@ extern "C" TZ_API int tz_create(const tz_config_t* cfg, tz_handle** out) {
     DM(d.start_env, G);
     DM(d.replay, G * TZ_MAX_PLIES);
     DM(d.replay_len, G);
-    DM(d.traj, G * TZ_MAX_DEPTH);
-    DM(d.traj_len, G);
-    DM(d.nn_queue, G);
+    DM(d.traj, Q * TZ_MAX_DEPTH);
+    DM(d.traj_len, Q);
+    DM(d.nn_queue, Q);
     DM(d.nn_count, 1);
-    DM(d.leaf_state, G);
-    DM(d.actions, G * d.M);
-    DM(d.n_actions, G);
-    DM(d.logits, G * d.M);
-    DM(d.value, G);
-    DM(d.variance, G);
+    DM(d.leaf_state, Q);
+    DM(d.actions, Q * d.M);
+    DM(d.n_actions, Q);
+    DM(d.logits, Q * d.M);
+    DM(d.value, Q);
+    DM(d.variance, Q);
     float* ln_table = nullptr;
     DM(ln_table, (size_t)TZ_LN_TABLE);
     DM(d.set_child, G * TZ_MAX_K);
@@ -450,7 +451,7 @@ extern "C" TZ_API int tz_set_agent(tz_handle* h, int kind, tz_agent_fn fn, void*
     CHECK_H(h);
     if (kind == TZ_AGENT_HOST) {
         if (!fn) return fail(TZ_EINVAL, "TZ_AGENT_HOST needs a callback");
-        const size_t G = (size_t)h->d.G, M = (size_t)h->d.M;
+        const size_t G = (size_t)h->d.Q, M = (size_t)h->d.M;
         if (!h->pin_states) {
             CU(cudaHostAlloc((void**)&h->pin_states, G * sizeof(TzState), cudaHostAllocDefault));
             CU(cudaHostAlloc((void**)&h->pin_actions, G * M * sizeof(uint16_t), cudaHostAllocDefault));
@@ -789,7 +790,7 @@ extern "C" TZ_API int tz_evaluate(tz_handle* h, const tz_state_t* states, int co
     const TzDev& d = h->d;
     if (!nn_ready(h)) return fail(TZ_ENOWEIGHTS, "tz_evaluate needs tz_set_weights first");
     if (!states || !actions || !n_actions || !logits || !values || !variances) return fail(TZ_EINVAL, "null argument");
-    if (count <= 0 || count > d.G) return fail(TZ_EINVAL, "count must be 1..n_games");
+    if (count <= 0 || count > d.Q) return fail(TZ_EINVAL, "count must be 1..max(n_games, tree_batch)");
     if (stride != d.M) return fail(TZ_EINVAL, "stride must equal move_stride (%d)", d.M);
     for (int i = 0; i < count; i++)
         if (n_actions[i] < 0 || n_actions[i] > stride) return fail(TZ_EINVAL, "bad n_actions[%d]", i);
@@ -836,7 +837,7 @@ extern "C" TZ_API int tz_debug_layer_limit(tz_handle* h, int limit) {
 extern "C" TZ_API int tz_debug_activations(tz_handle* h, int which, int count, float* out) {
     CHECK_H(h);
     if (!nn_ready(h)) return fail(TZ_ENOWEIGHTS, "no weights");
-    if (which < 0 || which > 2 || count <= 0 || count > h->d.G || !out) return fail(TZ_EINVAL, "bad argument");
+    if (which < 0 || which > 2 || count <= 0 || count > h->d.Q || !out) return fail(TZ_EINVAL, "bad argument");
     const int n = h->d.n, ch = which == 2 ? 64 : 256;
     const size_t total = (size_t)count * n * n * ch;
     Scratch s;
@@ -986,7 +987,8 @@ extern "C" TZ_API int tz_simhash_indices(tz_handle* h, const tz_state_t* states,
 
 static int tree_simulate(tz_handle* h, float beta, int batch_size, int max_forwards) {
     const TzDev& d = h->d;
-    if (batch_size <= 0 || batch_size > d.G) return fail(TZ_EINVAL, "batch_size must be 1..n_games (%d)", d.G);
+    if (batch_size <= 0 || batch_size > d.Q)
+        return fail(TZ_EINVAL, "batch_size must be 1..max(n_games, tree_batch) (%d)", d.Q);
     h->prof_active = false;
     launch_tree_forward(d, beta, batch_size, max_forwards, h->stream);
     int rc = run_agent(h);

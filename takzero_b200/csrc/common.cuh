@@ -78,6 +78,7 @@ enum {
 struct TzDev {
     int n, nn, half_komi, rev_limit;
     int G;          // games on this device
+    int Q;          // evaluation-queue capacity: max(G, tree_batch)
     int M;          // stride of per-position move / logit rows (<= TZ_MAX_MOVES)
     int game_base;  // global id of game 0 (multi-GPU sharding)
     TzArena arena;

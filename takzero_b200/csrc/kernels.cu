@@ -958,7 +958,7 @@ static inline int blocks_for(int items) { return (items + WPB - 1) / WPB; }
 void launch_select(const TzDev& d, int phase, int halving_i, const float* betas, cudaStream_t st) {
     k_select<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, phase, halving_i, betas);
 }
-void launch_agent_synth(const TzDev& d, cudaStream_t st) { k_agent_synth<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d); }
+void launch_agent_synth(const TzDev& d, cudaStream_t st) { k_agent_synth<<<blocks_for(d.Q), 32 * WPB, 0, st>>>(d); }
 void launch_expand(const TzDev& d, cudaStream_t st) { k_expand<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d); }
 void launch_gumbel_noise(const TzDev& d, float* out, int stride, unsigned long long seed, unsigned long long counter,
                          cudaStream_t st) {

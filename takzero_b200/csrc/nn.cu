@@ -443,7 +443,7 @@ int nn_set_weights(tz_handle* h, const char* const* names, const float* const* d
     }
 #undef NEED
     // activation buffers: guard rows + all boards, rounded up to whole tiles, + halo
-    s->max_positions = h->d.G;
+    s->max_positions = h->d.Q;
     const size_t used = (size_t)s->max_positions * nn;
     s->rows = conv::HALO + ((used + 2 * conv::TILE_M - 1) / (2 * conv::TILE_M)) * (2 * conv::TILE_M) + 2 * conv::HALO;
     auto dalloc = [&](void** p, size_t bytes) -> bool {
@@ -576,7 +576,7 @@ int nn_forward(tz_handle* h, const TzState* states, const int* count_ptr, int co
 
 int nn_forward_queue(tz_handle* h) {
     const TzDev& d = h->d;
-    return nn_forward(h, d.leaf_state, d.nn_count, d.G, d.actions, d.n_actions, d.logits, d.value, d.variance);
+    return nn_forward(h, d.leaf_state, d.nn_count, d.Q, d.actions, d.n_actions, d.logits, d.value, d.variance);
 }
 
 int nn_encode_planes(tz_handle* h, const TzState* states, int count, float* out_f32) {
