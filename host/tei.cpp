@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <deque>
 #include <iostream>
 #include <sstream>
 #include <string>
@@ -84,7 +85,16 @@ int main(int argc, char** argv) {
             mcts.set_positions(std::vector<tz_state_t>(1, e));  // node = Node::default()
         };
         std::string line;
-        while (std::getline(std::cin, line)) {
+        std::deque<std::string> pending;  // commands that arrived while a search was running
+        auto next_line = [&](std::string& out) {
+            if (!pending.empty()) {
+                out = pending.front();
+                pending.pop_front();
+                return true;
+            }
+            return (bool)std::getline(std::cin, out);
+        };
+        while (next_line(line)) {
             std::istringstream in(line);
             std::string cmd;
             in >> cmd;
@@ -182,13 +192,15 @@ int main(int argc, char** argv) {
                         last_info = Clock::now();
                     }
                     if (done) break;
-                    if (stdin_ready()) {  // `stop` (or anything else) ends the search, like GoStatus::Stopping
+                    if (stdin_ready()) {  // `stop` / `quit` end the search (GoStatus::Stopping); the rest waits
                         std::string peek;
-                        std::getline(std::cin, peek);
-                        if (peek.rfind("stop", 0) == 0 || peek.rfind("quit", 0) == 0) {
-                            if (peek.rfind("quit", 0) == 0) nodes = 0, move_time_ms = -2;
+                        if (!std::getline(std::cin, peek)) break;
+                        if (peek.rfind("stop", 0) == 0) break;
+                        if (peek.rfind("quit", 0) == 0) {
+                            move_time_ms = -2;
                             break;
                         }
+                        pending.push_back(peek);
                     }
                 }
                 const std::vector<Move> pv = mcts.principal_variation();

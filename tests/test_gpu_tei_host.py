@@ -43,13 +43,35 @@ def test_tei_session_matches_python_replay():
     v2, pv2 = python_go(m, 1000)
     m.close()
 
-    script = "\n".join([
-        "tei", "isready", f"teinewgame {n}", "position startpos moves a1 e5", "go nodes 2000",
-        f"position startpos moves a1 e5 {O.move_str(pv1[0])} {O.move_str(reply)}", "go nodes 1000", "quit", ""])
-    out = subprocess.run([exe, "--board", str(n), "--half-komi", str(hk), "--arena-slots", str(1 << 20)],
-                         input=script, capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0, out.stderr
-    lines = out.stdout.splitlines()
+    proc = subprocess.Popen([exe, "--board", str(n), "--half-komi", str(hk), "--arena-slots", str(1 << 20)],
+                            stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, bufsize=1)
+    lines = []
+
+    def send(cmd):
+        proc.stdin.write(cmd + "\n")
+        proc.stdin.flush()
+
+    def read_until(prefix):
+        while True:
+            line = proc.stdout.readline()
+            assert line, "engine exited: " + proc.stderr.read()
+            lines.append(line.rstrip("\n"))
+            if lines[-1].startswith(prefix):
+                return
+
+    send("tei")
+    read_until("teiok")
+    send("isready")
+    read_until("readyok")
+    send(f"teinewgame {n}")
+    send("position startpos moves a1 e5")
+    send("go nodes 2000")
+    read_until("bestmove")
+    send(f"position startpos moves a1 e5 {O.move_str(pv1[0])} {O.move_str(reply)}")  # extends: tree reuse
+    send("go nodes 1000")
+    read_until("bestmove")
+    send("quit")
+    assert proc.wait(timeout=60) == 0
     assert "teiok" in lines and "readyok" in lines
     best = [l.split()[1] for l in lines if l.startswith("bestmove")]
     assert best == [O.move_str(pv1[0]), O.move_str(pv2[0])]
