@@ -189,6 +189,10 @@ TZ_API int tz_select_best(tz_handle* h, tz_move_t* out_moves);
 TZ_API int tz_select_selfplay(tz_handle* h, int weighted_random_plies, uint32_t threshold, float allowed_eval_drop,
                        const uint64_t* randoms, uint64_t seed, tz_move_t* out_moves);
 TZ_API int tz_counters(tz_handle* h, tz_counters_t* out);
+/* BatchedMCTS::apply_noise / Node::apply_dirichlet (batched.rs:146-151, node/noise.rs:10-26): the host mixes
+ * p' = p*(1-ratio) + noise*ratio and takes logit' = ln(p') with its libm (as the reference does) from
+ * tz_root_children, then stores both here: [n_games][stride], child order */
+TZ_API int tz_set_root_priors(tz_handle* h, int stride, const float* prob, const float* logit);
 
 /* One self-play move of every game without host buffers (the loop body of selfplay/src/main.rs:
  * 138-153, 238-329 minus the file I/O): search with library-drawn Gumbel noise, improved-policy /

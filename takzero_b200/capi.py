@@ -152,6 +152,7 @@ def lib():
         "tz_select_best": ([vp, vp], i32),
         "tz_select_selfplay": ([vp, i32, u32, f32, vp, u64, vp], i32),
         "tz_counters": ([vp, P(Counters)], i32),
+        "tz_set_root_priors": ([vp, i32, vp, vp], i32),
         "tz_tree_simulate_simple": ([vp, f32], i32),
         "tz_tree_simulate_batch": ([vp, f32, i32], i32),
         "tz_tree_descend": ([vp, C.c_uint16], i32),
@@ -391,6 +392,18 @@ class BatchedMCTS:
         _check(lib().tz_select_selfplay(self._h, weighted_random_plies, threshold, allowed_drop, _ptr(r), seed,
                                         _ptr(out)))
         return out
+
+    def apply_noise(self, noise: np.ndarray, ratio: float) -> None:
+        """BatchedMCTS::apply_noise with injected Dirichlet samples `noise` [G, move_stride] (the reference
+        draws them from rand_distr, whose stream is not pinned): p' = p*(1-ratio) + noise*ratio, logit' = ln p'
+        in f32 on the host (node/noise.rs:18-25), stored back into the roots."""
+        tbl = self.root_children()
+        noise = _arr(noise, np.float32, (self.G, self.move_stride))
+        r = np.float32(ratio)
+        prob = (tbl["prob"] * (np.float32(1.0) - r) + noise * r).astype(np.float32)
+        with np.errstate(divide="ignore"):
+            logit = np.log(prob, dtype=np.float32)
+        _check(lib().tz_set_root_priors(self._h, self.move_stride, _ptr(prob), _ptr(logit)))
 
     def counters(self) -> Counters:
         c = Counters()

@@ -1033,3 +1033,16 @@ extern "C" TZ_API int tz_tree_principal_variation(tz_handle* h, tz_move_t* out_m
     CU(cudaGetLastError());
     return *len;
 }
+
+// BatchedMCTS::apply_noise (batched.rs:146-151) support: store host-computed priors / logits of the roots
+extern "C" TZ_API int tz_set_root_priors(tz_handle* h, int stride, const float* prob, const float* logit) {
+    CHECK_H(h);
+    const TzDev& d = h->d;
+    if (!prob || !logit || stride <= 0 || stride > d.M) return fail(TZ_EINVAL, "bad argument");
+    const size_t cells = (size_t)d.G * stride;
+    CU(cudaMemcpyAsync(h->tbl_f32a, prob, cells * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->tbl_f32b, logit, cells * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    launch_set_root_priors(d, stride, h->tbl_f32a, h->tbl_f32b, h->stream);
+    h->launches += 1;
+    return finish(h);
+}

@@ -910,6 +910,22 @@ __global__ void __launch_bounds__(32) k_tree_pv(TzDev d, uint16_t* out_moves, in
     if (lane == 0) *out_len = len;
 }
 
+// overwrite the priors of every root's children (Node::apply_dirichlet, node/noise.rs:10-26: the mixing and
+// the `ln` are done by the host with its libm, like the reference; this only stores the result)
+__global__ void __launch_bounds__(32 * WPB) k_set_root_priors(TzDev d, int stride, const float* prob, const float* logit) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * WPB + warp;
+    if (g >= d.G) return;
+    const GameTree t = game_tree(d.arena, g);
+    int n = (int)tz_meta_nchild(t.meta[0]);
+    if (n > stride) n = stride;
+    const uint32_t first = t.first[0];
+    for (int i = lane; i < n; i += 32) {
+        t.prob[first + i] = prob[(size_t)g * stride + i];
+        t.logit[first + i] = logit[(size_t)g * stride + i];
+    }
+}
+
 // ---- rules parity hooks --------------------------------------------------------------------
 
 __global__ void __launch_bounds__(32 * WPB) k_rules_probe(TzDev d, const TzState* states, int count, int stride,
@@ -981,6 +997,9 @@ void launch_tree_forward(const TzDev& d, float beta, int batch_size, int max_for
     k_tree_forward<<<1, 32, 0, st>>>(d, beta, batch_size, max_forwards);
 }
 void launch_tree_backward(const TzDev& d, cudaStream_t st) { k_tree_backward<<<1, 32, 0, st>>>(d); }
+void launch_set_root_priors(const TzDev& d, int stride, const float* prob, const float* logit, cudaStream_t st) {
+    k_set_root_priors<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, stride, prob, logit);
+}
 void launch_tree_pv(const TzDev& d, uint16_t* out_moves, int cap, int* out_len, cudaStream_t st) {
     k_tree_pv<<<1, 32, 0, st>>>(d, out_moves, cap, out_len);
 }

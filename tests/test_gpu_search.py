@@ -228,3 +228,28 @@ def test_arena_overflow_is_reported():
         for _ in range(20):
             m.simulate(None)
     m.close()
+
+
+def test_apply_noise_keeps_distribution():
+    """node/noise.rs:48-67 `distribution_stays_1_after_noise`: after mixing Dirichlet noise the priors still
+    sum to 1 and logit = ln p; the mixed priors are what the next search uses."""
+    n, hk, G = 4, 4, 8
+    m = capi.BatchedMCTS(n, hk, G, arena_slots=1 << 14)
+    m.new_openings(seed=3)
+    m.simulate(None)
+    before = m.root_children()
+    rng = np.random.default_rng(0)
+    noise = np.zeros((G, m.move_stride), dtype=np.float32)
+    for g in range(G):
+        noise[g, : before["n"][g]] = rng.dirichlet([0.3] * int(before["n"][g]))
+    m.apply_noise(noise, 0.25)
+    after = m.root_children()
+    for g in range(G):
+        k = after["n"][g]
+        p = after["prob"][g, :k]
+        assert abs(float(p.sum()) - 1.0) < 1e-5
+        want = before["prob"][g, :k] * np.float32(0.75) + noise[g, :k] * np.float32(0.25)
+        assert np.array_equal(p, want.astype(np.float32))
+        assert np.array_equal(after["logit"][g, :k], np.log(p, dtype=np.float32))
+    m.simulate(None)  # still searchable
+    m.close()
