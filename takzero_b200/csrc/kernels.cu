@@ -689,6 +689,16 @@ __global__ void __launch_bounds__(32 * WPB) k_root_table(TzDev d, int stride, in
         prob[o] = t.prob[c];
         std_dev[o] = t.std_dev[c];
     }
+    for (int i = n + lane; i < stride; i += 32) {  // cells past the last child read as zero
+        const size_t o = (size_t)g * stride + i;
+        moves[o] = 0;
+        visits[o] = 0;
+        eval_tag[o] = 0;
+        eval_bits[o] = 0;
+        logit[o] = 0.0f;
+        prob[o] = 0.0f;
+        std_dev[o] = 0.0f;
+    }
 }
 
 // per game: {eval tag, eval bits, visits, std bits, child count, arena slots in use}
@@ -764,6 +774,10 @@ __global__ void __launch_bounds__(32 * WPB) k_targets(TzDev d, float visitations
     for (int i = lane; i < m; i += 32) {
         out_policy[(size_t)g * stride + i] = p[i];
         if (out_moves) out_moves[(size_t)g * stride + i] = (uint16_t)tz_meta_move(t.meta[first + i]);
+    }
+    for (int i = m + lane; i < stride; i += 32) {
+        out_policy[(size_t)g * stride + i] = 0.0f;
+        if (out_moves) out_moves[(size_t)g * stride + i] = 0;
     }
     if (lane == 0) {
         out_n[g] = n;
