@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <stdexcept>
@@ -187,13 +188,30 @@ inline bool parse_tps(const std::string& text, int n, tz_state_t* g) {
     return true;
 }
 
-// Rust `{}` of an f32: shortest decimal that round-trips, never in exponent form ("1", "0.5", "-0.0009")
+// Rust `{}` of an f32: the shortest decimal digits that round-trip, written positionally (never in
+// exponent form): "1", "0.5", "-0.0009", "340000000000000000000000000000000000000"
 inline std::string format_f32(float v) {
     if (std::isnan(v)) return "NaN";
     if (std::isinf(v)) return v > 0 ? "inf" : "-inf";
-    char buf[128];
-    auto r = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::fixed);
-    return std::string(buf, r.ptr);
+    if (v == 0.0f) return std::signbit(v) ? "-0" : "0";
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof(buf), std::fabs(v), std::chars_format::scientific);  // d.ddde[+-]XX
+    std::string sci(buf, r.ptr);
+    const size_t epos = sci.find('e');
+    const int exp10 = std::atoi(sci.c_str() + epos + 1);
+    std::string digits;
+    for (size_t i = 0; i < epos; i++)
+        if (sci[i] != '.') digits += sci[i];
+    std::string out = std::signbit(v) ? "-" : "";
+    const int point = exp10 + 1;  // position of the decimal point relative to the first digit
+    if (point <= 0) {
+        out += "0." + std::string((size_t)(-point), '0') + digits;
+    } else if ((size_t)point >= digits.size()) {
+        out += digits + std::string((size_t)point - digits.size(), '0');
+    } else {
+        out += digits.substr(0, (size_t)point) + "." + digits.substr((size_t)point);
+    }
+    return out;
 }
 
 inline const char* result_string(int game_result) {  // tz_game_result codes

@@ -199,9 +199,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_OUT >> 3) << 17) |
                                    ((uint32_t)((2 * TILE_M) >> 4) << 24);
             int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0, it = 0;
+#ifdef TZ_DEBUG_TIMING
             long long w_t = 0, w_a = 0, w_b = 0;
-            (void)w_t, (void)w_a, (void)w_b;
             const long long mma_start = clock64();
+#endif
             for (int pt = pair; pt < pair_tiles; pt += npairs, it++) {
                 const int acc = it & 1;
                 TWAIT(w_t, mbar_wait_cluster(t_empty + 8 * acc, ((it >> 1) & 1) ^ 1));

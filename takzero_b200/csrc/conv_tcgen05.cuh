@@ -20,11 +20,14 @@
 //
 // One CTA = 128 output rows x 256 output channels (one UMMA M128 N256 accumulator of 256
 // TMEM columns, double buffered), persistent over row tiles.  Warp roles:
-//   warp 0   A producer   cp.async 16 B pieces of the 144-row halo tile, one 64-channel block per stage
-//   warp 1   B producer   cp.async.bulk of pre-arranged 32 KB weight blocks (64 K x 256 N) from L2
-//   warp 2   MMA issuer   one thread: 9 taps x 4 K-steps of tcgen05.mma per A block
-//   warp 3   TMEM allocator
-//   warps 4-7 epilogue    tcgen05.ld -> bias (+ residual) (+ ReLU) -> bf16 / f32 stores
+//   warps 0-3 epilogue    tcgen05.ld -> bias (+ residual) (+ ReLU) -> bf16 / f32 stores
+//   warp 4   A producer   cp.async 16 B pieces of the 144-row halo tile, one 64-channel block per stage
+//   warp 5   B producer   cp.async.bulk of pre-arranged 32 KB weight blocks (64 K x 256 N) from L2
+//   warp 6   MMA issuer   one thread: 9 taps x 4 K-steps of tcgen05.mma per A block
+//   warp 7   TMEM allocator
+// This file is the ONE-CTA kernel (kept for A/B and as the base of the shared helpers); the product path is
+// the CTA-pair kernel in conv_pair_tcgen05.cuh.  TZ_DEBUG_* macros are compile-time tuning experiments
+// (tools/build_variant.sh); the numbers they produced are in profiles/r1_conv_timing.txt.
 #pragma once
 #include <cuda_bf16.h>
 #include <stdio.h>
@@ -43,12 +46,6 @@ constexpr int A_STAGE_BYTES = 8 * A_KC_PITCH; // 18560 B = one 64-channel block
 #ifndef TZ_DEBUG_SKIP_STORE
 #define TZ_DEBUG_SKIP_STORE 0
 #endif
-#ifndef TZ_EPI_STAGED
-#define TZ_EPI_STAGED 0
-#endif
-#ifndef TZ_ROLE_SWAP
-#define TZ_ROLE_SWAP 1
-#endif
 #ifndef TZ_A_STAGES
 #define TZ_A_STAGES 4
 #endif
@@ -64,16 +61,10 @@ constexpr int THREADS = 256;
 // Warp roles.  The SM sub-partition arbiter favours the highest warp id, so the single-thread producer /
 // MMA roles sit on warps 4-7 and the instruction-heavy epilogue on warps 0-3 (warp w may only touch TMEM
 // lanes 32*(w%4)..+31, so any four warps with distinct w%4 can be the epilogue).
-#if TZ_ROLE_SWAP
 constexpr int W_EPI0 = 0, W_APROD = 4, W_BPROD = 5, W_MMA = 6, W_ALLOC = 7;
-#else
-constexpr int W_EPI0 = 4, W_APROD = 0, W_BPROD = 1, W_MMA = 2, W_ALLOC = 3;
-#endif
 constexpr int MASK_BYTES = 36 * 9 * 16;         // [N*N][9 taps] 128-bit lane masks
-constexpr int EPI_PITCH = 36;                   // floats per staged row (32 + 4: conflict-free 16-B accesses)
-constexpr int EPI_BYTES = TILE_M * EPI_PITCH * 4;  // f32 staging of one 32-column chunk of the tile
-constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + 1024 /*bias*/ +
-                           256 /*barriers*/ + MASK_BYTES + EPI_BYTES;
+constexpr int SMEM_BYTES =
+    A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + 1024 /*bias*/ + 256 /*barriers*/ + MASK_BYTES;
 
 struct Params {
     const __nv_bfloat16* in;        // [rows][cin] activations, dense rows
@@ -196,7 +187,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3(const Params p) {
     const uint32_t t_full = b_empty + 8 * B_STAGES, t_empty = t_full + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * A_STAGES + 2 * B_STAGES + 4);
     uint4* s_masks = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(bars) + 256);
-    float* s_epi = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_masks) + MASK_BYTES);
 
     const int count = p.count_ptr ? *p.count_ptr : p.count_max;
     const int nn = p.n * p.n;
@@ -301,9 +291,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3(const Params p) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_OUT >> 3) << 17) |
                                    ((uint32_t)(TILE_M >> 4) << 24);
             int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0, it = 0;
+#ifdef TZ_DEBUG_TIMING
             long long w_t = 0, w_a = 0, w_b = 0;
-            (void)w_t, (void)w_a, (void)w_b;
             const long long mma_start = clock64();
+#endif
             for (int t = blockIdx.x; t < tiles; t += gridDim.x, it++) {
                 const int acc = it & 1;
                 TWAIT(w_t, mbar_wait(t_empty + 8 * acc, ((it >> 1) & 1) ^ 1));
@@ -360,86 +351,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3(const Params p) {
         // memory -> coalesced copy-out (4 lanes per row for bf16, 8 for f32), where the residual is
         // loaded with the same coalesced pattern, added in f32, and ReLU / rounding are applied.  A warp
         // store then touches 8 (or 4) 128-B lines instead of 32.
-#if TZ_EPI_STAGED
-        const int wq = warp & 3;
-        float* stg = s_epi + wq * 32 * EPI_PITCH;
-        int it = 0;
-        for (int t = blockIdx.x; t < tiles; t += gridDim.x, it++) {
-            const int acc = it & 1;
-            const int rel0 = t * TILE_M + wq * 32;  // first row of this warp (row = position * n*n + square)
-            mbar_wait(t_full + 8 * acc, (it >> 1) & 1);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * N_OUT;
-#ifndef TZ_DEBUG_NO_EPILOGUE  // tuning experiment
-#pragma unroll 1
-            for (int c0 = 0; c0 < N_OUT; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(taddr + c0, v);
-                tmem_ld_wait();
-                float4* srow = reinterpret_cast<float4*>(stg + lane * EPI_PITCH);
-#pragma unroll
-                for (int j = 0; j < 8; j++)
-                    srow[j] = make_float4(__uint_as_float(v[4 * j]) + s_bias[c0 + 4 * j],
-                                          __uint_as_float(v[4 * j + 1]) + s_bias[c0 + 4 * j + 1],
-                                          __uint_as_float(v[4 * j + 2]) + s_bias[c0 + 4 * j + 2],
-                                          __uint_as_float(v[4 * j + 3]) + s_bias[c0 + 4 * j + 3]);
-                __syncwarp();
-                if (p.out_act) {
-                    const int piece = lane & 3;  // 8 channels
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int r = (lane >> 2) + 8 * k;
-                        const int rel = rel0 + r;
-                        if (rel < rows_used) {
-                            const size_t goff = (size_t)(p.guard + rel) * N_OUT + c0 + piece * 8;
-                            const float4 a0 = *reinterpret_cast<const float4*>(stg + r * EPI_PITCH + piece * 8);
-                            const float4 a1 = *reinterpret_cast<const float4*>(stg + r * EPI_PITCH + piece * 8 + 4);
-                            float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                            if (p.residual && !TZ_DEBUG_SKIP_RES) {
-                                const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + goff);
-                                const uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-                                for (int e = 0; e < 4; e++) {
-                                    f[e * 2] += __uint_as_float(w[e] << 16);
-                                    f[e * 2 + 1] += __uint_as_float(w[e] & 0xffff0000u);
-                                }
-                            }
-                            if (p.relu) {
-#pragma unroll
-                                for (int e = 0; e < 8; e++) f[e] = fmaxf(f[e], 0.0f);
-                            }
-                            if (!TZ_DEBUG_SKIP_STORE)
-                                *reinterpret_cast<uint4*>(p.out_act + goff) =
-                                    make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
-                                               pack_bf16(f[6], f[7]));
-                        }
-                    }
-                }
-                if (p.out_f32) {
-                    const int piece = lane & 7;  // 4 channels
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        const int r = (lane >> 3) + 4 * k;
-                        const int rel = rel0 + r;
-                        if (rel < rows_used) {
-                            float4 a = *reinterpret_cast<const float4*>(stg + r * EPI_PITCH + piece * 4);
-                            if (p.relu) a = make_float4(fmaxf(a.x, 0.0f), fmaxf(a.y, 0.0f), fmaxf(a.z, 0.0f), fmaxf(a.w, 0.0f));
-                            *reinterpret_cast<float4*>(p.out_f32 + (size_t)rel * N_OUT + c0 + piece * 4) = a;
-                        }
-                    }
-                }
-                __syncwarp();
-            }
-#endif
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(t_empty + 8 * acc);
-        }
-#else
         const int wq = warp & 3;
         int it = 0;
+#ifdef TZ_DEBUG_TIMING
         long long e_wait = 0, e_busy = 0;
-        (void)e_wait, (void)e_busy;
+#endif
         for (int t = blockIdx.x; t < tiles; t += gridDim.x, it++) {
             const int acc = it & 1;
             const int tr = wq * 32 + lane;
@@ -505,7 +421,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3(const Params p) {
 #ifdef TZ_DEBUG_TIMING
         if ((blockIdx.x == 0 || blockIdx.x == 77) && lane == 0 && wq == 1)
             printf("cta %d epi warp %d: tiles %d wait_full %lld busy %lld\n", blockIdx.x, warp, it, e_wait, e_busy);
-#endif
 #endif
     }
     tc_fence_before();
