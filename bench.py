@@ -361,7 +361,7 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
             "positions_per_s": positions / (ms / 1000.0), "nn_evals_per_s": evals / (ms / 1000.0),
             "known_fraction": known / sims if sims else 0.0,
-            "pipeline_tensor_frac": (evals / (ms / 1000.0)) * flops_pos / 1e12 / peak,
+            "pipeline_tensor_frac": (evals / (ms / 1000.0)) * flops_pos / 1e12 / (peak * world),
             "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "e2e": e2e,
             "cpu_baseline": cpu,
         }
