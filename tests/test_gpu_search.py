@@ -253,3 +253,24 @@ def test_apply_noise_keeps_distribution():
         assert np.array_equal(after["logit"][g, :k], np.log(p, dtype=np.float32))
     m.simulate(None)  # still searchable
     m.close()
+
+
+def test_move_stride_overflow_is_reported():
+    """More legal moves than the configured row stride: reported (TZ_STATUS_TOO_MANY_MOVES), never truncated."""
+    m = capi.BatchedMCTS(5, 4, 4, arena_slots=4096, move_stride=16)
+    m.new_openings(seed=1)
+    with pytest.raises(capi.TakzeroError, match="too_many_moves"):
+        m.simulate(None)
+    m.close()
+
+
+def test_single_game_and_odd_batch_sizes():
+    """Ragged sizes: 1 game and a game count that is not a multiple of the 4 games per CTA."""
+    for G in (1, 7):
+        m, ob, rng = make_pair(4, 4, G, 50 + G)
+        gum = rng.gumbel(size=(G, m.move_stride)).astype(np.float32)
+        got = m.gumbel_sequential_halving(np.zeros(G, np.float32), 4, 32, gum)
+        want = ob.gumbel_sequential_halving("synthetic", [0.0] * G, 4, 32, gum)
+        assert list(got) == want
+        assert_roots_equal(m, ob, f"G={G}")
+        m.close()
