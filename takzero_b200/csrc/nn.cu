@@ -13,7 +13,6 @@
 #include <string>
 #include <vector>
 
-#include "conv_pair_tcgen05.cuh"
 #include "conv_tcgen05.cuh"
 #include "nn.cuh"
 #include "rules.cuh"
@@ -37,17 +36,17 @@ struct NnState {
     std::vector<ConvLayer> tower;  // 2 per residual block
     float* head_w = nullptr;       // [2][256] conv1x1 weights (value, ube)
     float* head_misc = nullptr;    // [2] conv bias, [2][36] linear weights, [2] linear bias
-    __nv_bfloat16* planes = nullptr;  // [rows][64]
-    __nv_bfloat16* act_x = nullptr;   // [rows][256]
-    __nv_bfloat16* act_t = nullptr;   // [rows][256]
+    // chunk-planar activations (conv_tcgen05.cuh): [channels / 8][rows][8]
+    __nv_bfloat16* planes = nullptr;  // [8][rows][8]   input planes, 64 channels (C real ones)
+    __nv_bfloat16* act_x = nullptr;   // [32][rows][8]  residual stream
+    __nv_bfloat16* act_t = nullptr;   // [32][rows][8]  middle of a residual block
     __nv_bfloat16* act_scratch = nullptr;  // tuning hook only
-    float* logits_full = nullptr;     // [max_positions * n*n][256]
+    float* logits_full = nullptr;     // [64][max_positions * n*n][4] policy logits, 4-channel planes
     uint4* masks = nullptr;           // [n*n][9] disable-output-lane masks (conv_tcgen05.cuh)
     float* simhash_matrix = nullptr;  // [C*N*N][32] (net6_simhash.rs:136-139), optional
     uint32_t* simhash_set = nullptr;  // 2^32-bit set (bitvec.bin), optional; absent = empty set
     uint32_t* simhash_idx = nullptr;  // [max_positions] hash index of each queued position
     int layer_limit = -1;             // debug: stop the tower after this many convolutions
-    bool pair = true;                 // CTA-pair kernel (cta_group::2); TZ_CONV_MODE=single selects the 1-CTA kernel
     std::vector<void*> allocs;
     int sm_count = 148;
 };
@@ -64,10 +63,10 @@ void nn_free(tz_handle* h) {
 // ---- input planes (network/repr.rs:169-228) ----------------------------------------------------
 
 // One warp per position.  out_f32: [count][C][N][N] exactly like `game_repr` (parity hook);
-// out_bf16: dense rows [guard + position * N*N + square][64] feeding the first convolution.
+// out_bf16: chunk-planar [8][rows][8] (row = guard + position * N*N + square) feeding the first convolution.
 __global__ void __launch_bounds__(32 * WPB) k_encode(const TzState* states, const int* count_ptr, int count_max, int n,
                                                       int half_komi, float* out_f32, __nv_bfloat16* out_bf16,
-                                                      int guard) {
+                                                      int guard, long long rows) {
     __shared__ TzState s_state[WPB];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * WPB + warp;
@@ -114,11 +113,11 @@ __global__ void __launch_bounds__(32 * WPB) k_encode(const TzState* states, cons
         }
         if (out_bf16) {
             const size_t r = (size_t)guard + (size_t)q * nn + sq;
-            uint4* o = reinterpret_cast<uint4*>(out_bf16 + r * CIN_PAD);
 #pragma unroll
             for (int j = 0; j < CIN_PAD / 8; j++)
-                o[j] = make_uint4(conv::pack_bf16(v[j * 8], v[j * 8 + 1]), conv::pack_bf16(v[j * 8 + 2], v[j * 8 + 3]),
-                                  conv::pack_bf16(v[j * 8 + 4], v[j * 8 + 5]), conv::pack_bf16(v[j * 8 + 6], v[j * 8 + 7]));
+                *reinterpret_cast<uint4*>(out_bf16 + ((size_t)j * (size_t)rows + r) * 8) =
+                    make_uint4(conv::pack_bf16(v[j * 8], v[j * 8 + 1]), conv::pack_bf16(v[j * 8 + 2], v[j * 8 + 3]),
+                               conv::pack_bf16(v[j * 8 + 4], v[j * 8 + 5]), conv::pack_bf16(v[j * 8 + 6], v[j * 8 + 7]));
         }
     }
 }
@@ -191,46 +190,49 @@ __device__ __forceinline__ int move_channel(int n, uint16_t m) {
 // One warp per position: value head (conv1x1 + ReLU + Linear + tanh), UBE head (same, no tanh),
 // uncertainty = clamp(max(exp(ube), local), 0, 4) with local = 4.0 (empty SimHash set, i.e. a
 // freshly initialised reference network), and logits[i] = policy[move_index(action_i)].
-__global__ void __launch_bounds__(32 * WPB) k_heads_gather(const __nv_bfloat16* act, const float* logits_full,
+__global__ void __launch_bounds__(32 * WPB) k_heads_gather(const __nv_bfloat16* act, long long rows,
+                                                            const float* logits_full, long long f32_rows,
                                                             const float* head_w, const float* head_misc,
                                                             const uint16_t* actions, const int* n_actions,
                                                             const int* count_ptr, int count_max, int n, int M, int guard,
                                                             const uint32_t* simhash_set, const uint32_t* simhash_idx,
                                                             float* out_logits, float* out_value, float* out_variance) {
+    __shared__ float s_w[2 * FILTERS];
+    for (int i = threadIdx.x; i < 2 * FILTERS; i += blockDim.x) s_w[i] = head_w[i];
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * WPB + warp;
     const int count = count_ptr ? *count_ptr : count_max;
     if (q >= count) return;
     const int nn = n * n;
-    // lane owns channels lane*8 .. lane*8+7
-    float wv[8], wu[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        wv[j] = head_w[lane * 8 + j];
-        wu[j] = head_w[FILTERS + lane * 8 + j];
-    }
     const float bv = head_misc[0], bu = head_misc[1];
     const float* lin_v = head_misc + 2;
     const float* lin_u = head_misc + 2 + 36;
+    // lane = square (two passes for N = 6): the 1x1 convolutions are per-square dot products over the 256
+    // channels; consecutive lanes read consecutive 16-byte pieces of every chunk plane
     float acc_v = 0.0f, acc_u = 0.0f;
-    for (int sq = 0; sq < nn; sq++) {
+    for (int sq = lane; sq < nn; sq += 32) {
         const size_t r = (size_t)guard + (size_t)q * nn + sq;
-        const uint4 x = *reinterpret_cast<const uint4*>(act + r * FILTERS + lane * 8);
-        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
         float dv = 0.0f, du = 0.0f;
+#pragma unroll 4
+        for (int kc = 0; kc < FILTERS / 8; kc++) {
+            const uint4 x = *reinterpret_cast<const uint4*>(act + ((size_t)kc * (size_t)rows + r) * 8);
+            const uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
-            dv += lo * wv[e * 2] + hi * wv[e * 2 + 1];
-            du += lo * wu[e * 2] + hi * wu[e * 2 + 1];
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            dv += __shfl_xor_sync(0xffffffffu, dv, o);
-            du += __shfl_xor_sync(0xffffffffu, du, o);
+            for (int e = 0; e < 4; e++) {
+                const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
+                const int c = kc * 8 + e * 2;
+                dv += lo * s_w[c] + hi * s_w[c + 1];
+                du += lo * s_w[FILTERS + c] + hi * s_w[FILTERS + c + 1];
+            }
         }
         acc_v += fmaxf(dv + bv, 0.0f) * lin_v[sq];
         acc_u += fmaxf(du + bu, 0.0f) * lin_u[sq];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc_v += __shfl_xor_sync(0xffffffffu, acc_v, o);
+        acc_u += __shfl_xor_sync(0xffffffffu, acc_u, o);
     }
     if (lane == 0) {
         out_value[q] = tanhf(acc_v + head_misc[2 + 72]);
@@ -245,11 +247,12 @@ __global__ void __launch_bounds__(32 * WPB) k_heads_gather(const __nv_bfloat16* 
     }
     const int cnt = n_actions[q];
     const uint16_t* a = actions + (size_t)q * M;
-    const float* lf = logits_full + (size_t)q * nn * FILTERS;
     for (int i = lane; i < cnt; i += 32) {
         const uint16_t m = a[i];
         const int sq = ((m >> 3) & 7) * n + (m & 7);
-        out_logits[(size_t)q * M + i] = lf[(size_t)sq * FILTERS + move_channel(n, m)];
+        const int ch = move_channel(n, m);
+        out_logits[(size_t)q * M + i] =
+            logits_full[((size_t)(ch >> 2) * (size_t)f32_rows + (size_t)q * nn + sq) * 4 + (ch & 3)];
     }
 }
 
@@ -303,10 +306,9 @@ static int upload_conv(NnState* s, ConvLayer* L, const HostTensor* w, const Host
                 const int tap = ti == 0 ? 4 : (ti <= 4 ? ti - 1 : ti);  // tap = ky * 3 + kx
                 const float v = w->data[((size_t)co * cin + ci) * 9 + tap] * scale[co];
                 const int kb = ci / 64, kc = (ci % 64) / 8, e = ci % 8;
-                // one 32 KB block per (kb, tap): [8 k-chunks][256 n][8]; the CTA-pair kernel wants the two
-                // N halves as separate contiguous 16 KB images: [2][8][128][8]
-                const size_t in_blk = s->pair ? (((size_t)(co / 128) * 8 + kc) * 128 + co % 128) * 8 + e
-                                              : ((size_t)kc * 256 + co) * 8 + e;
+                // one 32 KB block per (kb, tap) holding the two N halves as separate contiguous 16 KB
+                // shared-memory images (one per CTA of the pair): [2 halves][8 k-chunks][128 n][8]
+                const size_t in_blk = (((size_t)(co / 128) * 8 + kc) * 128 + co % 128) * 8 + e;
                 blk[((size_t)kb * 9 + ti) * (8 * 256 * 8) + in_blk] = f32_to_bf16(v);
             }
     void* dw = nullptr;
@@ -345,7 +347,6 @@ int nn_set_weights(tz_handle* h, const char* const* names, const float* const* d
     nn_free(h);
     NnState* s = new NnState();
     h->nn = s;
-    if (const char* mode = getenv("TZ_CONV_MODE")) s->pair = strcmp(mode, "single") != 0;
     const int n = h->d.n, nn = n * n;
     s->n = n;
     s->in_channels = 2 * (2 * n + 3 + 2) + 2;
@@ -476,12 +477,10 @@ int nn_set_weights(tz_handle* h, const char* const* names, const float* const* d
             NN_FAIL(TZ_ENOMEM, "cudaMalloc masks");
         }
     }
-    if (cudaFuncSetAttribute(conv::k_conv3x3, cudaFuncAttributeMaxDynamicSharedMemorySize, conv::SMEM_BYTES) !=
-            cudaSuccess ||
-        cudaFuncSetAttribute(conv::k_conv3x3_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, conv::P_SMEM_BYTES) !=
-            cudaSuccess) {
+    if (cudaFuncSetAttribute(conv::k_conv3x3_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, conv::SMEM_BYTES) !=
+        cudaSuccess) {
         nn_free(h);
-        NN_FAIL(TZ_ECUDA, "cudaFuncSetAttribute(k_conv3x3, %d B smem) failed", conv::SMEM_BYTES);
+        NN_FAIL(TZ_ECUDA, "cudaFuncSetAttribute(k_conv3x3_pair, %d B smem) failed", conv::SMEM_BYTES);
     }
     cudaDeviceSynchronize();
     return TZ_OK;
@@ -499,11 +498,13 @@ static void launch_conv(tz_handle* h, const ConvLayer& L, const __nv_bfloat16* i
     conv::Params p;
     p.in = in;
     p.cin = L.cin;
+    p.rows = (long long)s->rows;
     p.w = L.w;
     p.bias = L.bias;
     p.residual = residual;
     p.out_act = out_act;
     p.out_f32 = out_f32;
+    p.f32_rows = (long long)s->max_positions * s->n * s->n;
     p.relu = relu;
     p.count_ptr = count_ptr;
     p.count_max = count_max;
@@ -511,14 +512,9 @@ static void launch_conv(tz_handle* h, const ConvLayer& L, const __nv_bfloat16* i
     p.guard = conv::HALO;
     p.masks = s->masks;
     const int max_tiles = (count_max * s->n * s->n + conv::TILE_M - 1) / conv::TILE_M;
-    if (s->pair) {
-        const int pairs = (max_tiles + 1) / 2, max_pairs = s->sm_count / 2;
-        const int grid = 2 * (pairs < max_pairs ? (pairs > 0 ? pairs : 1) : max_pairs);
-        conv::k_conv3x3_pair<<<grid, conv::THREADS, conv::P_SMEM_BYTES, h->stream>>>(p);
-    } else {
-        const int grid = max_tiles < s->sm_count ? max_tiles : s->sm_count;
-        conv::k_conv3x3<<<grid > 0 ? grid : 1, conv::THREADS, conv::SMEM_BYTES, h->stream>>>(p);
-    }
+    const int pairs = (max_tiles + 1) / 2, max_pairs = s->sm_count / 2;
+    const int grid = 2 * (pairs < max_pairs ? (pairs > 0 ? pairs : 1) : max_pairs);
+    conv::k_conv3x3_pair<<<grid, conv::THREADS, conv::SMEM_BYTES, h->stream>>>(p);
 }
 
 // states[count] (device), actions/n_actions by position -> logits/value/variance by position.
@@ -533,7 +529,7 @@ int nn_forward(tz_handle* h, const TzState* states, const int* count_ptr, int co
     {
         ProfScope ps(h, TZ_PROF_ENCODE);
         k_encode<<<wblocks, 32 * WPB, 0, h->stream>>>(states, count_ptr, count_max, d.n, d.half_komi, nullptr, s->planes,
-                                                      conv::HALO);
+                                                      conv::HALO, (long long)s->rows);
     }
     int done = 0;
     const int limit = s->layer_limit;
@@ -566,9 +562,10 @@ int nn_forward(tz_handle* h, const TzState* states, const int* count_ptr, int co
                                                        s->simhash_idx);
     {
         ProfScope ps(h, TZ_PROF_HEADS);
-        k_heads_gather<<<wblocks, 32 * WPB, 0, h->stream>>>(s->act_x, s->logits_full, s->head_w, s->head_misc, actions,
-                                                            n_actions, count_ptr, count_max, d.n, d.M, conv::HALO,
-                                                            s->simhash_set, s->simhash_idx, logits, value, variance);
+        k_heads_gather<<<wblocks, 32 * WPB, 0, h->stream>>>(
+            s->act_x, (long long)s->rows, s->logits_full, (long long)s->max_positions * d.n * d.n, s->head_w, s->head_misc,
+            actions, n_actions, count_ptr, count_max, d.n, d.M, conv::HALO, s->simhash_set, s->simhash_idx, logits, value,
+            variance);
     }
     h->launches += 2;
     return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
@@ -582,18 +579,18 @@ int nn_forward_queue(tz_handle* h) {
 int nn_encode_planes(tz_handle* h, const TzState* states, int count, float* out_f32) {
     const TzDev& d = h->d;
     k_encode<<<(count + WPB - 1) / WPB, 32 * WPB, 0, h->stream>>>(states, nullptr, count, d.n, d.half_komi, out_f32,
-                                                                  nullptr, 0);
+                                                                  nullptr, 0, 0);
     return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
 }
 
 // debug read-back: which = 0 act_x, 1 act_t, 2 planes; f32 [count][n*n][channels]
-__global__ void k_unpad(const __nv_bfloat16* buf, int channels, int count, int n, int guard, float* out) {
+__global__ void k_unpad(const __nv_bfloat16* buf, int channels, int count, int n, int guard, long long rows, float* out) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int nn = n * n;
     if (idx >= (size_t)count * nn * channels) return;
     const int c = (int)(idx % channels);
     const size_t cell = idx / channels;  // position * nn + square
-    out[idx] = __bfloat162float(buf[((size_t)guard + cell) * channels + c]);
+    out[idx] = __bfloat162float(buf[((size_t)(c >> 3) * (size_t)rows + (size_t)guard + cell) * 8 + (c & 7)]);
 }
 
 int nn_debug_read(tz_handle* h, int which, int count, float* out_dev) {
@@ -602,7 +599,8 @@ int nn_debug_read(tz_handle* h, int which, int count, float* out_dev) {
     const __nv_bfloat16* buf = which == 0 ? s->act_x : which == 1 ? s->act_t : s->planes;
     const int channels = which == 2 ? CIN_PAD : FILTERS;
     const size_t total = (size_t)count * s->n * s->n * channels;
-    k_unpad<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(buf, channels, count, s->n, conv::HALO, out_dev);
+    k_unpad<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(buf, channels, count, s->n, conv::HALO,
+                                                                    (long long)s->rows, out_dev);
     return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
 }
 
