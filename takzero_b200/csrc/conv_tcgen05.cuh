@@ -44,10 +44,16 @@ constexpr int HALO = 8;                        // >= N+1 for N <= 6
 constexpr int A_ROWS = TILE_M + 2 * HALO;      // 144
 constexpr int A_KC_BYTES = A_ROWS * 16;        // 2304 B: one chunk plane of the halo tile
 constexpr int A_STAGE_BYTES = 8 * A_KC_BYTES;  // 18432 B = one 64-channel block
-constexpr int A_STAGES = 4;
+#ifndef TZ_A_STAGES
+#define TZ_A_STAGES 4
+#endif
+#ifndef TZ_B_STAGES
+#define TZ_B_STAGES 8
+#endif
+constexpr int A_STAGES = TZ_A_STAGES;
 constexpr int B_KC_BYTES = 128 * 16;           // 2048 B between K-chunks of a weight half
 constexpr int B_STAGE_BYTES = 8 * B_KC_BYTES;  // 16384 B = 64 K x 128 N (one CTA's half)
-constexpr int B_STAGES = 8;
+constexpr int B_STAGES = TZ_B_STAGES;
 constexpr int N_OUT = 256;
 constexpr int THREADS = 256;
 constexpr int W_EPI0 = 0, W_APROD = 4, W_BPROD = 5, W_MMA = 6, W_ALLOC = 7;
