@@ -148,6 +148,18 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 
+// one lane of the (converged) warp, chosen by the hardware
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_rank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -320,8 +332,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                         }
                     }
             }
-        } else if (lane == 0) {
-            // ---- MMA issuer (leader only): kind::f16, D = f32, A = B = bf16 K-major, M = 256, N = 256, K = 16
+        } else {
+            // ---- MMA issuer (leader only): kind::f16, D = f32, A = B = bf16 K-major, M = 256, N = 256, K = 16.
+            // The whole warp runs the loop in uniform control flow (so descriptors, masks and barrier
+            // addresses live in uniform registers) and one elected lane issues; a `lane == 0` branch around
+            // the loop makes ptxas convert ~15 registers to uniform ones before EVERY mma, which made the
+            // issuing thread, not the tensor pipe, the limit.
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_OUT >> 3) << 17) |
                                    ((uint32_t)((2 * TILE_M) >> 4) << 24);
             int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0, it = 0;
@@ -348,28 +364,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                         const uint4 m0 = masks0[tap], m1 = masks1[tap];
                         const uint32_t a_tap = a_base + (HALO + off) * 16;
                         const uint32_t b_base = smem_u32(b_smem + b_stage * B_STAGE_BYTES);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int ks = 0; ks < 4; ks++) {
-                            const uint64_t adesc = make_desc(a_tap + ks * 2 * A_KC_BYTES, A_KC_BYTES);
-                            const uint64_t bdesc = make_desc(b_base + ks * 2 * B_KC_BYTES, B_KC_BYTES);
-                            tc_mma_pair(tmem_d, adesc, bdesc, idesc, (kb | ti | ks) != 0, m0, m1);
+                            for (int ks = 0; ks < 4; ks++) {
+                                const uint64_t adesc = make_desc(a_tap + ks * 2 * A_KC_BYTES, A_KC_BYTES);
+                                const uint64_t bdesc = make_desc(b_base + ks * 2 * B_KC_BYTES, B_KC_BYTES);
+                                tc_mma_pair(tmem_d, adesc, bdesc, idesc, (kb | ti | ks) != 0, m0, m1);
+                            }
+                            tc_commit_pair(b_empty + 8 * b_stage);
+                            if (ti == 8) tc_commit_pair(a_empty + 8 * a_stage);
+                            if (ti == 8 && kb == kblocks - 1) tc_commit_pair(t_full + 8 * acc);
                         }
-                        tc_commit_pair(b_empty + 8 * b_stage);
+                        __syncwarp();
                         if (++b_stage == B_STAGES) {
                             b_stage = 0;
                             b_phase ^= 1;
                         }
                     }
-                    tc_commit_pair(a_empty + 8 * a_stage);
                     if (++a_stage == A_STAGES) {
                         a_stage = 0;
                         a_phase ^= 1;
                     }
                 }
-                tc_commit_pair(t_full + 8 * acc);
             }
 #ifdef TZ_DEBUG_TIMING
-            if (pair == 0 || pair == 40)
+            if ((pair == 0 || pair == 40) && lane == 0)
                 printf("pair %d mma: tiles %d total %lld wait_tmem %lld wait_a %lld wait_b %lld\n", pair, it,
                        clock64() - mma_start, w_t, w_a, w_b);
 #endif
