@@ -5,14 +5,21 @@
 // reference's text formats (target.rs:56-73,215-232) so `learn` can consume them unchanged.
 //
 // Differences from the reference, all at the process boundary: constants are flags instead of
-// compile-time consts (main.rs:36-52); the model is a TZW1 tensor file instead of `model_latest.ot` and is
-// loaded once (the reference reloads it every move, main.rs:107); the `buffer_lengths.txt` throttle
-// (main.rs:93-104) is not implemented; the loop stops after --moves iterations.
+// compile-time consts (main.rs:36-52); the model is a TZW1 tensor file (`--weights`, default
+// <directory>/model_latest.tzw when present) instead of `model_latest.ot`, re-read before a move whenever the
+// file changed (the reference reloads unconditionally every move, main.rs:107); the `buffer_lengths.txt`
+// throttle with its checksum (main.rs:93-104,371-387) is honoured when that file exists; the loop stops after
+// --moves iterations.
+#include <sys/stat.h>
+
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../include/takzero_b200.hpp"
@@ -69,19 +76,57 @@ static Args parse(int argc, char** argv) {
     return a;
 }
 
+static const size_t MAX_SELFPLAY_BUFFER_LEN = 32000;  // main.rs:43
+
+// read_buffer_lengths (main.rs:371-387): "selfplay,reanalyze,checksum"; -1 absent, -2 malformed / torn read
+static long read_buffer_lengths(const std::string& directory) {
+    std::ifstream f(directory + "/buffer_lengths.txt");
+    if (!f) return -1;
+    std::string text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    std::vector<unsigned long long> nums;
+    std::stringstream ss(text);
+    std::string tok;
+    while (std::getline(ss, tok, ',')) {
+        char* end = nullptr;
+        const unsigned long long v = std::strtoull(tok.c_str(), &end, 10);
+        if (end != tok.c_str() && (*end == 0 || *end == '\n')) nums.push_back(v);
+    }
+    if (nums.size() < 3 || nums[0] + nums[1] != nums[2]) return -2;
+    return (long)nums[0];
+}
+
+static long long mtime_ns(const std::string& path) {
+    struct stat st;
+    if (stat(path.c_str(), &st) != 0) return -1;
+    return (long long)st.st_mtim.tv_sec * 1000000000LL + st.st_mtim.tv_nsec;
+}
+
 static void append(const std::string& path, const std::string& contents) {
     std::ofstream f(path, std::ios::app | std::ios::binary);
     if (!f || !(f << contents)) std::fprintf(stderr, "Could not save to %s, so here it is instead:\n%s", path.c_str(), contents.c_str());
 }
 
 int main(int argc, char** argv) {
-    const Args args = parse(argc, argv);
+    Args args = parse(argc, argv);
     try {
         BatchedMCTS mcts(args.board, args.half_komi, args.games, args.device, 0, args.arena_slots);
-        if (!args.weights.empty()) {
-            mcts.set_weights(Weights::load(args.weights));
-            mcts.set_agent(TZ_AGENT_NETWORK);
-        }
+        if (args.weights.empty() && mtime_ns(args.directory + "/model_latest.tzw") >= 0)
+            args.weights = args.directory + "/model_latest.tzw";
+        long long model_stamp = -1;
+        auto reload_model = [&]() {  // Net::load before every move (main.rs:107), skipped while unchanged
+            if (args.weights.empty()) return;
+            const long long stamp = mtime_ns(args.weights);
+            if (stamp == model_stamp) return;
+            try {
+                mcts.set_weights(Weights::load(args.weights));
+                mcts.set_agent(TZ_AGENT_NETWORK);
+                model_stamp = stamp;
+            } catch (const std::exception& e) {
+                if (model_stamp < 0) throw;  // no model at all yet
+                std::fprintf(stderr, "Cannot load model: %s, keeping the previous one.\n", e.what());
+            }
+        };
+        reload_model();
         mcts.new_openings(args.seed);  // BatchedMCTS::new -> Env::new_opening
         const int G = args.games, n = args.board, stride = mcts.move_stride();
         // `exploration` feature: the first half of the batch searches with BETA (main.rs:81-87)
@@ -96,6 +141,14 @@ int main(int argc, char** argv) {
         std::vector<std::vector<IncompleteTarget>> policy_targets(G);
         std::vector<tz_state_t> cur = mcts.envs();
         for (int step = 0; step < args.moves; step++) {
+            // wait while the trainer's exploitation buffer is full (main.rs:93-104)
+            for (;;) {
+                const long exploitation = read_buffer_lengths(args.directory);
+                if (exploitation == -1 || (exploitation >= 0 && (size_t)exploitation <= MAX_SELFPLAY_BUFFER_LEN)) break;
+                if (exploitation == -2) std::fprintf(stderr, "Could not read buffer lengths: wrong checksum or missing component\n");
+                std::this_thread::sleep_for(std::chrono::seconds(1));
+            }
+            reload_model();
             std::vector<Move> selected =
                 mcts.gumbel_sequential_halving(betas, args.sampled_actions, args.budget, args.seed);
             const std::vector<Move> sampled = mcts.select_actions_in_selfplay(args.weighted_random_plies, args.seed);

@@ -155,6 +155,9 @@ TZ_API int tz_set_positions(tz_handle* h, const tz_state_t* states, const uint8_
 TZ_API int tz_get_positions(tz_handle* h, tz_state_t* out);
 /* Env::new_opening (env.rs:65-79); sym/adj NULL = draw from the library RNG with `seed` */
 TZ_API int tz_new_openings(tz_handle* h, const uint8_t* mask, const int* sym, const int* adj, uint64_t seed);
+/* the random part of Env::new_opening_with_random_steps (env.rs:81-96): `steps` uniformly random legal moves
+ * in every selected game (library RNG keyed by seed / global game id / ply), roots reset */
+TZ_API int tz_random_steps(tz_handle* h, const uint8_t* mask, int steps, uint64_t seed);
 TZ_API int tz_reset_roots(tz_handle* h, const uint8_t* mask);              /* *node = Node::default() */
 
 /* ---- search ----------------------------------------------------------------------------- */

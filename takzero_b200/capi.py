@@ -138,6 +138,7 @@ def lib():
         "tz_get_positions": ([vp, vp], i32),
         "tz_new_openings": ([vp, vp, vp, vp, u64], i32),
         "tz_reset_roots": ([vp, vp], i32),
+        "tz_random_steps": ([vp, vp, i32, u64], i32),
         "tz_set_agent": ([vp, i32, vp, vp], i32),
         "tz_simulate": ([vp, vp], i32),
         "tz_gumbel_sequential_halving": ([vp, vp, i32, u32, vp, i32, u64, vp], i32),
@@ -288,6 +289,11 @@ class BatchedMCTS:
         a = None if adj is None else _arr(adj, np.int32, (self.G,))
         m = None if mask is None else _arr(mask, np.uint8, (self.G,))
         _check(lib().tz_new_openings(self._h, _ptr(m), _ptr(s), _ptr(a), seed))
+
+    def random_steps(self, steps: int, seed: int = 0, mask=None):
+        """The random part of `new_opening_with_random_steps` (env.rs:81-96)."""
+        m = None if mask is None else _arr(mask, np.uint8, (self.G,))
+        _check(lib().tz_random_steps(self._h, _ptr(m), steps, seed))
 
     def reset_roots(self, mask=None):
         m = None if mask is None else _arr(mask, np.uint8, (self.G,))

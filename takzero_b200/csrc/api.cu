@@ -434,6 +434,16 @@ extern "C" TZ_API int tz_new_openings(tz_handle* h, const uint8_t* mask, const i
     return TZ_OK;
 }
 
+extern "C" TZ_API int tz_random_steps(tz_handle* h, const uint8_t* mask, int steps, uint64_t seed) {
+    CHECK_H(h);
+    if (steps < 0) return fail(TZ_EINVAL, "steps must be >= 0");
+    const uint8_t* dmask;
+    int rc = upload_mask(h, mask, &dmask);
+    if (rc) return rc;
+    launch_random_steps(h->d, dmask, steps, seed, h->stream);
+    return finish(h);
+}
+
 extern "C" TZ_API int tz_reset_roots(tz_handle* h, const uint8_t* mask) {
     CHECK_H(h);
     const uint8_t* dmask;

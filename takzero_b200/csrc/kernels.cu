@@ -620,6 +620,28 @@ __global__ void __launch_bounds__(32 * WPB) k_new_openings(TzDev d, const uint8_
     warp_fresh_game(d, g, &s_state[warp], lane);
 }
 
+// Environment::new_opening_with_random_steps (env.rs:81-96) after the opening: `steps` uniformly random legal
+// moves per game (stops early when a game has no legal move, i.e. is over); roots are reset.  The reference
+// draws from `rand` (unpinned); here the choice is hash(seed, global game id, ply) mod the move count.
+__global__ void __launch_bounds__(32 * WPB) k_random_steps(TzDev d, const uint8_t* mask, int steps,
+                                                           unsigned long long seed) {
+    __shared__ TzState s_state[WPB];
+    __shared__ uint16_t s_moves[WPB][TZ_MAX_MOVES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * WPB + warp;
+    if (g >= d.G || (mask && !mask[g])) return;
+    TzState* st = &s_state[warp];
+    warp_load_state(st, &d.env[g], lane);
+    for (int i = 0; i < steps; i++) {
+        if (warp_terminal(st, d.n, d.half_komi, d.rev_limit, lane) != TZ_T_NONE) break;
+        const int cnt = warp_movegen(st, d.n, s_moves[warp], lane);
+        if (cnt <= 0) break;
+        const uint64_t h = rng_hash(seed, (uint64_t)(d.game_base + g), (uint64_t)st->ply, 0x57e95ULL);
+        warp_apply(st, d.n, s_moves[warp][h % (uint64_t)cnt], lane);
+    }
+    warp_fresh_game(d, g, st, lane);
+}
+
 __global__ void __launch_bounds__(32 * WPB) k_set_positions(TzDev d, const TzState* states, const uint8_t* mask) {
     __shared__ TzState s_state[WPB];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1020,6 +1042,9 @@ void launch_tree_pv(const TzDev& d, uint16_t* out_moves, int cap, int* out_len, 
 void launch_new_openings(const TzDev& d, const uint8_t* mask, const int* sym, const int* adj, unsigned long long seed,
                          unsigned long long counter, cudaStream_t st) {
     k_new_openings<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, mask, sym, adj, seed, counter);
+}
+void launch_random_steps(const TzDev& d, const uint8_t* mask, int steps, unsigned long long seed, cudaStream_t st) {
+    k_random_steps<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, mask, steps, seed);
 }
 void launch_set_positions(const TzDev& d, const TzState* states, const uint8_t* mask, cudaStream_t st) {
     k_set_positions<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, states, mask);

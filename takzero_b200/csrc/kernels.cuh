@@ -35,3 +35,4 @@ void launch_apply_moves(const TzDev& d, TzState* states, const uint16_t* moves, 
 void launch_merge_moves(const TzDev& d, int weighted_random_plies, const uint16_t* sampled, uint16_t* moves,
                         cudaStream_t st);
 void launch_set_root_priors(const TzDev& d, int stride, const float* prob, const float* logit, cudaStream_t st);
+void launch_random_steps(const TzDev& d, const uint8_t* mask, int steps, unsigned long long seed, cudaStream_t st);

@@ -81,3 +81,29 @@ def test_empty_and_invalid(handles):
     bad = np.array([O.parse_move("a1+")], dtype=np.uint16)
     _, ok = h.apply(st, bad)
     assert ok[0] == 0
+
+
+def test_random_steps_are_legal_playouts(handles):
+    """new_opening_with_random_steps (env.rs:81-96): every position reached is what the oracle reaches by
+    replaying some legal move from the previous one, and plies advance by `steps` unless the game ended."""
+    n, hk = 5, 4
+    m = capi.BatchedMCTS(n, hk, 64, arena_slots=4096)
+    m.new_openings(seed=3)
+    prev = m.positions()
+    for step in range(12):
+        m.random_steps(1, seed=11)
+        cur = m.positions()
+        for g in range(64):
+            before = state_to_game(prev[g], n, hk)
+            if O.terminal(before) != O.T_NONE:
+                assert states_equal(cur[g], prev[g])
+                continue
+            nexts = []
+            for mv in O.possible_moves(before):
+                g2 = before.copy()
+                O.play(g2, mv)
+                nexts.append(games_to_states([g2])[0])
+            assert any(states_equal(cur[g], x) for x in nexts), f"step {step} game {g}"
+        prev = cur
+    assert len({bytes(p["height"]) for p in prev}) > 20  # the games diverged
+    m.close()
