@@ -155,3 +155,21 @@ def test_cpp_reanalyze_host(tmp_path):
     got = open(tmp_path / "targets-reanalyze.txt").read()
     assert got.count("\n") == 2 * G
     assert got == want
+
+
+def test_cpp_selfplay_host_with_network_weights_and_buffer_file(tmp_path):
+    """The C++ host loads a TZW1 model (model_latest.tzw in --directory, like model_latest.ot), honours a valid
+    buffer_lengths.txt (selfplay/src/main.rs:93-104,371-387) and searches with the device network."""
+    from takzero_b200 import weights
+
+    tz_build.build()
+    exe = os.path.join(os.path.dirname(capi.LIB_PATH), "bin", "selfplay")
+    weights.save_tzw(str(tmp_path / "model_latest.tzw"), weights.random_init(4, seed=1, blocks=2))
+    (tmp_path / "buffer_lengths.txt").write_text("100,50,150")  # selfplay, reanalyze, checksum: below the limit
+    out = subprocess.run([exe, "--directory", str(tmp_path), "--board", "4", "--half-komi", "4", "--games", "64",
+                          "--sampled-actions", "8", "--budget", "48", "--moves", "30", "--seed", "3",
+                          "--arena-slots", str(1 << 15)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    assert "30 moves of 64 games" in out.stdout and f"{64 * 30 * 49} simulations" in out.stdout
+    lines = open(tmp_path / "targets-selfplay.txt").read().splitlines()
+    assert lines and all(len(l.split(";")) == 4 for l in lines)
