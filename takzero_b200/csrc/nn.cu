@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "conv_tcgen05.cuh"
@@ -344,7 +345,26 @@ int nn_set_weights(tz_handle* h, const char* const* names, const float* const* d
         t.shape.assign(shapes[i], shapes[i] + ndims[i]);
         ts.push_back(t);
     }
-    nn_free(h);
+    // a model reload (selfplay/src/main.rs:107 does one per move) keeps the activation buffers of the previous
+    // state: only the weights are re-folded and re-uploaded
+    struct OldState {
+        NnState* p;
+        ~OldState() {
+            if (!p) return;
+            for (void* a : p->allocs) cudaFree(a);
+            delete p;
+        }
+        void* take(void* ptr) {  // hand one allocation over to the new state
+            if (!ptr) return nullptr;
+            for (size_t i = 0; i < p->allocs.size(); i++)
+                if (p->allocs[i] == ptr) {
+                    p->allocs.erase(p->allocs.begin() + (long)i);
+                    return ptr;
+                }
+            return nullptr;
+        }
+    } old{h->nn};
+    h->nn = nullptr;
     NnState* s = new NnState();
     h->nn = s;
     const int n = h->d.n, nn = n * n;
@@ -452,13 +472,32 @@ int nn_set_weights(tz_handle* h, const char* const* names, const float* const* d
         s->allocs.push_back(*p);
         return cudaMemset(*p, 0, bytes) == cudaSuccess;
     };
-    if (!dalloc((void**)&s->planes, s->rows * CIN_PAD * 2) || !dalloc((void**)&s->act_x, s->rows * FILTERS * 2) ||
-        !dalloc((void**)&s->act_t, s->rows * FILTERS * 2) ||
-        !dalloc((void**)&s->logits_full, (size_t)s->max_positions * nn * FILTERS * 4)) {
-        nn_free(h);
-        NN_FAIL(TZ_ENOMEM, "cudaMalloc activations");
+    const bool reuse = old.p && old.p->n == n && old.p->max_positions == h->d.Q && old.p->rows == s->rows;
+    if (reuse) {
+        auto steal = [&](auto*& dst, auto* src) {
+            dst = static_cast<std::remove_reference_t<decltype(dst)>>(old.take(src));
+            if (dst) s->allocs.push_back(dst);
+        };
+        steal(s->planes, old.p->planes);
+        steal(s->act_x, old.p->act_x);
+        steal(s->act_t, old.p->act_t);
+        steal(s->act_scratch, old.p->act_scratch);
+        steal(s->logits_full, old.p->logits_full);
+        steal(s->masks, old.p->masks);
+        steal(s->simhash_matrix, old.p->simhash_matrix);
+        steal(s->simhash_set, old.p->simhash_set);
+        steal(s->simhash_idx, old.p->simhash_idx);
     }
+    if (!reuse || !s->planes || !s->act_x || !s->act_t || !s->logits_full)
     {
+        if (!dalloc((void**)&s->planes, s->rows * CIN_PAD * 2) || !dalloc((void**)&s->act_x, s->rows * FILTERS * 2) ||
+            !dalloc((void**)&s->act_t, s->rows * FILTERS * 2) ||
+            !dalloc((void**)&s->logits_full, (size_t)s->max_positions * nn * FILTERS * 4)) {
+            nn_free(h);
+            NN_FAIL(TZ_ENOMEM, "cudaMalloc activations");
+        }
+    }
+    if (!s->masks) {
         // lane masks: bit i of mask[start][tap] is set when tile row i (board square (start + i) mod nn)
         // has no (dy,dx) neighbour on the board
         std::vector<uint32_t> mk((size_t)nn * 9 * 4, 0);

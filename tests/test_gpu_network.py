@@ -189,3 +189,28 @@ def test_simhash_indices_and_uncertainty():
     assert np.abs(variances - want_var).max() <= 2e-2
     assert (variances[~seen] == 4.0).all()
     m.close()
+
+
+def test_model_reload_replaces_weights_and_keeps_buffers():
+    """Net::load before every move (selfplay/src/main.rs:107): a second tz_set_weights takes effect for the
+    next evaluation (activation buffers are reused, only the folded weights change)."""
+    n, hk, count = 4, 4, 32
+    games = sample_positions(n, hk, count, 21)
+    actions = [O.possible_moves(g) for g in games]
+    states = games_to_states(games)
+    m = capi.BatchedMCTS(n, hk, count, arena_slots=4096)
+    outs = []
+    for seed in (1, 2, 1):
+        ref = net_ref.Net(n, seed=seed, blocks=2)
+        network.set_weights(m, ref.tensors())
+        logits, values, _ = network.evaluate(m, states, actions)
+        want_logits, want_values, _ = ref.policy_value_uncertainty(games, actions)
+        assert max(float(np.abs(a - b).max()) for a, b in zip(logits, want_logits)) <= TOL
+        assert float(np.abs(values - want_values).max()) <= TOL
+        outs.append(np.concatenate(logits))
+    assert np.array_equal(outs[0], outs[2]) and not np.array_equal(outs[0], outs[1])
+    m.set_agent(capi.AGENT_NETWORK)
+    m.new_openings(seed=1)
+    m.gumbel_sequential_halving(None, 8, 48, None, seed=1)
+    assert m.status() == 0
+    m.close()
