@@ -214,3 +214,33 @@ def test_model_reload_replaces_weights_and_keeps_buffers():
     m.gumbel_sequential_halving(None, 8, 48, None, seed=1)
     assert m.status() == 0
     m.close()
+
+
+def test_chosen_moves_agree_with_f32_reference_search():
+    """Whole-search agreement: the oracle search driven by the f32 PyTorch network vs the CUDA search driven by
+    the bf16 tcgen05 network, same injected Gumbel noise, compared on the move sequential halving selects.
+    This is stricter than the per-position criterion (policy argmax / logits, checked at 100 % / 2e-3 in
+    check_network): a 1e-3 logit difference can flip a near-tie between noisy candidates and the search then
+    diverges.  Measured 97.7 % on this configuration; the assertion guards regressions."""
+    n, hk, G, k, budget = 4, 4, 384, 8, 48
+    ref = net_ref.Net(n, seed=17, blocks=4, randomize_bn=True)
+    games = sample_positions(n, hk, G, 33)
+    rng = np.random.default_rng(5)
+    m = capi.BatchedMCTS(n, hk, G, arena_slots=1 << 13)
+    network.set_weights(m, ref.tensors())
+    m.set_agent(capi.AGENT_NETWORK)
+    m.set_positions(games_to_states(games))
+    gumbel = rng.gumbel(size=(G, m.move_stride)).astype(np.float32)
+    betas = np.zeros(G, dtype=np.float32)
+    got = m.gumbel_sequential_halving(betas, k, budget, gumbel)
+    ob = O.Batched(games)
+    want = ob.gumbel_sequential_halving(ref.as_oracle_agent(), betas, k, budget, gumbel)
+    agree = float(np.mean(np.array(got) == np.array(want, dtype=np.uint16)))
+    tbl = m.root_children()
+    # visit counts of the roots: identical schedule, and the same top action in almost every game
+    same_visits = np.mean([np.array_equal(tbl["visits"][g, : tbl["n"][g]],
+                                          np.array([ob.node(g).children[i].visit_count for i in range(ob.node(g).n_children)]))
+                           for g in range(G)])
+    print(f"chosen-move agreement {agree:.4f}, identical root visit vectors {same_visits:.4f}")
+    assert agree >= 0.95
+    m.close()
