@@ -280,7 +280,7 @@ def main():
         with open(ncu_path) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
     roofline = {
-        "kernel": "conv::k_conv3x3 (bf16 implicit GEMM, tcgen05/TMEM)", "bound": "tensor", "achieved": achieved,
+        "kernel": "conv::k_conv3x3_pair (bf16 implicit GEMM, tcgen05 cta_group::2 / TMEM)", "bound": "tensor", "achieved": achieved,
         "peak": peak, "peak_kind": peak_kind, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
         "traffic": traffic,
         "sampled": {"locksteps": int(prof.locksteps), "positions": int(prof.positions),
