@@ -221,7 +221,8 @@ def main():
     tensors = weights.random_init(BOARD_N, seed=123 + rank)
     if world > 1:
         tensors = tzd.broadcast_weights(tensors, src=0, device=cuda_dev)
-    network.set_weights(m, tensors)
+    net_dtype = network.DTYPE_F16 if os.environ.get("TZ_BENCH_DTYPE", "bf16") == "f16" else network.DTYPE_BF16
+    network.set_weights(m, tensors, net_dtype)
     weight_load_s = time.perf_counter() - t_w
     m.set_agent(capi.AGENT_NETWORK)
     m.new_openings(seed=1000)
@@ -358,7 +359,8 @@ def main():
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
+            "vs_baseline": None, "dtype": "f16" if net_dtype == network.DTYPE_F16 else "bf16", "data": "synthetic",
+            "config": cfg,
             "positions_per_s": positions / (ms / 1000.0), "nn_evals_per_s": evals / (ms / 1000.0),
             "known_fraction": known / sims if sims else 0.0,
             "pipeline_tensor_frac": (evals / (ms / 1000.0)) * flops_pos / 1e12 / (peak * world),

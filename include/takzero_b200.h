@@ -247,6 +247,11 @@ TZ_API int tz_tree_principal_variation(tz_handle* h, tz_move_t* out_moves, int c
  * The number of residual blocks is taken from the names (16 for net4/net6, 20 for net5).  BatchNorm is
  * folded (eval mode, eps 1e-5) and the convolutions are converted to bf16 here. */
 TZ_API int tz_set_weights(tz_handle* h, const tz_tensor_t* tensors, int count);
+/* 16-bit type the NEXT tz_set_weights converts weights and activations to.  TZ_DTYPE_BF16 (default) is what
+ * the design targets; TZ_DTYPE_F16 runs the same tcgen05 kind::f16 kernels on IEEE half (3 more mantissa
+ * bits, ~8x smaller error against the f32 reference, but 65504 range: an overflow surfaces as TZ_STATUS_NAN). */
+enum { TZ_DTYPE_BF16 = 0, TZ_DTYPE_F16 = 1 };
+TZ_API int tz_set_network_dtype(tz_handle* h, int dtype);
 /* `impl Agent for Net`::policy_value_uncertainty (net6_simhash.rs:259-324) on host buffers:
  * count <= n_games positions, actions [count][stride] -> logits [count][stride], values, variances */
 TZ_API int tz_evaluate(tz_handle* h, const tz_state_t* states, int count, const tz_move_t* actions,

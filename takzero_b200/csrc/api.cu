@@ -1056,3 +1056,10 @@ extern "C" TZ_API int tz_set_root_priors(tz_handle* h, int stride, const float* 
     h->launches += 1;
     return finish(h);
 }
+
+extern "C" TZ_API int tz_set_network_dtype(tz_handle* h, int dtype) {
+    if (!h) return fail(TZ_EINVAL, "null handle");
+    if (dtype != TZ_DTYPE_BF16 && dtype != TZ_DTYPE_F16) return fail(TZ_EINVAL, "dtype must be TZ_DTYPE_BF16 or TZ_DTYPE_F16");
+    h->nn_f16 = dtype == TZ_DTYPE_F16;
+    return TZ_OK;
+}

@@ -1,4 +1,4 @@
-// conv_tcgen05.cuh -- 3x3 convolution of the ResNet tower as a bf16 implicit GEMM on the
+// conv_tcgen05.cuh -- 3x3 convolution of the ResNet tower as a bf16 (optionally fp16) implicit GEMM on the
 // 5th-generation tensor cores (tcgen05.mma cta_group::2, accumulators in TMEM), sm_100a only.
 //
 // Replaces libtorch's conv2d + batch_norm2d (+ add + relu) of the reference tower
@@ -34,6 +34,7 @@
 // the earlier row-major one-CTA / pair kernels are in profiles/r1_conv_timing.txt.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -77,6 +78,7 @@ struct Params {
     int n;                          // board size
     int guard;                      // leading guard rows of the activation planes (= HALO)
     const uint4* masks;             // [n*n][9] disable-output-lane masks by (first tile row) mod n*n
+    int f16;                        // 16-bit storage / operand type: 0 = bf16, 1 = IEEE fp16 (same UMMA kind::f16)
 };
 
 #ifdef TZ_DEBUG_TIMING
@@ -145,6 +147,18 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
+}
+// two 16-bit activations <-> f32, in the network's storage type (bf16 or fp16; warp-uniform flag)
+__device__ __forceinline__ uint32_t pack16(float a, float b, int f16) {
+    if (f16) {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    return pack_bf16(a, b);
+}
+__device__ __forceinline__ float2 unpack16(uint32_t w, int f16) {
+    if (f16) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
 }
 
 
@@ -338,7 +352,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
             // addresses live in uniform registers) and one elected lane issues; a `lane == 0` branch around
             // the loop makes ptxas convert ~15 registers to uniform ones before EVERY mma, which made the
             // issuing thread, not the tensor pipe, the limit.
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_OUT >> 3) << 17) |
+            // a_format / b_format (bits 7..9 / 10..12): 0 = F16, 1 = BF16
+            const uint32_t fmt = p.f16 ? 0u : 1u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N_OUT >> 3) << 17) |
                                    ((uint32_t)((2 * TILE_M) >> 4) << 24);
             int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0, it = 0;
 #ifdef TZ_DEBUG_TIMING
@@ -424,8 +440,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                             const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
                             for (int e = 0; e < 4; e++) {
-                                f[j * 8 + e * 2] += __uint_as_float(w[e] << 16);
-                                f[j * 8 + e * 2 + 1] += __uint_as_float(w[e] & 0xffff0000u);
+                                const float2 x = unpack16(w[e], p.f16);
+                                f[j * 8 + e * 2] += x.x;
+                                f[j * 8 + e * 2 + 1] += x.y;
                             }
                         }
                     }
@@ -437,8 +454,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
 #pragma unroll
                         for (int j = 0; j < 4; j++)
                             *reinterpret_cast<uint4*>(p.out_act + (size_t)(c0 / 8 + j) * plane + grow) =
-                                make_uint4(pack_bf16(f[j * 8], f[j * 8 + 1]), pack_bf16(f[j * 8 + 2], f[j * 8 + 3]),
-                                           pack_bf16(f[j * 8 + 4], f[j * 8 + 5]), pack_bf16(f[j * 8 + 6], f[j * 8 + 7]));
+                                make_uint4(pack16(f[j * 8], f[j * 8 + 1], p.f16), pack16(f[j * 8 + 2], f[j * 8 + 3], p.f16),
+                                           pack16(f[j * 8 + 4], f[j * 8 + 5], p.f16), pack16(f[j * 8 + 6], f[j * 8 + 7], p.f16));
                     }
                     if (p.out_f32) {
 #pragma unroll

@@ -48,6 +48,7 @@ struct NnState {
     uint32_t* simhash_set = nullptr;  // 2^32-bit set (bitvec.bin), optional; absent = empty set
     uint32_t* simhash_idx = nullptr;  // [max_positions] hash index of each queued position
     int layer_limit = -1;             // debug: stop the tower after this many convolutions
+    int f16 = 0;                      // 16-bit type of weights / activations: 0 bf16 (default), 1 fp16
     std::vector<void*> allocs;
     int sm_count = 148;
 };
@@ -67,7 +68,7 @@ void nn_free(tz_handle* h) {
 // out_bf16: chunk-planar [8][rows][8] (row = guard + position * N*N + square) feeding the first convolution.
 __global__ void __launch_bounds__(32 * WPB) k_encode(const TzState* states, const int* count_ptr, int count_max, int n,
                                                       int half_komi, float* out_f32, __nv_bfloat16* out_bf16,
-                                                      int guard, long long rows) {
+                                                      int guard, long long rows, int f16) {
     __shared__ TzState s_state[WPB];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * WPB + warp;
@@ -117,8 +118,8 @@ __global__ void __launch_bounds__(32 * WPB) k_encode(const TzState* states, cons
 #pragma unroll
             for (int j = 0; j < CIN_PAD / 8; j++)
                 *reinterpret_cast<uint4*>(out_bf16 + ((size_t)j * (size_t)rows + r) * 8) =
-                    make_uint4(conv::pack_bf16(v[j * 8], v[j * 8 + 1]), conv::pack_bf16(v[j * 8 + 2], v[j * 8 + 3]),
-                               conv::pack_bf16(v[j * 8 + 4], v[j * 8 + 5]), conv::pack_bf16(v[j * 8 + 6], v[j * 8 + 7]));
+                    make_uint4(conv::pack16(v[j * 8], v[j * 8 + 1], f16), conv::pack16(v[j * 8 + 2], v[j * 8 + 3], f16),
+                               conv::pack16(v[j * 8 + 4], v[j * 8 + 5], f16), conv::pack16(v[j * 8 + 6], v[j * 8 + 7], f16));
         }
     }
 }
@@ -197,7 +198,8 @@ __global__ void __launch_bounds__(32 * WPB) k_heads_gather(const __nv_bfloat16* 
                                                             const uint16_t* actions, const int* n_actions,
                                                             const int* count_ptr, int count_max, int n, int M, int guard,
                                                             const uint32_t* simhash_set, const uint32_t* simhash_idx,
-                                                            float* out_logits, float* out_value, float* out_variance) {
+                                                            float* out_logits, float* out_value, float* out_variance,
+                                                            int f16) {
     __shared__ float s_w[2 * FILTERS];
     for (int i = threadIdx.x; i < 2 * FILTERS; i += blockDim.x) s_w[i] = head_w[i];
     __syncthreads();
@@ -221,7 +223,8 @@ __global__ void __launch_bounds__(32 * WPB) k_heads_gather(const __nv_bfloat16* 
             const uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-                const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
+                const float2 xy = conv::unpack16(w[e], f16);
+                const float lo = xy.x, hi = xy.y;
                 const int c = kc * 8 + e * 2;
                 dv += lo * s_w[c] + hi * s_w[c + 1];
                 du += lo * s_w[FILTERS + c] + hi * s_w[FILTERS + c + 1];
@@ -284,6 +287,29 @@ static uint16_t f32_to_bf16(float f) {
     return (uint16_t)(u >> 16);
 }
 
+static uint16_t f32_to_f16(float f) {  // round to nearest even, overflow -> inf, subnormals kept
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    const uint32_t sign = (u >> 16) & 0x8000u;
+    const int32_t exp = (int32_t)((u >> 23) & 0xff) - 127 + 15;
+    uint32_t man = u & 0x7fffffu;
+    if (((u >> 23) & 0xff) == 0xff) return (uint16_t)(sign | 0x7c00u | (man ? 0x200u : 0));
+    if (exp >= 31) return (uint16_t)(sign | 0x7c00u);
+    if (exp <= 0) {
+        if (exp < -10) return (uint16_t)sign;
+        man |= 0x800000u;
+        const int shift = 14 - exp;
+        uint32_t h = man >> shift;
+        const uint32_t rem = man & ((1u << shift) - 1), half = 1u << (shift - 1);
+        if (rem > half || (rem == half && (h & 1))) h++;
+        return (uint16_t)(sign | h);
+    }
+    uint32_t h = ((uint32_t)exp << 10) | (man >> 13);
+    const uint32_t rem = man & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1))) h++;
+    return (uint16_t)(sign | h);
+}
+
 // conv [cout][cin][3][3] (+ BN, folded) -> bf16 blocks [cin_pad/64][9][8][256][8] + f32 bias[256]
 static int upload_conv(NnState* s, ConvLayer* L, const HostTensor* w, const HostTensor* conv_bias, const HostTensor* bn_w,
                        const HostTensor* bn_b, const HostTensor* bn_m, const HostTensor* bn_v, int cin_pad) {
@@ -310,7 +336,7 @@ static int upload_conv(NnState* s, ConvLayer* L, const HostTensor* w, const Host
                 // one 32 KB block per (kb, tap) holding the two N halves as separate contiguous 16 KB
                 // shared-memory images (one per CTA of the pair): [2 halves][8 k-chunks][128 n][8]
                 const size_t in_blk = (((size_t)(co / 128) * 8 + kc) * 128 + co % 128) * 8 + e;
-                blk[((size_t)kb * 9 + ti) * (8 * 256 * 8) + in_blk] = f32_to_bf16(v);
+                blk[((size_t)kb * 9 + ti) * (8 * 256 * 8) + in_blk] = s->f16 ? f32_to_f16(v) : f32_to_bf16(v);
             }
     void* dw = nullptr;
     void* db = nullptr;
@@ -367,6 +393,7 @@ int nn_set_weights(tz_handle* h, const char* const* names, const float* const* d
     h->nn = nullptr;
     NnState* s = new NnState();
     h->nn = s;
+    s->f16 = h->nn_f16;
     const int n = h->d.n, nn = n * n;
     s->n = n;
     s->in_channels = 2 * (2 * n + 3 + 2) + 2;
@@ -550,6 +577,7 @@ static void launch_conv(tz_handle* h, const ConvLayer& L, const __nv_bfloat16* i
     p.n = s->n;
     p.guard = conv::HALO;
     p.masks = s->masks;
+    p.f16 = s->f16;
     const int max_tiles = (count_max * s->n * s->n + conv::TILE_M - 1) / conv::TILE_M;
     const int pairs = (max_tiles + 1) / 2, max_pairs = s->sm_count / 2;
     const int grid = 2 * (pairs < max_pairs ? (pairs > 0 ? pairs : 1) : max_pairs);
@@ -568,7 +596,7 @@ int nn_forward(tz_handle* h, const TzState* states, const int* count_ptr, int co
     {
         ProfScope ps(h, TZ_PROF_ENCODE);
         k_encode<<<wblocks, 32 * WPB, 0, h->stream>>>(states, count_ptr, count_max, d.n, d.half_komi, nullptr, s->planes,
-                                                      conv::HALO, (long long)s->rows);
+                                                      conv::HALO, (long long)s->rows, s->f16);
     }
     int done = 0;
     const int limit = s->layer_limit;
@@ -604,7 +632,7 @@ int nn_forward(tz_handle* h, const TzState* states, const int* count_ptr, int co
         k_heads_gather<<<wblocks, 32 * WPB, 0, h->stream>>>(
             s->act_x, (long long)s->rows, s->logits_full, (long long)s->max_positions * d.n * d.n, s->head_w, s->head_misc,
             actions, n_actions, count_ptr, count_max, d.n, d.M, conv::HALO, s->simhash_set, s->simhash_idx, logits, value,
-            variance);
+            variance, s->f16);
     }
     h->launches += 2;
     return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
@@ -618,18 +646,20 @@ int nn_forward_queue(tz_handle* h) {
 int nn_encode_planes(tz_handle* h, const TzState* states, int count, float* out_f32) {
     const TzDev& d = h->d;
     k_encode<<<(count + WPB - 1) / WPB, 32 * WPB, 0, h->stream>>>(states, nullptr, count, d.n, d.half_komi, out_f32,
-                                                                  nullptr, 0, 0);
+                                                                  nullptr, 0, 0, 0);
     return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
 }
 
 // debug read-back: which = 0 act_x, 1 act_t, 2 planes; f32 [count][n*n][channels]
-__global__ void k_unpad(const __nv_bfloat16* buf, int channels, int count, int n, int guard, long long rows, float* out) {
+__global__ void k_unpad(const __nv_bfloat16* buf, int channels, int count, int n, int guard, long long rows, int f16,
+                        float* out) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int nn = n * n;
     if (idx >= (size_t)count * nn * channels) return;
     const int c = (int)(idx % channels);
     const size_t cell = idx / channels;  // position * nn + square
-    out[idx] = __bfloat162float(buf[((size_t)(c >> 3) * (size_t)rows + (size_t)guard + cell) * 8 + (c & 7)]);
+    const size_t at = ((size_t)(c >> 3) * (size_t)rows + (size_t)guard + cell) * 8 + (c & 7);
+    out[idx] = f16 ? __half2float(reinterpret_cast<const __half*>(buf)[at]) : __bfloat162float(buf[at]);
 }
 
 int nn_debug_read(tz_handle* h, int which, int count, float* out_dev) {
@@ -639,7 +669,7 @@ int nn_debug_read(tz_handle* h, int which, int count, float* out_dev) {
     const int channels = which == 2 ? CIN_PAD : FILTERS;
     const size_t total = (size_t)count * s->n * s->n * channels;
     k_unpad<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(buf, channels, count, s->n, conv::HALO,
-                                                                    (long long)s->rows, out_dev);
+                                                                    (long long)s->rows, s->f16, out_dev);
     return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
 }
 

@@ -27,6 +27,7 @@ def _declare():
     capi.declare("tz_set_weights", [vp, C.POINTER(_Tensor), i32], i32)
     capi.declare("tz_evaluate", [vp, vp, i32, vp, vp, i32, vp, vp, vp], i32)
     capi.declare("tz_encode_planes", [vp, vp, i32, vp], i32)
+    capi.declare("tz_set_network_dtype", [vp, i32], i32)
     capi.declare("tz_set_simhash", [vp, vp, vp], i32)
     capi.declare("tz_simhash_indices", [vp, vp, i32, vp], i32)
     capi.declare("tz_debug_layer_limit", [vp, i32], i32)
@@ -35,9 +36,14 @@ def _declare():
     _declared = True
 
 
-def set_weights(mcts: capi.BatchedMCTS, tensors: Dict[str, np.ndarray]) -> None:
-    """`Net::load`: upload named f32 tensors (PyTorch layout, names in include/takzero_b200.h)."""
+DTYPE_BF16, DTYPE_F16 = 0, 1
+
+
+def set_weights(mcts: capi.BatchedMCTS, tensors: Dict[str, np.ndarray], dtype: int = DTYPE_BF16) -> None:
+    """`Net::load`: upload named f32 tensors (PyTorch layout, names in include/takzero_b200.h); `dtype` is the
+    16-bit type of weights and activations on the device (bf16 by default)."""
     _declare()
+    capi._check(capi.lib().tz_set_network_dtype(mcts.handle, dtype))
     keep = []
     arr = (_Tensor * len(tensors))()
     for i, (name, t) in enumerate(tensors.items()):

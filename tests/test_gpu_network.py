@@ -47,12 +47,12 @@ def test_encode_golden_vector():
     m.close()
 
 
-def check_network(n, half_komi, count, blocks, seed, randomize_bn):
+def check_network(n, half_komi, count, blocks, seed, randomize_bn, dtype=network.DTYPE_BF16, tol=TOL):
     ref = net_ref.Net(n, seed=seed, blocks=blocks, randomize_bn=randomize_bn)
     games = sample_positions(n, half_komi, count, seed)
     actions = [O.possible_moves(g) for g in games]
     m = capi.BatchedMCTS(n, half_komi, count, arena_slots=4096)
-    network.set_weights(m, ref.tensors())
+    network.set_weights(m, ref.tensors(), dtype)
     logits, values, variances = network.evaluate(m, games_to_states(games), actions)
     want_logits, want_values, want_var = ref.policy_value_uncertainty(games, actions)
     worst = 0.0
@@ -63,8 +63,8 @@ def check_network(n, half_komi, count, blocks, seed, randomize_bn):
         agree += int(np.argmax(logits[i]) == np.argmax(want_logits[i]))
     dv = float(np.abs(values - want_values).max())
     print(f"n={n} blocks={blocks}: max |dlogit| {worst:.4g}, max |dvalue| {dv:.4g}, argmax agreement {agree}/{count}")
-    assert worst <= TOL, f"policy logits differ by {worst}"
-    assert dv <= TOL, f"values differ by {dv}"
+    assert worst <= tol, f"policy logits differ by {worst}"
+    assert dv <= tol, f"values differ by {dv}"
     assert np.array_equal(variances, want_var)  # 4.0 everywhere with an empty SimHash set
     assert agree >= 0.99 * count
     m.close()
@@ -114,6 +114,12 @@ def test_network_full_4x4():
 
 def test_network_full_5x5():
     check_network(5, 4, 48, 20, 123, False)
+
+
+def test_network_fp16_mode_is_tighter():
+    """TZ_DTYPE_F16: same kernels on IEEE half; the error against the f32 reference is ~8x smaller."""
+    check_network(6, 4, 96, 16, 123, False, dtype=network.DTYPE_F16, tol=1.5e-3)
+    check_network(4, 4, 64, 2, 11, True, dtype=network.DTYPE_F16, tol=1.5e-3)
 
 
 def test_search_with_device_network_matches_injected_outputs():
@@ -216,18 +222,20 @@ def test_model_reload_replaces_weights_and_keeps_buffers():
     m.close()
 
 
-def test_chosen_moves_agree_with_f32_reference_search():
+@pytest.mark.parametrize("dtype,floor", [(network.DTYPE_BF16, 0.95), (network.DTYPE_F16, 0.99)])
+def test_chosen_moves_agree_with_f32_reference_search(dtype, floor):
     """Whole-search agreement: the oracle search driven by the f32 PyTorch network vs the CUDA search driven by
-    the bf16 tcgen05 network, same injected Gumbel noise, compared on the move sequential halving selects.
+    the 16-bit tcgen05 network, same injected Gumbel noise, compared on the move sequential halving selects.
     This is stricter than the per-position criterion (policy argmax / logits, checked at 100 % / 2e-3 in
     check_network): a 1e-3 logit difference can flip a near-tie between noisy candidates and the search then
-    diverges.  Measured 97.7 % on this configuration; the assertion guards regressions."""
+    diverges.  bf16 (the default) measures 97.7 % here, fp16 99.7 %, which is the
+    north star's ">= 99 % of positions"; the floors guard regressions."""
     n, hk, G, k, budget = 4, 4, 384, 8, 48
     ref = net_ref.Net(n, seed=17, blocks=4, randomize_bn=True)
     games = sample_positions(n, hk, G, 33)
     rng = np.random.default_rng(5)
     m = capi.BatchedMCTS(n, hk, G, arena_slots=1 << 13)
-    network.set_weights(m, ref.tensors())
+    network.set_weights(m, ref.tensors(), dtype)
     m.set_agent(capi.AGENT_NETWORK)
     m.set_positions(games_to_states(games))
     gumbel = rng.gumbel(size=(G, m.move_stride)).astype(np.float32)
@@ -241,6 +249,6 @@ def test_chosen_moves_agree_with_f32_reference_search():
     same_visits = np.mean([np.array_equal(tbl["visits"][g, : tbl["n"][g]],
                                           np.array([ob.node(g).children[i].visit_count for i in range(ob.node(g).n_children)]))
                            for g in range(G)])
-    print(f"chosen-move agreement {agree:.4f}, identical root visit vectors {same_visits:.4f}")
-    assert agree >= 0.95
+    print(f"dtype {dtype}: chosen-move agreement {agree:.4f}, identical root visit vectors {same_visits:.4f}")
+    assert agree >= floor
     m.close()
