@@ -5,13 +5,11 @@
 // reference's text formats (target.rs:56-73,215-232) so `learn` can consume them unchanged.
 //
 // Differences from the reference, all at the process boundary: constants are flags instead of
-// compile-time consts (main.rs:36-52); the model is a TZW1 tensor file (`--weights`, default
-// <directory>/model_latest.tzw when present) instead of `model_latest.ot`, re-read before a move whenever the
-// file changed (the reference reloads unconditionally every move, main.rs:107); the `buffer_lengths.txt`
-// throttle with its checksum (main.rs:93-104,371-387) is honoured when that file exists; the loop stops after
-// --moves iterations.
-#include <sys/stat.h>
-
+// compile-time consts (main.rs:36-52); the model is `--weights` or <directory>/model_latest.ot (the tch archive
+// `learn` writes, read without libtorch; a TZW1 file `model_latest.tzw` is the second choice), re-read before a
+// move whenever the file changed (the reference reloads unconditionally every move, main.rs:107); the
+// `buffer_lengths.txt` throttle with its checksum (main.rs:93-104,371-387) is honoured when that file exists;
+// the loop stops after --moves iterations.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -78,29 +76,6 @@ static Args parse(int argc, char** argv) {
 
 static const size_t MAX_SELFPLAY_BUFFER_LEN = 32000;  // main.rs:43
 
-// read_buffer_lengths (main.rs:371-387): "selfplay,reanalyze,checksum"; -1 absent, -2 malformed / torn read
-static long read_buffer_lengths(const std::string& directory) {
-    std::ifstream f(directory + "/buffer_lengths.txt");
-    if (!f) return -1;
-    std::string text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
-    std::vector<unsigned long long> nums;
-    std::stringstream ss(text);
-    std::string tok;
-    while (std::getline(ss, tok, ',')) {
-        char* end = nullptr;
-        const unsigned long long v = std::strtoull(tok.c_str(), &end, 10);
-        if (end != tok.c_str() && (*end == 0 || *end == '\n')) nums.push_back(v);
-    }
-    if (nums.size() < 3 || nums[0] + nums[1] != nums[2]) return -2;
-    return (long)nums[0];
-}
-
-static long long mtime_ns(const std::string& path) {
-    struct stat st;
-    if (stat(path.c_str(), &st) != 0) return -1;
-    return (long long)st.st_mtim.tv_sec * 1000000000LL + st.st_mtim.tv_nsec;
-}
-
 static void append(const std::string& path, const std::string& contents) {
     std::ofstream f(path, std::ios::app | std::ios::binary);
     if (!f || !(f << contents)) std::fprintf(stderr, "Could not save to %s, so here it is instead:\n%s", path.c_str(), contents.c_str());
@@ -110,15 +85,15 @@ int main(int argc, char** argv) {
     Args args = parse(argc, argv);
     try {
         BatchedMCTS mcts(args.board, args.half_komi, args.games, args.device, 0, args.arena_slots);
-        if (args.weights.empty() && mtime_ns(args.directory + "/model_latest.tzw") >= 0)
-            args.weights = args.directory + "/model_latest.tzw";
+        for (const char* name : {"/model_latest.ot", "/model_latest.tzw"})
+            if (args.weights.empty() && mtime_ns(args.directory + name) >= 0) args.weights = args.directory + name;
         long long model_stamp = -1;
         auto reload_model = [&]() {  // Net::load before every move (main.rs:107), skipped while unchanged
             if (args.weights.empty()) return;
             const long long stamp = mtime_ns(args.weights);
             if (stamp == model_stamp) return;
             try {
-                mcts.set_weights(Weights::load(args.weights));
+                mcts.load_model(args.weights);
                 mcts.set_agent(TZ_AGENT_NETWORK);
                 model_stamp = stamp;
             } catch (const std::exception& e) {
@@ -143,9 +118,9 @@ int main(int argc, char** argv) {
         for (int step = 0; step < args.moves; step++) {
             // wait while the trainer's exploitation buffer is full (main.rs:93-104)
             for (;;) {
-                const long exploitation = read_buffer_lengths(args.directory);
-                if (exploitation == -1 || (exploitation >= 0 && (size_t)exploitation <= MAX_SELFPLAY_BUFFER_LEN)) break;
-                if (exploitation == -2) std::fprintf(stderr, "Could not read buffer lengths: wrong checksum or missing component\n");
+                const BufferLengths lengths = read_buffer_lengths(args.directory);
+                if (lengths.status == -1 || (lengths.status == 0 && lengths.selfplay <= MAX_SELFPLAY_BUFFER_LEN)) break;
+                if (lengths.status == -2) std::fprintf(stderr, "Could not read buffer lengths: wrong checksum or missing component\n");
                 std::this_thread::sleep_for(std::chrono::seconds(1));
             }
             reload_model();

@@ -72,7 +72,7 @@ int main(int argc, char** argv) {
         // one game (the tree) with a large arena; the evaluation queue holds BATCH_SIZE leaves
         BatchedMCTS mcts(board, half_komi, 1, device, 0, arena_slots, BATCH_SIZE);
         if (!weights.empty()) {
-            mcts.set_weights(Weights::load(weights));
+            mcts.load_model(weights);
             mcts.set_agent(TZ_AGENT_NETWORK);
         }
         tz_state_t start_env = mcts.envs()[0];  // Env::default()

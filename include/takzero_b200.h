@@ -247,6 +247,20 @@ TZ_API int tz_tree_principal_variation(tz_handle* h, tz_move_t* out_moves, int c
  * The number of residual blocks is taken from the names (16 for net4/net6, 20 for net5).  BatchNorm is
  * folded (eval mode, eps 1e-5) and the convolutions are converted to bf16 here. */
 TZ_API int tz_set_weights(tz_handle* h, const tz_tensor_t* tensors, int count);
+/* Net::load (network/mod.rs:20-27, net6_simhash.rs:164-181) from the reference's own model file: `path` is a tch
+ * `VarStore::save` archive (`model_latest.ot`, written by learn/src/main.rs:166,257 and re-read before every move
+ * by selfplay/src/main.rs:107 and reanalyze/src/main.rs:93), parsed here without libtorch (ZIP + pickle); a
+ * `torch.save` state dict or this repository's TZW1 container work too.  tch variable names are mapped to the
+ * names above: the two SmallBlocks of a ResidualBlock share one path (residual.rs:52-54), so the file holds
+ * `core.res_block_B.conv2d.weight` (block half 0) and `core.res_block_B.conv2d.weight__K` (half 1).  When the file
+ * has a `simhash_matrix`, it and the sidecar `bitvec.bin` next to the file (absent = empty set) go through
+ * tz_set_simhash. */
+TZ_API int tz_load_model(tz_handle* h, const char* path);
+/* Tensor::load_multi: calls fn for every tensor of the file (converted to contiguous f32) with the mapped and the
+ * stored name; returns the tensor count or a negative code.  Needs no GPU. */
+typedef void (*tz_model_tensor_fn)(void* ctx, const char* name, const char* stored_name, const float* data,
+                                   const int64_t* shape, int ndim);
+TZ_API int tz_read_model_file(const char* path, tz_model_tensor_fn fn, void* ctx);
 /* 16-bit type the NEXT tz_set_weights converts weights and activations to.  TZ_DTYPE_BF16 (default) is what
  * the design targets; TZ_DTYPE_F16 runs the same tcgen05 kind::f16 kernels on IEEE half (3 more mantissa
  * bits, ~8x smaller error against the f32 reference, but 65504 range: an overflow surfaces as TZ_STATUS_NAN). */

@@ -17,10 +17,13 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <utility>
 #include <vector>
+
+#include <sys/stat.h>
 
 #include "takzero_b200.h"
 
@@ -311,38 +314,62 @@ struct Replay {
     }
 };
 
-// ---- weights file (our own container: "TZW1", count, then per tensor name / shape / f32 data) ----------------
+// ---- files the reference's processes synchronise through ------------------------------------------------------
+
+// `buffer_lengths.txt`, written by learn/src/main.rs:195-209 as "{selfplay},{reanalyze},{sum}" and read by
+// read_buffer_lengths (selfplay/src/main.rs:371-387, reanalyze/src/main.rs:304-320): status 0 ok, -1 no such file
+// (io error), -2 missing component / wrong checksum (torn read)
+struct BufferLengths {
+    int status = -1;
+    size_t selfplay = 0, reanalyze = 0;
+};
+inline BufferLengths read_buffer_lengths(const std::string& directory) {
+    BufferLengths out;
+    std::ifstream f(directory + "/buffer_lengths.txt");
+    if (!f) return out;
+    const std::string text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    std::vector<unsigned long long> nums;
+    std::stringstream ss(text);
+    std::string tok;
+    while (std::getline(ss, tok, ',')) {
+        char* end = nullptr;
+        const unsigned long long v = std::strtoull(tok.c_str(), &end, 10);
+        if (end != tok.c_str() && (*end == 0 || *end == '\n')) nums.push_back(v);
+    }
+    out.status = -2;
+    if (nums.size() < 3 || nums[0] + nums[1] != nums[2]) return out;
+    out.status = 0;
+    out.selfplay = (size_t)nums[0];
+    out.reanalyze = (size_t)nums[1];
+    return out;
+}
+
+inline long long mtime_ns(const std::string& path) {
+    struct stat st;
+    if (stat(path.c_str(), &st) != 0) return -1;
+    return (long long)st.st_mtim.tv_sec * 1000000000LL + st.st_mtim.tv_nsec;
+}
+
+// ---- model files: the reference's `model_latest.ot` (tch VarStore archive), a `torch.save` state dict or this
+// repository's TZW1 container, all parsed by the library (tz_read_model_file) -----------------------------------
 
 struct Weights {
     std::vector<std::string> names;
     std::vector<std::vector<int64_t>> shapes;
     std::vector<std::vector<float>> data;
-    static Weights load(const std::string& path) {
-        std::ifstream f(path, std::ios::binary);
-        if (!f) throw std::runtime_error("cannot open " + path);
-        char magic[4];
-        uint32_t count = 0;
-        f.read(magic, 4);
-        f.read(reinterpret_cast<char*>(&count), 4);
-        if (std::memcmp(magic, "TZW1", 4) != 0) throw std::runtime_error(path + ": not a TZW1 file");
+    static Weights load(const std::string& path) {  // Tensor::load_multi
         Weights w;
-        for (uint32_t i = 0; i < count; i++) {
-            uint32_t len = 0, ndim = 0;
-            f.read(reinterpret_cast<char*>(&len), 4);
-            std::string name(len, '\0');
-            f.read(name.data(), len);
-            f.read(reinterpret_cast<char*>(&ndim), 4);
-            std::vector<int64_t> shape(ndim);
-            f.read(reinterpret_cast<char*>(shape.data()), 8 * ndim);
-            size_t numel = 1;
-            for (int64_t d : shape) numel *= (size_t)d;
-            std::vector<float> v(numel);
-            f.read(reinterpret_cast<char*>(v.data()), 4 * numel);
-            if (!f) throw std::runtime_error(path + ": truncated");
-            w.names.push_back(std::move(name));
-            w.shapes.push_back(std::move(shape));
-            w.data.push_back(std::move(v));
-        }
+        check(tz_read_model_file(
+            path.c_str(),
+            [](void* ctx, const char* name, const char*, const float* data, const int64_t* shape, int ndim) {
+                Weights& self = *static_cast<Weights*>(ctx);
+                self.names.emplace_back(name);
+                self.shapes.emplace_back(shape, shape + ndim);
+                size_t numel = 1;
+                for (int i = 0; i < ndim; i++) numel *= (size_t)shape[i];
+                self.data.emplace_back(data, data + numel);
+            },
+            &w));
         return w;
     }
 };
@@ -380,6 +407,8 @@ class BatchedMCTS {
             t[i] = tz_tensor_t{w.names[i].c_str(), w.data[i].data(), w.shapes[i].data(), (int)w.shapes[i].size()};
         check(tz_set_weights(h_, t.data(), (int)t.size()));
     }
+    // Net::load(path, device) (network/mod.rs:20-27, net6_simhash.rs:164-181) incl. the `bitvec.bin` sidecar
+    void load_model(const std::string& path) { check(tz_load_model(h_, path.c_str())); }
     void set_agent(int kind, tz_agent_fn fn = nullptr, void* ctx = nullptr) { check(tz_set_agent(h_, kind, fn, ctx)); }
     void new_openings(uint64_t seed) { check(tz_new_openings(h_, nullptr, nullptr, nullptr, seed)); }
     void set_positions(const std::vector<tz_state_t>& envs) { check(tz_set_positions(h_, envs.data(), nullptr)); }

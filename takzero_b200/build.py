@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtakzero_b200.so")
-SOURCES = ["api.cu", "kernels.cu", "nn.cu"]
+SOURCES = ["api.cu", "kernels.cu", "nn.cu", "model_file.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--cudart", "static",
@@ -45,7 +45,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     bdir = os.path.join(HERE, "build")
     os.makedirs(bdir, exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(bdir, src.replace(".cu", ".o"))
+        obj = os.path.join(bdir, os.path.splitext(src)[0] + ".o")
         cmd = [nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

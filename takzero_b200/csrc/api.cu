@@ -39,6 +39,8 @@ static int fail(int code, const char* fmt, ...) {
         CU(cudaSetDevice((h)->device));                               \
     } while (0)
 
+void tz_internal_set_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }  // model_file.cpp
+
 extern "C" TZ_API const char* tz_last_error(void) { return g_err; }
 extern "C" TZ_API const char* tz_version(void) { return "takzero_b200 0.1 (sm_100a)"; }
 

@@ -371,6 +371,39 @@ int nn_set_weights(tz_handle* h, const char* const* names, const float* const* d
         t.shape.assign(shapes[i], shapes[i] + ndims[i]);
         ts.push_back(t);
     }
+    // check names and shapes before touching the current model: a reload from a bad file (the reference keeps its
+    // previous `net` when Net::load fails, selfplay/src/main.rs:107-119) must leave the handle usable
+    {
+        const long long n0 = h->d.n, cin0 = 2 * (2 * n0 + 3 + 2) + 2, cout0 = 3 + 4 * ((1ll << n0) - 2);
+        std::vector<std::pair<std::string, std::vector<long long>>> req;
+        auto bn = [&](const std::string& p) {
+            for (const char* f : {"weight", "bias", "running_mean", "running_var"}) req.push_back({p + "." + f, {FILTERS}});
+        };
+        req.push_back({"core.input_conv2d.weight", {FILTERS, cin0, 3, 3}});
+        bn("core.batch_norm");
+        int nb = 0;
+        while (find(ts, "core.res_block_" + std::to_string(nb) + ".0.conv2d.weight")) nb++;
+        if (nb == 0) NN_FAIL(TZ_EINVAL, "no residual blocks (core.res_block_0.0.conv2d.weight) found");
+        for (int b = 0; b < nb; b++)
+            for (int j = 0; j < 2; j++) {
+                const std::string p = "core.res_block_" + std::to_string(b) + "." + std::to_string(j);
+                req.push_back({p + ".conv2d.weight", {FILTERS, FILTERS, 3, 3}});
+                bn(p + ".batch_norm");
+            }
+        req.push_back({"policy.conv2d.weight", {cout0, FILTERS, 3, 3}});
+        req.push_back({"policy.conv2d.bias", {cout0}});
+        for (const char* head : {"value", "ube"}) {
+            req.push_back({std::string(head) + ".conv2d.weight", {1, FILTERS, 1, 1}});
+            req.push_back({std::string(head) + ".conv2d.bias", {1}});
+            req.push_back({std::string(head) + ".linear.weight", {1, n0 * n0}});
+            req.push_back({std::string(head) + ".linear.bias", {1}});
+        }
+        for (const auto& r : req) {
+            const HostTensor* t = find(ts, r.first);
+            if (!t) NN_FAIL(TZ_EINVAL, "missing tensor %s", r.first.c_str());
+            if (t->shape != r.second) NN_FAIL(TZ_EINVAL, "tensor %s has the wrong shape", r.first.c_str());
+        }
+    }
     // a model reload (selfplay/src/main.rs:107 does one per move) keeps the activation buffers of the previous
     // state: only the weights are re-folded and re-uploaded
     struct OldState {

@@ -16,6 +16,9 @@ class _Tensor(C.Structure):
                 ("ndim", C.c_int)]
 
 
+_MODEL_TENSOR_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_int64),
+                               C.c_int)
+
 _declared = False
 
 
@@ -33,6 +36,8 @@ def _declare():
     capi.declare("tz_debug_layer_limit", [vp, i32], i32)
     capi.declare("tz_debug_activations", [vp, i32, i32, vp], i32)
     capi.declare("tz_debug_time_tower", [vp, i32, i32, C.POINTER(C.c_double)], i32)
+    capi.declare("tz_load_model", [vp, C.c_char_p], i32)
+    capi.declare("tz_read_model_file", [C.c_char_p, _MODEL_TENSOR_FN, vp], i32)
     _declared = True
 
 
@@ -52,6 +57,31 @@ def set_weights(mcts: capi.BatchedMCTS, tensors: Dict[str, np.ndarray], dtype: i
         keep += [a, shape]
         arr[i] = _Tensor(name.encode(), a.ctypes.data_as(C.POINTER(C.c_float)), shape, a.ndim)
     capi._check(capi.lib().tz_set_weights(mcts.handle, arr, len(tensors)))
+
+
+def load_model(mcts: capi.BatchedMCTS, path: str, dtype: int = DTYPE_BF16) -> None:
+    """`Net::load(path, device)` (network/mod.rs:20-27, net6_simhash.rs:164-181): read the reference's
+    `model_latest.ot` (tch VarStore archive; also a `torch.save` state dict or a TZW1 file) inside the library,
+    upload it, and take the SimHash matrix / `bitvec.bin` sidecar when the file has them."""
+    _declare()
+    capi._check(capi.lib().tz_set_network_dtype(mcts.handle, dtype))
+    capi._check(capi.lib().tz_load_model(mcts.handle, str(path).encode()))
+
+
+def read_model_file(path: str, stored_names: bool = False) -> Dict[str, np.ndarray]:
+    """`Tensor::load_multi`: every tensor of a model file as f32, keyed by the library's tensor names (or by the
+    names stored in the file).  Parsed by the C++ reader of the library; needs no GPU."""
+    _declare()
+    out: Dict[str, np.ndarray] = {}
+
+    def cb(_ctx, name, stored, data, shape, ndim):
+        shp = tuple(shape[i] for i in range(ndim))
+        n = int(np.prod(shp)) if ndim else 1
+        a = np.ctypeslib.as_array(data, shape=(n,)).copy() if n else np.zeros(0, np.float32)
+        out[(stored if stored_names else name).decode()] = a.reshape(shp)
+
+    capi._check(capi.lib().tz_read_model_file(str(path).encode(), _MODEL_TENSOR_FN(cb), None))
+    return out
 
 
 def evaluate(mcts: capi.BatchedMCTS, states: np.ndarray, actions: Sequence[Sequence[int]]):

@@ -79,3 +79,33 @@ def save_tzw(path: str, tensors: Dict[str, np.ndarray]) -> None:
             f.write(struct.pack("<I", len(nb)) + nb + struct.pack("<I", a.ndim))
             f.write(struct.pack(f"<{a.ndim}q", *a.shape))
             f.write(a.tobytes())
+
+
+def tch_names(tensors: Dict[str, np.ndarray], first_suffix: int = 0) -> Dict[str, np.ndarray]:
+    """Rename this package's tensor names to the ones tch's `VarStore` gives the reference network: both
+    `SmallBlock`s of a `ResidualBlock` are built on one path (network/residual.rs:52-54), so half 0 keeps
+    `core.res_block_B.conv2d.weight` and half 1 gets the collision suffix `__K` (K = variables in the store when the
+    clash happened; the reader ignores the value, `first_suffix` only makes test files look real)."""
+    import re
+
+    out: Dict[str, np.ndarray] = {}
+    k = first_suffix
+    for name, t in tensors.items():
+        m = re.fullmatch(r"(core\.res_block_\d+)\.([01])\.(.+)", name)
+        if m:
+            name = f"{m.group(1)}.{m.group(3)}" + (f"__{k}" if m.group(2) == "1" else "")
+        out[name] = t
+        k += 1
+    return out
+
+
+def save_ot(path: str, tensors: Dict[str, np.ndarray], rename: bool = True) -> None:
+    """Write a libtorch module archive with one tensor attribute per name -- the container tch's
+    `VarStore::save` produces for `model_latest.ot` (ZIP: `<stem>/data.pkl` + `<stem>/data/<key>`).  Used to make
+    test inputs for the library's `.ot` reader; torch is the writer, so this is tooling, not the product path."""
+    import torch
+
+    m = torch.jit.ScriptModule()
+    for name, t in (tch_names(tensors) if rename else tensors).items():
+        m._c._register_attribute(name, torch._C.TensorType.get(), torch.from_numpy(np.ascontiguousarray(t)))
+    m._c.save(str(path))

@@ -197,6 +197,51 @@ def test_simhash_indices_and_uncertainty():
     m.close()
 
 
+def test_load_model_from_tch_archive_with_bitvec_sidecar(tmp_path):
+    """Net::load (network/mod.rs:20-27, net6_simhash.rs:164-181) from the reference's own files: a tch-named
+    `model_latest.ot` plus the `bitvec.bin` SimHash set beside it give exactly the outputs of tz_set_weights +
+    tz_set_simhash with the same tensors (bit for bit), in both weight dtypes."""
+    from takzero_b200 import weights
+
+    n, hk, count = 6, 4, 48
+    ref = net_ref.Net(n, seed=13, blocks=2, randomize_bn=True)
+    games = sample_positions(n, hk, count, 13)
+    actions = [O.possible_moves(g) for g in games]
+    states = games_to_states(games)
+    a = capi.BatchedMCTS(n, hk, count, arena_slots=4096)
+    network.set_weights(a, ref.tensors())
+    network.set_simhash(a, ref.simhash_matrix.numpy())
+    ref.simhash_set = {int(x) for x in network.simhash_indices(a, states)[::3]}
+    bits = ref.bitset_bytes()
+    network.set_simhash(a, ref.simhash_matrix.numpy(), bits)
+    want = network.evaluate(a, states, actions)
+    assert (want[2] < 4.0).sum() >= count // 3
+
+    tensors = dict(ref.tensors())
+    tensors["simhash_matrix"] = ref.simhash_matrix.numpy()
+    weights.save_ot(str(tmp_path / "model_latest.ot"), tensors)
+    np.asarray(bits, dtype=np.uint8).tofile(str(tmp_path / "bitvec.bin"))
+    b = capi.BatchedMCTS(n, hk, count, arena_slots=4096)
+    network.load_model(b, str(tmp_path / "model_latest.ot"))
+    got = network.evaluate(b, states, actions)
+    for x, y in zip(want[0], got[0]):
+        assert np.array_equal(x, y)
+    assert np.array_equal(want[1], got[1]) and np.array_equal(want[2], got[2])
+    # without the sidecar: the empty set of a fresh network, every local uncertainty is 4.0
+    (tmp_path / "bitvec.bin").unlink()
+    network.load_model(b, str(tmp_path / "model_latest.ot"))
+    assert (network.evaluate(b, states, actions)[2] == 4.0).all()
+    # a file that lacks a tensor is refused with its name, and the previous model stays usable
+    tensors.pop("policy.conv2d.bias")
+    weights.save_ot(str(tmp_path / "broken.ot"), tensors)
+    with pytest.raises(capi.TakzeroError, match="policy.conv2d.bias"):
+        network.load_model(b, str(tmp_path / "broken.ot"))
+    again = network.evaluate(b, states, actions)
+    assert all(np.array_equal(x, y) for x, y in zip(want[0], again[0])) and np.array_equal(want[1], again[1])
+    for h in (a, b):
+        h.close()
+
+
 def test_model_reload_replaces_weights_and_keeps_buffers():
     """Net::load before every move (selfplay/src/main.rs:107): a second tz_set_weights takes effect for the
     next evaluation (activation buffers are reused, only the folded weights change)."""

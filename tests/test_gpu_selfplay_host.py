@@ -103,6 +103,21 @@ def _mix64(x):
     return x
 
 
+def _sample_distinct(seed, b, count, n):
+    """host/reanalyze.cpp `sample_distinct`: slot g takes the first value of its hash sequence not taken before."""
+    out, taken = [], set()
+    for g in range(count):
+        attempt = 0
+        while True:
+            i = _mix64(seed * 0x9E3779B97F4A7C15 + b * 1000003 + g + attempt * 0x632BE59BD9B4E019) % n
+            attempt += 1
+            if i not in taken:
+                taken.add(i)
+                out.append(i)
+                break
+    return out
+
+
 def test_cpp_reanalyze_host(tmp_path):
     """host/reanalyze.cpp (reanalyze/src/main.rs:147-235): fresh-root search over positions expanded from
     replays.txt; value / policy / ube rules checked against an independent Python + oracle replay."""
@@ -134,7 +149,7 @@ def test_cpp_reanalyze_host(tmp_path):
     m = capi.BatchedMCTS(n, hk, G, arena_slots=1 << 15)
     want = ""
     for b in range(2):
-        idx = [_mix64(seed * 0x9E3779B97F4A7C15 + b * 1000003 + g) % len(positions) for g in range(G)]
+        idx = _sample_distinct(seed, b, G, len(positions))
         batch = [positions[i] for i in idx]
         m.set_positions(games_to_states(batch))
         selected = m.gumbel_sequential_halving(np.zeros(G, np.float32), k, budget, None, seed=seed + b)
@@ -157,14 +172,20 @@ def test_cpp_reanalyze_host(tmp_path):
     assert got == want
 
 
-def test_cpp_selfplay_host_with_network_weights_and_buffer_file(tmp_path):
-    """The C++ host loads a TZW1 model (model_latest.tzw in --directory, like model_latest.ot), honours a valid
-    buffer_lengths.txt (selfplay/src/main.rs:93-104,371-387) and searches with the device network."""
+@pytest.mark.parametrize("fmt", ["ot", "tzw"])
+def test_cpp_selfplay_host_with_network_weights_and_buffer_file(tmp_path, fmt):
+    """The C++ host finds the model in --directory -- `model_latest.ot`, the tch archive `learn` writes
+    (selfplay/src/main.rs:107), or a TZW1 file -- honours a valid buffer_lengths.txt (main.rs:93-104,371-387)
+    and searches with the device network."""
     from takzero_b200 import weights
 
     tz_build.build()
     exe = os.path.join(os.path.dirname(capi.LIB_PATH), "bin", "selfplay")
-    weights.save_tzw(str(tmp_path / "model_latest.tzw"), weights.random_init(4, seed=1, blocks=2))
+    w = weights.random_init(4, seed=1, blocks=2)
+    if fmt == "ot":
+        weights.save_ot(str(tmp_path / "model_latest.ot"), w)
+    else:
+        weights.save_tzw(str(tmp_path / "model_latest.tzw"), w)
     (tmp_path / "buffer_lengths.txt").write_text("100,50,150")  # selfplay, reanalyze, checksum: below the limit
     out = subprocess.run([exe, "--directory", str(tmp_path), "--board", "4", "--half-komi", "4", "--games", "64",
                           "--sampled-actions", "8", "--budget", "48", "--moves", "30", "--seed", "3",
