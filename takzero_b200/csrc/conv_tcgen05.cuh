@@ -305,9 +305,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w) + (size_t)rank * B_STAGE_BYTES;
                 for (int blk = 0; blk < kblocks * 9; blk++) {
                     mbar_wait(b_empty + 8 * stage, phase ^ 1);
+#ifdef TZ_EXP_NO_B  // energy experiment (INVALID results): only the first B_STAGES weight blocks are ever copied
+                    if (pt != pair || blk >= B_STAGES) {
+                        mbar_arrive(b_sig + 8 * stage);
+                    } else
+#endif
+                    {
                     mbar_arrive_expect_tx(b_sig + 8 * stage, B_STAGE_BYTES);
                     bulk_g2s(smem_u32(b_smem + stage * B_STAGE_BYTES), src + (size_t)blk * 2 * B_STAGE_BYTES,
                              B_STAGE_BYTES, b_sig + 8 * stage);
+                    }
                     if (++stage == B_STAGES) {
                         stage = 0;
                         phase ^= 1;
