@@ -30,6 +30,15 @@
 //   t_empty[acc]            leader, count 8: epilogue warps of both CTAs
 // Warp roles per CTA: warps 0-3 epilogue (tcgen05.ld -> bias, residual, ReLU -> stores), warp 4 A producer,
 // warp 5 B producer, warp 6 MMA issuer (leader) / A relay (peer), warp 7 TMEM allocator / B relay (peer).
+// Fused tower: one launch can run a CHAIN of layers (Params::layers[0..n_layers)).  The work items
+// (layer, pair tile) are numbered layer-major and dealt round-robin to the persistent CTA pairs, so a pair gets
+// 15.57 tiles per layer on average instead of a whole number per launch, and the launch gap, prologue and
+// pipeline refill between layers disappear.  A 3x3 tap reaches at most HALO rows into the neighbouring tiles,
+// so item (L, t) depends only on items (L-1, t-1..t+1): the epilogue warps publish their finished tile with a
+// release increment of progress[t] and the A producer of a dependent item spins on an acquire load, then
+// crosses to the async proxy with fence.proxy.async before its bulk copies.  The same three waits also cover the
+// write-after-read hazards of the two ping-pong activation buffers (a layer's output buffer is the input buffer
+// of the layer before it).  The launch is cooperative: every pair must be resident, or the spin would deadlock.
 // TZ_DEBUG_TIMING is a compile-time tuning experiment (tools/build_variant.sh); the numbers it produced for
 // the earlier row-major one-CTA / pair kernels are in profiles/r1_conv_timing.txt.
 #pragma once
@@ -60,25 +69,34 @@ constexpr int THREADS = 256;
 constexpr int W_EPI0 = 0, W_APROD = 4, W_BPROD = 5, W_MMA = 6, W_ALLOC = 7;
 constexpr int MASK_BYTES = 36 * 9 * 16;        // [N*N][9 taps] 128-bit lane masks
 constexpr int SMEM_BYTES =
-    A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + 1024 /*bias*/ + 512 /*barriers*/ + MASK_BYTES;
+    A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + 4096 /*bias, one copy per epilogue warp*/ + 512 /*barriers*/ +
+    MASK_BYTES;
+constexpr int MAX_LAYERS = 48;                 // layers one launch can chain (net5: 40 tower convolutions)
 
-struct Params {
+struct Layer {
     const __nv_bfloat16* in;        // [cin/8][rows][8] activations
-    int cin;                        // channels of `in` (multiple of 64)
-    long long rows;                 // rows per chunk plane of in / residual / out_act (incl. guard + halo)
     const __nv_bfloat16* w;         // [cin/64][9 taps][2 halves][8][128][8] pre-arranged weight blocks
     const float* bias;              // [256]
     const __nv_bfloat16* residual;  // [32][rows][8] or null
     __nv_bfloat16* out_act;         // [32][rows][8] or null
     float* out_f32;                 // [64][f32_rows][4] (policy logits, no guard rows) or null
-    long long f32_rows;
+    int cin;                        // channels of `in` (multiple of 64)
     int relu;
+};
+
+struct Params {
+    Layer layers[MAX_LAYERS];       // run back to back; layer l reads what layer l-1 wrote
+    int n_layers;
+    long long rows;                 // rows per chunk plane of in / residual / out_act (incl. guard + halo)
+    long long f32_rows;
     const int* count_ptr;           // number of positions (device), or null: use count_max
     int count_max;
     int n;                          // board size
     int guard;                      // leading guard rows of the activation planes (= HALO)
     const uint4* masks;             // [n*n][9] disable-output-lane masks by (first tile row) mod n*n
     int f16;                        // 16-bit storage / operand type: 0 = bf16, 1 = IEEE fp16 (same UMMA kind::f16)
+    unsigned* progress;             // [pair tiles], zeroed before the launch: epilogue-warp arrivals per tile
+                                    // (8 per finished layer); may be null when n_layers == 1
 };
 
 #ifdef TZ_DEBUG_TIMING
@@ -122,6 +140,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
         "l"(src), "r"(bytes), "r"(bar)
         : "memory");
 }
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// generic-proxy writes (observed through the acquire above) -> async-proxy reads of this thread's bulk copies
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // K-major, no swizzle: 8x8 core matrices of 128 contiguous bytes; LBO = byte distance of the
@@ -218,14 +246,14 @@ __device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t adesc, uin
 }
 
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x3_pair(const Params p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x3_pair(const __grid_constant__ Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
     uint8_t* a_smem = smem;
     uint8_t* b_smem = smem + A_STAGES * A_STAGE_BYTES;
     float* s_bias = reinterpret_cast<float*>(b_smem + B_STAGES * B_STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_bias) + 1024);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_bias) + 4096);
     const uint32_t bar0 = smem_u32(bars);
     const uint32_t a_full = bar0, a_land = a_full + 8 * A_STAGES, a_empty = a_land + 8 * A_STAGES;
     const uint32_t b_full = a_empty + 8 * A_STAGES, b_land = b_full + 8 * B_STAGES;
@@ -238,7 +266,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
     const int nn = p.n * p.n;
     const int rows_used = count * nn;
     const int pair_tiles = (rows_used + 2 * TILE_M - 1) / (2 * TILE_M);
-    const int kblocks = p.cin >> 6;
+    const int items = pair_tiles * p.n_layers;  // item i = (layer i / pair_tiles, pair tile i % pair_tiles)
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
     if (threadIdx.x == 0) {
@@ -264,7 +292,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < N_OUT; i += THREADS) s_bias[i] = p.bias[i];
     for (int i = threadIdx.x; i < nn * 9; i += THREADS) s_masks[i] = p.masks[i];
     tc_fence_before();
     __syncthreads();
@@ -278,10 +305,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
         // ---- A producer (both CTAs): this CTA's 144-row halo tile, 8 chunk planes of 2304 B per stage
         if (lane == 0) {
             int stage = 0, phase = 0;
-            for (int pt = pair; pt < pair_tiles; pt += npairs) {
+            for (int item = pair; item < items; item += npairs) {
+                const int layer = item / pair_tiles, pt = item - layer * pair_tiles;
+                const Layer& L = p.layers[layer];
+                if (layer > 0) {
+                    // rows [t*128 - HALO, t*128 + 128 + HALO) of the previous layer's output: CTA tiles t-1, t, t+1,
+                    // i.e. pair tiles {pt-1, pt} for rank 0 and {pt, pt+1} for rank 1
+                    const unsigned need = 8u * (unsigned)layer;
+                    const int lo = pt - 1 + (int)rank;
+                    for (int q = lo; q <= lo + 1; q++)
+                        if (q >= 0 && q < pair_tiles)
+                            while (ld_acquire_gpu(p.progress + q) < need) __nanosleep(40);
+                    fence_proxy_async();
+                }
                 const int t = pt * 2 + (int)rank;
                 const uint8_t* src_tile =
-                    reinterpret_cast<const uint8_t*>(p.in) + (size_t)(p.guard + t * TILE_M - HALO) * 16;
+                    reinterpret_cast<const uint8_t*>(L.in) + (size_t)(p.guard + t * TILE_M - HALO) * 16;
+                const int kblocks = L.cin >> 6;
                 for (int kb = 0; kb < kblocks; kb++) {
                     mbar_wait(a_empty + 8 * stage, phase ^ 1);
                     mbar_arrive_expect_tx(a_sig + 8 * stage, A_STAGE_BYTES);
@@ -301,19 +341,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
         // ---- B producer (both CTAs): this CTA's half (128 of the 256 N rows) of every weight block
         if (lane == 0) {
             int stage = 0, phase = 0;
-            for (int pt = pair; pt < pair_tiles; pt += npairs) {
-                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w) + (size_t)rank * B_STAGE_BYTES;
-                for (int blk = 0; blk < kblocks * 9; blk++) {
+            for (int item = pair; item < items; item += npairs) {
+                const Layer& L = p.layers[item / pair_tiles];
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(L.w) + (size_t)rank * B_STAGE_BYTES;
+                const int blocks = (L.cin >> 6) * 9;
+                for (int blk = 0; blk < blocks; blk++) {
                     mbar_wait(b_empty + 8 * stage, phase ^ 1);
 #ifdef TZ_EXP_NO_B  // energy experiment (INVALID results): only the first B_STAGES weight blocks are ever copied
-                    if (pt != pair || blk >= B_STAGES) {
+                    if (item != pair || blk >= B_STAGES) {
                         mbar_arrive(b_sig + 8 * stage);
                     } else
 #endif
                     {
-                    mbar_arrive_expect_tx(b_sig + 8 * stage, B_STAGE_BYTES);
-                    bulk_g2s(smem_u32(b_smem + stage * B_STAGE_BYTES), src + (size_t)blk * 2 * B_STAGE_BYTES,
-                             B_STAGE_BYTES, b_sig + 8 * stage);
+                        mbar_arrive_expect_tx(b_sig + 8 * stage, B_STAGE_BYTES);
+                        bulk_g2s(smem_u32(b_smem + stage * B_STAGE_BYTES), src + (size_t)blk * 2 * B_STAGE_BYTES,
+                                 B_STAGE_BYTES, b_sig + 8 * stage);
                     }
                     if (++stage == B_STAGES) {
                         stage = 0;
@@ -327,8 +369,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
         if (rank != 0 && lane == 0) {
             int stage = 0, phase = 0;
             const uint32_t b_full_leader = map_to_rank(b_full, 0);
-            for (int pt = pair; pt < pair_tiles; pt += npairs)
-                for (int blk = 0; blk < kblocks * 9; blk++) {
+            for (int item = pair; item < items; item += npairs) {
+                const int blocks = (p.layers[item / pair_tiles].cin >> 6) * 9;
+                for (int blk = 0; blk < blocks; blk++) {
                     mbar_wait(b_land + 8 * stage, phase);
                     mbar_arrive_cluster(b_full_leader + 8 * stage);
                     if (++stage == B_STAGES) {
@@ -336,6 +379,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                         phase ^= 1;
                     }
                 }
+            }
         }
     } else if (warp == W_MMA) {
         if (rank != 0) {
@@ -343,7 +387,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
             if (lane == 0) {
                 int stage = 0, phase = 0;
                 const uint32_t a_full_leader = map_to_rank(a_full, 0);
-                for (int pt = pair; pt < pair_tiles; pt += npairs)
+                for (int item = pair; item < items; item += npairs) {
+                    const int kblocks = p.layers[item / pair_tiles].cin >> 6;
                     for (int kb = 0; kb < kblocks; kb++) {
                         mbar_wait(a_land + 8 * stage, phase);
                         mbar_arrive_cluster(a_full_leader + 8 * stage);
@@ -352,6 +397,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                             phase ^= 1;
                         }
                     }
+                }
             }
         } else {
             // ---- MMA issuer (leader only): kind::f16, D = f32, A = B = bf16 K-major, M = 256, N = 256, K = 16.
@@ -368,7 +414,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
             long long w_t = 0, w_a = 0, w_b = 0;
             const long long mma_start = clock64();
 #endif
-            for (int pt = pair; pt < pair_tiles; pt += npairs, it++) {
+            for (int item = pair; item < items; item += npairs, it++) {
+                const int layer = item / pair_tiles, pt = item - layer * pair_tiles;
+                const int kblocks = p.layers[layer].cin >> 6;
                 const int acc = it & 1;
                 TWAIT(w_t, mbar_wait(t_empty + 8 * acc, ((it >> 1) & 1) ^ 1));
                 tc_fence_after();
@@ -421,8 +469,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
         const int wq = warp & 3;
         const uint32_t t_empty_leader = map_to_rank(t_empty, 0);
         const size_t plane = (size_t)p.rows * 8;  // elements per chunk plane
-        int it = 0;
-        for (int pt = pair; pt < pair_tiles; pt += npairs, it++) {
+        float* bias_w = s_bias + wq * N_OUT;      // this warp's copy of the current layer's bias
+        int it = 0, bias_layer = -1;
+        for (int item = pair; item < items; item += npairs, it++) {
+            const int layer = item / pair_tiles, pt = item - layer * pair_tiles;
+            const Layer& L = p.layers[layer];
+            if (layer != bias_layer) {
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < N_OUT / 32; j++) bias_w[lane + 32 * j] = __ldg(L.bias + lane + 32 * j);
+                __syncwarp();
+                bias_layer = layer;
+            }
+            const __nv_bfloat16* residual = L.residual;
+            __nv_bfloat16* out_act = L.out_act;
+            float* out_f32 = L.out_f32;
+            const int relu = L.relu;
             const int acc = it & 1;
             const int t = pt * 2 + (int)rank;
             const int rel = t * TILE_M + wq * 32 + lane;  // row = position * n*n + square
@@ -430,6 +492,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
             const size_t grow = (size_t)(p.guard + rel) * 8;  // element offset of the row inside a plane
             mbar_wait(t_full + 8 * acc, (it >> 1) & 1);
             tc_fence_after();
+            // Inside a fused launch the residual rows were written by another SM two layers ago.  One gpu-scope
+            // acquire per tile (on the counter that writer released) makes the plain loads below see them: it costs
+            // an L1 invalidate per warp and tile, whereas L2-only (ld.cg) loads made the epilogue 1.8x slower
+            // than the MMAs of a tile.
+            if (residual != nullptr && layer >= 2) (void)ld_acquire_gpu(p.progress + pt);
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * N_OUT;
 #pragma unroll 1
             for (int c0 = 0; c0 < N_OUT; c0 += 32) {
@@ -439,11 +506,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                 if (valid) {
                     float f[32];
 #pragma unroll
-                    for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]) + s_bias[c0 + j];
-                    if (p.residual) {
+                    for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]) + bias_w[c0 + j];
+                    if (residual) {
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
-                            const uint4 r = *reinterpret_cast<const uint4*>(p.residual + (size_t)(c0 / 8 + j) * plane + grow);
+                            const uint4 r = *reinterpret_cast<const uint4*>(residual + (size_t)(c0 / 8 + j) * plane + grow);
                             const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
                             for (int e = 0; e < 4; e++) {
@@ -453,28 +520,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                             }
                         }
                     }
-                    if (p.relu) {
+                    if (relu) {
 #pragma unroll
                         for (int j = 0; j < 32; j++) f[j] = fmaxf(f[j], 0.0f);
                     }
-                    if (p.out_act) {
+                    if (out_act) {
 #pragma unroll
                         for (int j = 0; j < 4; j++)
-                            *reinterpret_cast<uint4*>(p.out_act + (size_t)(c0 / 8 + j) * plane + grow) =
+                            *reinterpret_cast<uint4*>(out_act + (size_t)(c0 / 8 + j) * plane + grow) =
                                 make_uint4(pack16(f[j * 8], f[j * 8 + 1], p.f16), pack16(f[j * 8 + 2], f[j * 8 + 3], p.f16),
                                            pack16(f[j * 8 + 4], f[j * 8 + 5], p.f16), pack16(f[j * 8 + 6], f[j * 8 + 7], p.f16));
                     }
-                    if (p.out_f32) {
+                    if (out_f32) {
 #pragma unroll
                         for (int j = 0; j < 8; j++)
-                            *reinterpret_cast<float4*>(p.out_f32 + ((size_t)(c0 / 4 + j) * (size_t)p.f32_rows + (size_t)rel) * 4) =
+                            *reinterpret_cast<float4*>(out_f32 + ((size_t)(c0 / 4 + j) * (size_t)p.f32_rows + (size_t)rel) * 4) =
                                 make_float4(f[j * 4], f[j * 4 + 1], f[j * 4 + 2], f[j * 4 + 3]);
                     }
                 }
             }
+            if (p.n_layers > 1) __threadfence();  // this thread's rows are visible device-wide before the tile is published
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(t_empty_leader + 8 * acc);
+            if (lane == 0) {
+                mbar_arrive_cluster(t_empty_leader + 8 * acc);
+                if (p.n_layers > 1) red_release_gpu_add(p.progress + pt, 1u);
+            }
         }
     }
     tc_fence_before();

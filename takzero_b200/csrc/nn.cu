@@ -47,6 +47,9 @@ struct NnState {
     float* simhash_matrix = nullptr;  // [C*N*N][32] (net6_simhash.rs:136-139), optional
     uint32_t* simhash_set = nullptr;  // 2^32-bit set (bitvec.bin), optional; absent = empty set
     uint32_t* simhash_idx = nullptr;  // [max_positions] hash index of each queued position
+    unsigned* progress = nullptr;     // [pair tiles] tile-completion counters of the fused tower launch
+    int max_pairs = 74;               // CTA pairs that can be resident at once (cooperative launch bound)
+    int fused = 1;                    // 1: the tower is one multi-layer launch; 0 (TZ_TOWER=layers): one launch per layer
     int layer_limit = -1;             // debug: stop the tower after this many convolutions
     int f16 = 0;                      // 16-bit type of weights / activations: 0 bf16 (default), 1 fp16
     std::vector<void*> allocs;
@@ -581,6 +584,30 @@ int nn_set_weights(tz_handle* h, const char* const* names, const float* const* d
         nn_free(h);
         NN_FAIL(TZ_ECUDA, "cudaFuncSetAttribute(k_conv3x3_pair, %d B smem) failed", conv::SMEM_BYTES);
     }
+    {
+        // CTA pairs that fit on the device at once: the fused tower spins on other pairs' progress, so its grid
+        // must never exceed this
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * (s->sm_count / 2));
+        cfg.blockDim = dim3(conv::THREADS);
+        cfg.dynamicSmemBytes = conv::SMEM_BYTES;
+        int clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&clusters, conv::k_conv3x3_pair, &cfg) == cudaSuccess && clusters > 0)
+            s->max_pairs = clusters < s->sm_count / 2 ? clusters : s->sm_count / 2;
+        else
+            s->max_pairs = s->sm_count / 2;
+        const char* mode = getenv("TZ_TOWER");
+        s->fused = !(mode && strcmp(mode, "layers") == 0);
+        const size_t tiles = (s->rows + 2 * conv::TILE_M - 1) / (2 * conv::TILE_M) + 1;
+        if (reuse) {
+            s->progress = static_cast<unsigned*>(old.take(old.p->progress));
+            if (s->progress) s->allocs.push_back(s->progress);
+        }
+        if (!s->progress && !dalloc((void**)&s->progress, tiles * sizeof(unsigned))) {
+            nn_free(h);
+            NN_FAIL(TZ_ENOMEM, "cudaMalloc progress");
+        }
+    }
     cudaDeviceSynchronize();
     return TZ_OK;
 }
@@ -591,30 +618,84 @@ void nn_set_layer_limit(tz_handle* h, int limit) {
 
 // ---- forward ---------------------------------------------------------------------------------------------
 
-static void launch_conv(tz_handle* h, const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* residual,
-                        __nv_bfloat16* out_act, float* out_f32, int relu, const int* count_ptr, int count_max) {
+static conv::Layer conv_layer(const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* residual,
+                              __nv_bfloat16* out_act, float* out_f32, int relu) {
+    conv::Layer l;
+    l.in = in;
+    l.w = L.w;
+    l.bias = L.bias;
+    l.residual = residual;
+    l.out_act = out_act;
+    l.out_f32 = out_f32;
+    l.cin = L.cin;
+    l.relu = relu;
+    return l;
+}
+
+// Launches p.layers[0..n_layers) as ONE persistent kernel.  With more than one layer the CTA pairs synchronise
+// through s->progress inside the kernel, so the launch is cooperative (all pairs resident, or it fails loudly).
+static cudaError_t launch_layers(tz_handle* h, conv::Params& p, const int* count_ptr, int count_max) {
     const NnState* s = h->nn;
-    conv::Params p;
-    p.in = in;
-    p.cin = L.cin;
     p.rows = (long long)s->rows;
-    p.w = L.w;
-    p.bias = L.bias;
-    p.residual = residual;
-    p.out_act = out_act;
-    p.out_f32 = out_f32;
     p.f32_rows = (long long)s->max_positions * s->n * s->n;
-    p.relu = relu;
     p.count_ptr = count_ptr;
     p.count_max = count_max;
     p.n = s->n;
     p.guard = conv::HALO;
     p.masks = s->masks;
     p.f16 = s->f16;
+    p.progress = s->progress;
     const int max_tiles = (count_max * s->n * s->n + conv::TILE_M - 1) / conv::TILE_M;
-    const int pairs = (max_tiles + 1) / 2, max_pairs = s->sm_count / 2;
-    const int grid = 2 * (pairs < max_pairs ? (pairs > 0 ? pairs : 1) : max_pairs);
-    conv::k_conv3x3_pair<<<grid, conv::THREADS, conv::SMEM_BYTES, h->stream>>>(p);
+    const int pair_tiles = (max_tiles + 1) / 2;
+    const long long items = (long long)pair_tiles * p.n_layers;
+    const int pairs = items < s->max_pairs ? (items > 0 ? (int)items : 1) : s->max_pairs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(conv::THREADS);
+    cfg.dynamicSmemBytes = conv::SMEM_BYTES;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    if (p.n_layers > 1) {
+        cudaError_t e = cudaMemsetAsync(s->progress, 0, (size_t)(pair_tiles > 0 ? pair_tiles : 1) * sizeof(unsigned), h->stream);
+        if (e != cudaSuccess) return e;
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, conv::k_conv3x3_pair, p);
+}
+
+static void launch_conv(tz_handle* h, const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* residual,
+                        __nv_bfloat16* out_act, float* out_f32, int relu, const int* count_ptr, int count_max) {
+    conv::Params p;
+    p.layers[0] = conv_layer(L, in, residual, out_act, out_f32, relu);
+    p.n_layers = 1;
+    launch_layers(h, p, count_ptr, count_max);
+}
+
+// The whole network body: input conv (planes -> x), residual blocks (conv(x) -> t, conv(t) + x -> x), policy conv
+// (x -> f32 logits).  Fused: all of it is one launch (chunks of conv::MAX_LAYERS); returns the number of launches.
+static int launch_network(tz_handle* h, const int* count_ptr, int count_max) {
+    NnState* s = h->nn;
+    std::vector<conv::Layer> all;
+    all.push_back(conv_layer(s->input, s->planes, nullptr, s->act_x, nullptr, 1));
+    for (int l = 0; l < 2 * s->blocks; l++)
+        all.push_back((l & 1) ? conv_layer(s->tower[l], s->act_t, s->act_x, s->act_x, nullptr, 1)
+                              : conv_layer(s->tower[l], s->act_x, nullptr, s->act_t, nullptr, 1));
+    all.push_back(conv_layer(s->policy, s->act_x, nullptr, nullptr, s->logits_full, 0));
+    int launches = 0;
+    for (size_t first = 0; first < all.size();) {
+        const size_t left = all.size() - first;
+        const size_t chunk = s->fused ? (left < (size_t)conv::MAX_LAYERS ? left : (size_t)conv::MAX_LAYERS) : 1;
+        conv::Params p;
+        for (size_t i = 0; i < chunk; i++) p.layers[i] = all[first + i];
+        p.n_layers = (int)chunk;
+        launch_layers(h, p, count_ptr, count_max);
+        first += chunk;
+        launches++;
+    }
+    return launches;
 }
 
 // states[count] (device), actions/n_actions by position -> logits/value/variance by position.
@@ -631,31 +712,31 @@ int nn_forward(tz_handle* h, const TzState* states, const int* count_ptr, int co
         k_encode<<<wblocks, 32 * WPB, 0, h->stream>>>(states, count_ptr, count_max, d.n, d.half_komi, nullptr, s->planes,
                                                       conv::HALO, (long long)s->rows, s->f16);
     }
-    int done = 0;
     const int limit = s->layer_limit;
-    auto more = [&]() { return limit < 0 || done < limit; };
-    if (more()) {
-        ProfScope ps(h, TZ_PROF_CONV_INPUT);
-        launch_conv(h, s->input, s->planes, nullptr, s->act_x, nullptr, 1, count_ptr, count_max);
-        done++;
-    }
-    for (int b = 0; b < s->blocks; b++) {
+    if (limit >= 0) {  // debug hook: the first `limit` convolutions, one launch each
+        int done = 0;
+        auto more = [&]() { return done < limit; };
         if (more()) {
-            ProfScope ps(h, TZ_PROF_CONV_TOWER);
-            launch_conv(h, s->tower[2 * b], s->act_x, nullptr, s->act_t, nullptr, 1, count_ptr, count_max);
+            launch_conv(h, s->input, s->planes, nullptr, s->act_x, nullptr, 1, count_ptr, count_max);
             done++;
         }
-        if (more()) {
-            ProfScope ps(h, TZ_PROF_CONV_TOWER);
-            launch_conv(h, s->tower[2 * b + 1], s->act_t, s->act_x, s->act_x, nullptr, 1, count_ptr, count_max);
-            done++;
+        for (int b = 0; b < s->blocks; b++) {
+            if (more()) {
+                launch_conv(h, s->tower[2 * b], s->act_x, nullptr, s->act_t, nullptr, 1, count_ptr, count_max);
+                done++;
+            }
+            if (more()) {
+                launch_conv(h, s->tower[2 * b + 1], s->act_t, s->act_x, s->act_x, nullptr, 1, count_ptr, count_max);
+                done++;
+            }
         }
+        h->launches += 1 + done;
+        return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
     }
-    h->launches += 1 + done;
-    if (limit >= 0) return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
     {
-        ProfScope ps(h, TZ_PROF_CONV_POLICY);
-        launch_conv(h, s->policy, s->act_x, nullptr, nullptr, s->logits_full, 0, count_ptr, count_max);
+        // input, tower and policy convolutions are one launch, so the sampled profile books all of it here
+        ProfScope ps(h, TZ_PROF_CONV_TOWER);
+        h->launches += 1 + launch_network(h, count_ptr, count_max);
     }
     if (s->simhash_set)
         k_simhash<<<wblocks, 32 * WPB, 0, h->stream>>>(states, count_ptr, count_max, d.n, d.half_komi, s->simhash_matrix,
@@ -667,7 +748,7 @@ int nn_forward(tz_handle* h, const TzState* states, const int* count_ptr, int co
             actions, n_actions, count_ptr, count_max, d.n, d.M, conv::HALO, s->simhash_set, s->simhash_idx, logits, value,
             variance, s->f16);
     }
-    h->launches += 2;
+    h->launches += 1;
     return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
 }
 
@@ -710,6 +791,17 @@ int nn_debug_read(tz_handle* h, int which, int count, float* out_dev) {
 // `count` positions with CUDA events; returns the mean milliseconds per convolution launch.  The block
 // stream X is only read (the second convolution writes to a scratch buffer), so the data stay whatever
 // the last tz_evaluate left there -- realistic activations, which matters under the power cap.
+// TZ_EXP_GAP_US (environment, tuning experiment): idle this many microseconds between the timed launches, to see
+// whether the power-capped tensor clock absorbs idle gaps (it does: see profiles/r1_conv_timing.txt)
+__global__ void k_idle(long long ns) {
+    long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        __nanosleep(1000);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    } while (t - t0 < ns);
+}
+
 int nn_time_tower(tz_handle* h, int count, int reps, double* ms_per_conv) {
     NnState* s = h->nn;
     if (!s) return TZ_ENOWEIGHTS;
@@ -726,10 +818,14 @@ int nn_time_tower(tz_handle* h, int count, int reps, double* ms_per_conv) {
         launch_conv(h, s->tower[0], s->act_x, nullptr, s->act_t, nullptr, 1, nullptr, count);
         launch_conv(h, s->tower[1], s->act_t, s->act_x, s->act_scratch, nullptr, 1, nullptr, count);
     }
+    const char* gap_env = getenv("TZ_EXP_GAP_US");
+    const long long gap_ns = gap_env ? 1000ll * atoll(gap_env) : 0;
     cudaEventRecord(a, h->stream);
     for (int i = 0; i < reps; i++) {
         launch_conv(h, s->tower[0], s->act_x, nullptr, s->act_t, nullptr, 1, nullptr, count);
+        if (gap_ns) k_idle<<<1, 1, 0, h->stream>>>(gap_ns);
         launch_conv(h, s->tower[1], s->act_t, s->act_x, s->act_scratch, nullptr, 1, nullptr, count);
+        if (gap_ns) k_idle<<<1, 1, 0, h->stream>>>(gap_ns);
     }
     cudaEventRecord(b, h->stream);
     cudaEventSynchronize(b);
