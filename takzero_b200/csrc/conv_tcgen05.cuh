@@ -39,6 +39,13 @@
 // crosses to the async proxy with fence.proxy.async before its bulk copies.  The same three waits also cover the
 // write-after-read hazards of the two ping-pong activation buffers (a layer's output buffer is the input buffer
 // of the layer before it).  The launch is cooperative: every pair must be resident, or the spin would deadlock.
+// Chunks: the positions of a launch are cut into equal chunks of at least Params::chunk_min_tiles pair tiles and the items are numbered
+// chunk-major, so a chunk runs through ALL its layers before the next one starts.  Activations live in two small
+// ping-pong sets (even / odd chunks) that stay resident in the 126 MB L2 -- the layer-to-layer traffic never
+// reaches HBM, which under the power cap is worth ~7 % of throughput.  Only the input planes, the policy logits
+// and the two head features per row (the value / UBE 1x1 convolutions, folded into the last tower layer's
+// epilogue) use global rows.  A chunk's first layer waits until the chunk two before it has completely finished
+// (chunk_done), because it overwrites that chunk's activation set.
 // TZ_DEBUG_TIMING is a compile-time tuning experiment (tools/build_variant.sh); the numbers it produced for
 // the earlier row-major one-CTA / pair kernels are in profiles/r1_conv_timing.txt.
 #pragma once
@@ -77,17 +84,24 @@ struct Layer {
     const __nv_bfloat16* in;        // [cin/8][rows][8] activations
     const __nv_bfloat16* w;         // [cin/64][9 taps][2 halves][8][128][8] pre-arranged weight blocks
     const float* bias;              // [256]
-    const __nv_bfloat16* residual;  // [32][rows][8] or null
-    __nv_bfloat16* out_act;         // [32][rows][8] or null
-    float* out_f32;                 // [64][f32_rows][4] (policy logits, no guard rows) or null
+    const __nv_bfloat16* residual;  // [32][rows_set][8] or null
+    __nv_bfloat16* out_act;         // [32][rows_set][8] or null
+    float* out_f32;                 // [64][f32_rows][4] (policy logits, global rows without guard) or null
+    const float* head_w;            // [2][256] value / UBE 1x1 convolution weights, or null
+    float* head_out;                // [f32_rows][2]: the two head dot products of every (global) row
     int cin;                        // channels of `in` (multiple of 64)
     int relu;
+    int in_global;                  // 1: `in` holds all positions (input planes, rows_global per plane);
+                                    // 0: `in` is the chunk's activation set like residual / out_act
 };
 
 struct Params {
     Layer layers[MAX_LAYERS];       // run back to back; layer l reads what layer l-1 wrote
     int n_layers;
-    long long rows;                 // rows per chunk plane of in / residual / out_act (incl. guard + halo)
+    long long rows_global;          // rows per chunk plane of a buffer holding all positions (incl. guard + halo)
+    long long rows_set;             // rows per chunk plane of one activation set
+    long long set_stride;           // elements between activation set 0 (even chunks) and set 1 (odd chunks)
+    int chunk_min_tiles;            // least pair tiles (256 rows) per chunk; huge: the whole launch is one chunk
     long long f32_rows;
     const int* count_ptr;           // number of positions (device), or null: use count_max
     int count_max;
@@ -95,8 +109,49 @@ struct Params {
     int guard;                      // leading guard rows of the activation planes (= HALO)
     const uint4* masks;             // [n*n][9] disable-output-lane masks by (first tile row) mod n*n
     int f16;                        // 16-bit storage / operand type: 0 = bf16, 1 = IEEE fp16 (same UMMA kind::f16)
-    unsigned* progress;             // [pair tiles], zeroed before the launch: epilogue-warp arrivals per tile
-                                    // (8 per finished layer); may be null when n_layers == 1
+    unsigned* progress;             // [chunks][pair tiles per chunk], zeroed before the launch: epilogue-warp
+                                    // arrivals per tile (8 per finished layer); may be null when n_layers == 1
+    unsigned* chunk_done;           // [chunks]: epilogue-warp arrivals of the last layer (8 per tile)
+};
+
+// work item -> (chunk, layer, pair tile); every role of the kernel walks the same sequence
+struct Item {
+    int chunk, layer, pt;
+    int tiles;   // pair tiles of this chunk
+    int rows;    // valid rows of this chunk
+};
+struct Schedule {
+    int chunk_rows;   // rows of a full chunk
+    int chunk_tiles;  // pair tiles of a full chunk
+    int rows_used;    // rows of the launch
+    int n_layers;
+    int items;
+    __device__ __forceinline__ void init(int count, int nn, int chunk_min_tiles, int layers) {
+        rows_used = count * nn;
+        // balanced chunks of at least chunk_min_tiles pair tiles (fewer than about two tiles per CTA pair and the
+        // pairs stall on each other's progress; a sliver of a last chunk would walk through the layers alone)
+        const int c1 = count > 0 ? count : 1;
+        const int all_tiles = (rows_used + 2 * TILE_M - 1) / (2 * TILE_M);
+        const int n_chunks = all_tiles >= 2 * chunk_min_tiles ? all_tiles / chunk_min_tiles : 1;
+        const int cp = (c1 + n_chunks - 1) / n_chunks;
+        chunk_rows = cp * nn;
+        chunk_tiles = (chunk_rows + 2 * TILE_M - 1) / (2 * TILE_M);
+        n_layers = layers;
+        const int full = rows_used / chunk_rows, rest = rows_used - full * chunk_rows;
+        items = (full * chunk_tiles + (rest + 2 * TILE_M - 1) / (2 * TILE_M)) * layers;
+    }
+    __device__ __forceinline__ Item at(int item) const {
+        Item it;
+        const int per_chunk = chunk_tiles * n_layers;
+        it.chunk = item / per_chunk;
+        const int r = item - it.chunk * per_chunk;
+        const int left = rows_used - it.chunk * chunk_rows;
+        it.rows = left < chunk_rows ? left : chunk_rows;
+        it.tiles = (it.rows + 2 * TILE_M - 1) / (2 * TILE_M);
+        it.layer = r / it.tiles;
+        it.pt = r - it.layer * it.tiles;
+        return it;
+    }
 };
 
 #ifdef TZ_DEBUG_TIMING
@@ -264,9 +319,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
 
     const int count = p.count_ptr ? *p.count_ptr : p.count_max;
     const int nn = p.n * p.n;
-    const int rows_used = count * nn;
-    const int pair_tiles = (rows_used + 2 * TILE_M - 1) / (2 * TILE_M);
-    const int items = pair_tiles * p.n_layers;  // item i = (layer i / pair_tiles, pair tile i % pair_tiles)
+    Schedule sched;
+    sched.init(count, nn, p.chunk_min_tiles, p.n_layers);
+    const int items = sched.items;
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
     if (threadIdx.x == 0) {
@@ -306,21 +361,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
         if (lane == 0) {
             int stage = 0, phase = 0;
             for (int item = pair; item < items; item += npairs) {
-                const int layer = item / pair_tiles, pt = item - layer * pair_tiles;
+                const Item it = sched.at(item);
+                const int layer = it.layer, pt = it.pt;
                 const Layer& L = p.layers[layer];
                 if (layer > 0) {
                     // rows [t*128 - HALO, t*128 + 128 + HALO) of the previous layer's output: CTA tiles t-1, t, t+1,
                     // i.e. pair tiles {pt-1, pt} for rank 0 and {pt, pt+1} for rank 1
                     const unsigned need = 8u * (unsigned)layer;
+                    const unsigned* prog = p.progress + (size_t)it.chunk * sched.chunk_tiles;
                     const int lo = pt - 1 + (int)rank;
                     for (int q = lo; q <= lo + 1; q++)
-                        if (q >= 0 && q < pair_tiles)
-                            while (ld_acquire_gpu(p.progress + q) < need) __nanosleep(40);
+                        if (q >= 0 && q < it.tiles)
+                            while (ld_acquire_gpu(prog + q) < need) __nanosleep(40);
                     fence_proxy_async();
+                } else if (it.chunk >= 2 && p.n_layers > 1) {
+                    // this chunk's first layer overwrites the activation set of chunk - 2: all of it must be done
+                    const unsigned need = 8u * (unsigned)sched.chunk_tiles;
+                    while (ld_acquire_gpu(p.chunk_done + it.chunk - 2) < need) __nanosleep(40);
                 }
                 const int t = pt * 2 + (int)rank;
+                const size_t in_rows = L.in_global ? (size_t)p.rows_global : (size_t)p.rows_set;
+                const size_t in_first = L.in_global ? (size_t)it.chunk * sched.chunk_rows : 0;  // row of the chunk
+                const __nv_bfloat16* in_base = L.in_global ? L.in : L.in + (size_t)(it.chunk & 1) * p.set_stride;
                 const uint8_t* src_tile =
-                    reinterpret_cast<const uint8_t*>(L.in) + (size_t)(p.guard + t * TILE_M - HALO) * 16;
+                    reinterpret_cast<const uint8_t*>(in_base) + (in_first + (size_t)(p.guard + t * TILE_M - HALO)) * 16;
                 const int kblocks = L.cin >> 6;
                 for (int kb = 0; kb < kblocks; kb++) {
                     mbar_wait(a_empty + 8 * stage, phase ^ 1);
@@ -328,7 +392,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                     const uint32_t dst = smem_u32(a_smem + stage * A_STAGE_BYTES);
 #pragma unroll
                     for (int kc = 0; kc < 8; kc++)
-                        bulk_g2s(dst + kc * A_KC_BYTES, src_tile + (size_t)(kb * 8 + kc) * (size_t)p.rows * 16, A_KC_BYTES,
+                        bulk_g2s(dst + kc * A_KC_BYTES, src_tile + (size_t)(kb * 8 + kc) * in_rows * 16, A_KC_BYTES,
                                  a_sig + 8 * stage);
                     if (++stage == A_STAGES) {
                         stage = 0;
@@ -342,7 +406,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
         if (lane == 0) {
             int stage = 0, phase = 0;
             for (int item = pair; item < items; item += npairs) {
-                const Layer& L = p.layers[item / pair_tiles];
+                const Layer& L = p.layers[sched.at(item).layer];
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(L.w) + (size_t)rank * B_STAGE_BYTES;
                 const int blocks = (L.cin >> 6) * 9;
                 for (int blk = 0; blk < blocks; blk++) {
@@ -370,7 +434,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
             int stage = 0, phase = 0;
             const uint32_t b_full_leader = map_to_rank(b_full, 0);
             for (int item = pair; item < items; item += npairs) {
-                const int blocks = (p.layers[item / pair_tiles].cin >> 6) * 9;
+                const int blocks = (p.layers[sched.at(item).layer].cin >> 6) * 9;
                 for (int blk = 0; blk < blocks; blk++) {
                     mbar_wait(b_land + 8 * stage, phase);
                     mbar_arrive_cluster(b_full_leader + 8 * stage);
@@ -388,7 +452,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                 int stage = 0, phase = 0;
                 const uint32_t a_full_leader = map_to_rank(a_full, 0);
                 for (int item = pair; item < items; item += npairs) {
-                    const int kblocks = p.layers[item / pair_tiles].cin >> 6;
+                    const int kblocks = p.layers[sched.at(item).layer].cin >> 6;
                     for (int kb = 0; kb < kblocks; kb++) {
                         mbar_wait(a_land + 8 * stage, phase);
                         mbar_arrive_cluster(a_full_leader + 8 * stage);
@@ -415,8 +479,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
             const long long mma_start = clock64();
 #endif
             for (int item = pair; item < items; item += npairs, it++) {
-                const int layer = item / pair_tiles, pt = item - layer * pair_tiles;
-                const int kblocks = p.layers[layer].cin >> 6;
+                const Item wi = sched.at(item);
+                const int pt = wi.pt;
+                const int kblocks = p.layers[wi.layer].cin >> 6;
                 const int acc = it & 1;
                 TWAIT(w_t, mbar_wait(t_empty + 8 * acc, ((it >> 1) & 1) ^ 1));
                 tc_fence_after();
@@ -468,11 +533,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
         // ---- epilogue (both CTAs): own 128 rows from own TMEM; t_empty lives in the leader
         const int wq = warp & 3;
         const uint32_t t_empty_leader = map_to_rank(t_empty, 0);
-        const size_t plane = (size_t)p.rows * 8;  // elements per chunk plane
-        float* bias_w = s_bias + wq * N_OUT;      // this warp's copy of the current layer's bias
+        const size_t plane = (size_t)p.rows_set * 8;  // elements per chunk plane of an activation set
+        float* bias_w = s_bias + wq * N_OUT;          // this warp's copy of the current layer's bias
         int it = 0, bias_layer = -1;
         for (int item = pair; item < items; item += npairs, it++) {
-            const int layer = item / pair_tiles, pt = item - layer * pair_tiles;
+            const Item wi = sched.at(item);
+            const int layer = wi.layer, pt = wi.pt;
             const Layer& L = p.layers[layer];
             if (layer != bias_layer) {
                 __syncwarp();
@@ -481,22 +547,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                 __syncwarp();
                 bias_layer = layer;
             }
-            const __nv_bfloat16* residual = L.residual;
-            __nv_bfloat16* out_act = L.out_act;
+            const size_t set_off = (size_t)(wi.chunk & 1) * p.set_stride;
+            const __nv_bfloat16* residual = L.residual ? L.residual + set_off : nullptr;
+            __nv_bfloat16* out_act = L.out_act ? L.out_act + set_off : nullptr;
             float* out_f32 = L.out_f32;
+            const float* head_w = L.head_w;
             const int relu = L.relu;
             const int acc = it & 1;
             const int t = pt * 2 + (int)rank;
-            const int rel = t * TILE_M + wq * 32 + lane;  // row = position * n*n + square
-            const bool valid = rel < rows_used;
+            const int rel = t * TILE_M + wq * 32 + lane;  // row of the chunk = position * n*n + square
+            const bool valid = rel < wi.rows;
             const size_t grow = (size_t)(p.guard + rel) * 8;  // element offset of the row inside a plane
+            const size_t grel = (size_t)wi.chunk * sched.chunk_rows + (size_t)rel;  // row among all positions
+            float head_v = 0.0f, head_u = 0.0f;
             mbar_wait(t_full + 8 * acc, (it >> 1) & 1);
             tc_fence_after();
             // Inside a fused launch the residual rows were written by another SM two layers ago.  One gpu-scope
             // acquire per tile (on the counter that writer released) makes the plain loads below see them: it costs
             // an L1 invalidate per warp and tile, whereas L2-only (ld.cg) loads made the epilogue 1.8x slower
             // than the MMAs of a tile.
-            if (residual != nullptr && layer >= 2) (void)ld_acquire_gpu(p.progress + pt);
+            if (residual != nullptr && layer >= 2)
+                (void)ld_acquire_gpu(p.progress + (size_t)wi.chunk * sched.chunk_tiles + pt);
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * N_OUT;
 #pragma unroll 1
             for (int c0 = 0; c0 < N_OUT; c0 += 32) {
@@ -534,17 +605,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                     if (out_f32) {
 #pragma unroll
                         for (int j = 0; j < 8; j++)
-                            *reinterpret_cast<float4*>(out_f32 + ((size_t)(c0 / 4 + j) * (size_t)p.f32_rows + (size_t)rel) * 4) =
+                            *reinterpret_cast<float4*>(out_f32 + ((size_t)(c0 / 4 + j) * (size_t)p.f32_rows + grel) * 4) =
                                 make_float4(f[j * 4], f[j * 4 + 1], f[j * 4 + 2], f[j * 4 + 3]);
+                    }
+                    if (head_w) {  // value / UBE 1x1 convolutions over the tower output (net6_simhash.rs:88-119)
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            head_v = fmaf(f[j], __ldg(head_w + c0 + j), head_v);
+                            head_u = fmaf(f[j], __ldg(head_w + N_OUT + c0 + j), head_u);
+                        }
                     }
                 }
             }
+            if (head_w && valid) *reinterpret_cast<float2*>(L.head_out + grel * 2) = make_float2(head_v, head_u);
             if (p.n_layers > 1) __threadfence();  // this thread's rows are visible device-wide before the tile is published
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive_cluster(t_empty_leader + 8 * acc);
-                if (p.n_layers > 1) red_release_gpu_add(p.progress + pt, 1u);
+                if (p.n_layers > 1) {
+                    red_release_gpu_add(p.progress + (size_t)wi.chunk * sched.chunk_tiles + pt, 1u);
+                    if (layer == p.n_layers - 1) red_release_gpu_add(p.chunk_done + wi.chunk, 1u);
+                }
             }
         }
     }

@@ -32,22 +32,29 @@ struct NnState {
     int n = 0, blocks = 0;
     int in_channels = 0, out_channels = 0;
     int max_positions = 0;
-    size_t rows = 0;  // rows of the activation buffers
+    size_t rows = 0;      // rows per chunk plane of the buffers that hold all positions (planes)
+    size_t rows_set = 0;  // rows per chunk plane of one activation set (one chunk of positions)
+    int chunk_min_tiles = 0;   // least pair tiles the network runs through all layers at a time (conv_tcgen05.cuh)
+    int chunk_positions = 0;   // most positions of one chunk = what one activation set holds
+    int chunk_tiles = 0, max_chunks = 0;  // bounds: pair tiles of one chunk, chunks of one launch
     ConvLayer input, policy;
     std::vector<ConvLayer> tower;  // 2 per residual block
     float* head_w = nullptr;       // [2][256] conv1x1 weights (value, ube)
     float* head_misc = nullptr;    // [2] conv bias, [2][36] linear weights, [2] linear bias
     // chunk-planar activations (conv_tcgen05.cuh): [channels / 8][rows][8]
     __nv_bfloat16* planes = nullptr;  // [8][rows][8]   input planes, 64 channels (C real ones)
-    __nv_bfloat16* act_x = nullptr;   // [32][rows][8]  residual stream
-    __nv_bfloat16* act_t = nullptr;   // [32][rows][8]  middle of a residual block
-    __nv_bfloat16* act_scratch = nullptr;  // tuning hook only
+    __nv_bfloat16* act_x = nullptr;   // [2 sets][32][rows_set][8]  residual stream (even / odd chunks)
+    __nv_bfloat16* act_t = nullptr;   // [2 sets][32][rows_set][8]  middle of a residual block
+    __nv_bfloat16* tune_buf[3] = {nullptr, nullptr, nullptr};  // tuning hook only: [32][rows][8] each
+    float* head_feat = nullptr;       // [max_positions * n*n][2] value / UBE 1x1 convolution outputs per row
     float* logits_full = nullptr;     // [64][max_positions * n*n][4] policy logits, 4-channel planes
     uint4* masks = nullptr;           // [n*n][9] disable-output-lane masks (conv_tcgen05.cuh)
     float* simhash_matrix = nullptr;  // [C*N*N][32] (net6_simhash.rs:136-139), optional
     uint32_t* simhash_set = nullptr;  // 2^32-bit set (bitvec.bin), optional; absent = empty set
     uint32_t* simhash_idx = nullptr;  // [max_positions] hash index of each queued position
-    unsigned* progress = nullptr;     // [pair tiles] tile-completion counters of the fused tower launch
+    size_t progress_len = 0;
+    unsigned* progress = nullptr;     // [chunks][pair tiles] tile-completion counters of the fused launch, then
+                                      // [chunks] chunk-completion counters
     int max_pairs = 74;               // CTA pairs that can be resident at once (cooperative launch bound)
     int fused = 1;                    // 1: the tower is one multi-layer launch; 0 (TZ_TOWER=layers): one launch per layer
     int layer_limit = -1;             // debug: stop the tower after this many convolutions
@@ -195,17 +202,12 @@ __device__ __forceinline__ int move_channel(int n, uint16_t m) {
 // One warp per position: value head (conv1x1 + ReLU + Linear + tanh), UBE head (same, no tanh),
 // uncertainty = clamp(max(exp(ube), local), 0, 4) with local = 4.0 (empty SimHash set, i.e. a
 // freshly initialised reference network), and logits[i] = policy[move_index(action_i)].
-__global__ void __launch_bounds__(32 * WPB) k_heads_gather(const __nv_bfloat16* act, long long rows,
-                                                            const float* logits_full, long long f32_rows,
-                                                            const float* head_w, const float* head_misc,
+__global__ void __launch_bounds__(32 * WPB) k_heads_gather(const float* head_feat, const float* logits_full,
+                                                            long long f32_rows, const float* head_misc,
                                                             const uint16_t* actions, const int* n_actions,
-                                                            const int* count_ptr, int count_max, int n, int M, int guard,
+                                                            const int* count_ptr, int count_max, int n, int M,
                                                             const uint32_t* simhash_set, const uint32_t* simhash_idx,
-                                                            float* out_logits, float* out_value, float* out_variance,
-                                                            int f16) {
-    __shared__ float s_w[2 * FILTERS];
-    for (int i = threadIdx.x; i < 2 * FILTERS; i += blockDim.x) s_w[i] = head_w[i];
-    __syncthreads();
+                                                            float* out_logits, float* out_value, float* out_variance) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * WPB + warp;
     const int count = count_ptr ? *count_ptr : count_max;
@@ -214,27 +216,13 @@ __global__ void __launch_bounds__(32 * WPB) k_heads_gather(const __nv_bfloat16* 
     const float bv = head_misc[0], bu = head_misc[1];
     const float* lin_v = head_misc + 2;
     const float* lin_u = head_misc + 2 + 36;
-    // lane = square (two passes for N = 6): the 1x1 convolutions are per-square dot products over the 256
-    // channels; consecutive lanes read consecutive 16-byte pieces of every chunk plane
+    // lane = square (two passes for N = 6); the 1x1 convolutions (per-square dot products over the 256 channels)
+    // were computed by the epilogue of the last tower convolution: head_feat[row] = {value, ube} features
     float acc_v = 0.0f, acc_u = 0.0f;
     for (int sq = lane; sq < nn; sq += 32) {
-        const size_t r = (size_t)guard + (size_t)q * nn + sq;
-        float dv = 0.0f, du = 0.0f;
-#pragma unroll 4
-        for (int kc = 0; kc < FILTERS / 8; kc++) {
-            const uint4 x = *reinterpret_cast<const uint4*>(act + ((size_t)kc * (size_t)rows + r) * 8);
-            const uint32_t w[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const float2 xy = conv::unpack16(w[e], f16);
-                const float lo = xy.x, hi = xy.y;
-                const int c = kc * 8 + e * 2;
-                dv += lo * s_w[c] + hi * s_w[c + 1];
-                du += lo * s_w[FILTERS + c] + hi * s_w[FILTERS + c + 1];
-            }
-        }
-        acc_v += fmaxf(dv + bv, 0.0f) * lin_v[sq];
-        acc_u += fmaxf(du + bu, 0.0f) * lin_u[sq];
+        const float2 d = *reinterpret_cast<const float2*>(head_feat + ((size_t)q * nn + sq) * 2);
+        acc_v += fmaxf(d.x + bv, 0.0f) * lin_v[sq];
+        acc_u += fmaxf(d.y + bu, 0.0f) * lin_u[sq];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -535,7 +523,30 @@ int nn_set_weights(tz_handle* h, const char* const* names, const float* const* d
         s->allocs.push_back(*p);
         return cudaMemset(*p, 0, bytes) == cudaSuccess;
     };
-    const bool reuse = old.p && old.p->n == n && old.p->max_positions == h->d.Q && old.p->rows == s->rows;
+    {
+        // chunking: at least TZ_NN_CHUNK_TILES pair tiles (256 rows each) per chunk, default 150 = two per CTA
+        // pair (measured plateau 144..192 on 8192 6x6 positions); 0 or the per-layer mode = one chunk
+        // (a chain longer than MAX_LAYERS is cut into several launches and cannot keep chunks apart)
+        const char* mode = getenv("TZ_TOWER");
+        s->fused = !(mode && strcmp(mode, "layers") == 0);
+        const char* ct = getenv("TZ_NN_CHUNK_TILES");
+        const int tiles = ct ? atoi(ct) : 150;
+        const int all_tiles = (int)((used + 2 * conv::TILE_M - 1) / (2 * conv::TILE_M));
+        if (!s->fused || tiles <= 0 || all_tiles < 2 * tiles || 2 * s->blocks + 2 > conv::MAX_LAYERS) {
+            s->chunk_min_tiles = 1 << 28;
+            s->chunk_tiles = all_tiles > 0 ? all_tiles : 1;
+            s->max_chunks = 1;
+            s->chunk_positions = s->max_positions;
+        } else {
+            s->chunk_min_tiles = tiles;
+            s->chunk_tiles = 2 * tiles + 2;  // a chunk has fewer than 2 * tiles tiles (+ rounding)
+            s->max_chunks = all_tiles / tiles;
+            s->chunk_positions = (s->chunk_tiles - 1) * 2 * conv::TILE_M / nn;
+        }
+        s->rows_set = conv::HALO + (size_t)s->chunk_tiles * (2 * conv::TILE_M) + 2 * conv::HALO;
+    }
+    const bool reuse = old.p && old.p->n == n && old.p->max_positions == h->d.Q && old.p->rows == s->rows &&
+                       old.p->rows_set == s->rows_set && old.p->max_chunks == s->max_chunks;
     if (reuse) {
         auto steal = [&](auto*& dst, auto* src) {
             dst = static_cast<std::remove_reference_t<decltype(dst)>>(old.take(src));
@@ -544,17 +555,19 @@ int nn_set_weights(tz_handle* h, const char* const* names, const float* const* d
         steal(s->planes, old.p->planes);
         steal(s->act_x, old.p->act_x);
         steal(s->act_t, old.p->act_t);
-        steal(s->act_scratch, old.p->act_scratch);
+        steal(s->head_feat, old.p->head_feat);
+        for (int i = 0; i < 3; i++) steal(s->tune_buf[i], old.p->tune_buf[i]);
         steal(s->logits_full, old.p->logits_full);
         steal(s->masks, old.p->masks);
         steal(s->simhash_matrix, old.p->simhash_matrix);
         steal(s->simhash_set, old.p->simhash_set);
         steal(s->simhash_idx, old.p->simhash_idx);
     }
-    if (!reuse || !s->planes || !s->act_x || !s->act_t || !s->logits_full)
+    if (!reuse || !s->planes || !s->act_x || !s->act_t || !s->logits_full || !s->head_feat)
     {
-        if (!dalloc((void**)&s->planes, s->rows * CIN_PAD * 2) || !dalloc((void**)&s->act_x, s->rows * FILTERS * 2) ||
-            !dalloc((void**)&s->act_t, s->rows * FILTERS * 2) ||
+        if (!dalloc((void**)&s->planes, s->rows * CIN_PAD * 2) || !dalloc((void**)&s->act_x, 2 * s->rows_set * FILTERS * 2) ||
+            !dalloc((void**)&s->act_t, 2 * s->rows_set * FILTERS * 2) ||
+            !dalloc((void**)&s->head_feat, (size_t)s->max_positions * nn * 2 * sizeof(float)) ||
             !dalloc((void**)&s->logits_full, (size_t)s->max_positions * nn * FILTERS * 4)) {
             nn_free(h);
             NN_FAIL(TZ_ENOMEM, "cudaMalloc activations");
@@ -596,9 +609,8 @@ int nn_set_weights(tz_handle* h, const char* const* names, const float* const* d
             s->max_pairs = clusters < s->sm_count / 2 ? clusters : s->sm_count / 2;
         else
             s->max_pairs = s->sm_count / 2;
-        const char* mode = getenv("TZ_TOWER");
-        s->fused = !(mode && strcmp(mode, "layers") == 0);
-        const size_t tiles = (s->rows + 2 * conv::TILE_M - 1) / (2 * conv::TILE_M) + 1;
+        const size_t tiles = (size_t)s->max_chunks * s->chunk_tiles + s->max_chunks + 16;
+        s->progress_len = tiles;
         if (reuse) {
             s->progress = static_cast<unsigned*>(old.take(old.p->progress));
             if (s->progress) s->allocs.push_back(s->progress);
@@ -627,27 +639,40 @@ static conv::Layer conv_layer(const ConvLayer& L, const __nv_bfloat16* in, const
     l.residual = residual;
     l.out_act = out_act;
     l.out_f32 = out_f32;
+    l.head_w = nullptr;
+    l.head_out = nullptr;
     l.cin = L.cin;
     l.relu = relu;
+    l.in_global = 0;
     return l;
 }
 
-// Launches p.layers[0..n_layers) as ONE persistent kernel.  With more than one layer the CTA pairs synchronise
-// through s->progress inside the kernel, so the launch is cooperative (all pairs resident, or it fails loudly).
-static cudaError_t launch_layers(tz_handle* h, conv::Params& p, const int* count_ptr, int count_max) {
+// Launches p.layers[0..n_layers) as ONE persistent kernel over activation sets of `rows_set` rows holding
+// one chunk (at least `chunk_min_tiles` pair tiles) each.  With more than one layer the CTA pairs synchronise through s->progress
+// inside the kernel, so the launch is cooperative (all pairs resident, or it fails loudly).
+static cudaError_t launch_layers(tz_handle* h, conv::Params& p, const int* count_ptr, int count_max, size_t rows_set,
+                                 int chunk_min_tiles) {
     const NnState* s = h->nn;
-    p.rows = (long long)s->rows;
-    p.f32_rows = (long long)s->max_positions * s->n * s->n;
+    const int nn = s->n * s->n;
+    p.rows_global = (long long)s->rows;
+    p.rows_set = (long long)rows_set;
+    p.set_stride = (long long)rows_set * FILTERS;
+    p.chunk_min_tiles = chunk_min_tiles;
+    p.f32_rows = (long long)s->max_positions * nn;
     p.count_ptr = count_ptr;
     p.count_max = count_max;
     p.n = s->n;
     p.guard = conv::HALO;
     p.masks = s->masks;
     p.f16 = s->f16;
+    // upper bounds of what the kernel derives from the device-side count (conv::Schedule::init)
+    const int all_tiles = (count_max * nn + 2 * conv::TILE_M - 1) / (2 * conv::TILE_M);
+    const int chunks = all_tiles >= 2 * chunk_min_tiles ? all_tiles / chunk_min_tiles : 1;
+    const int chunk_tiles = chunks > 1 ? 2 * chunk_min_tiles + 2 : (all_tiles > 0 ? all_tiles : 1);
+    const size_t counters = (size_t)chunks * chunk_tiles + chunks;
     p.progress = s->progress;
-    const int max_tiles = (count_max * s->n * s->n + conv::TILE_M - 1) / conv::TILE_M;
-    const int pair_tiles = (max_tiles + 1) / 2;
-    const long long items = (long long)pair_tiles * p.n_layers;
+    p.chunk_done = s->progress + (size_t)chunks * chunk_tiles;
+    const long long items = (long long)all_tiles * p.n_layers;
     const int pairs = items < s->max_pairs ? (items > 0 ? (int)items : 1) : s->max_pairs;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs);
@@ -656,7 +681,9 @@ static cudaError_t launch_layers(tz_handle* h, conv::Params& p, const int* count
     cfg.stream = h->stream;
     cudaLaunchAttribute attr[1];
     if (p.n_layers > 1) {
-        cudaError_t e = cudaMemsetAsync(s->progress, 0, (size_t)(pair_tiles > 0 ? pair_tiles : 1) * sizeof(unsigned), h->stream);
+        if (counters > s->progress_len || (chunks > 1 && (size_t)chunk_tiles * 2 * conv::TILE_M + 3 * conv::HALO > rows_set))
+            return cudaErrorInvalidValue;
+        cudaError_t e = cudaMemsetAsync(s->progress, 0, counters * sizeof(unsigned), h->stream);
         if (e != cudaSuccess) return e;
         attr[0].id = cudaLaunchAttributeCooperative;
         attr[0].val.cooperative = 1;
@@ -666,24 +693,30 @@ static cudaError_t launch_layers(tz_handle* h, conv::Params& p, const int* count
     return cudaLaunchKernelEx(&cfg, conv::k_conv3x3_pair, p);
 }
 
-static void launch_conv(tz_handle* h, const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* residual,
-                        __nv_bfloat16* out_act, float* out_f32, int relu, const int* count_ptr, int count_max) {
+// one convolution over `count_max` positions that all sit in ONE activation set of `rows_set` rows
+static void launch_conv(tz_handle* h, const conv::Layer& layer, const int* count_ptr, int count_max, size_t rows_set) {
     conv::Params p;
-    p.layers[0] = conv_layer(L, in, residual, out_act, out_f32, relu);
+    p.layers[0] = layer;
     p.n_layers = 1;
-    launch_layers(h, p, count_ptr, count_max);
+    launch_layers(h, p, count_ptr, count_max, rows_set, 1 << 28);
 }
 
-// The whole network body: input conv (planes -> x), residual blocks (conv(x) -> t, conv(t) + x -> x), policy conv
-// (x -> f32 logits).  Fused: all of it is one launch (chunks of conv::MAX_LAYERS); returns the number of launches.
-static int launch_network(tz_handle* h, const int* count_ptr, int count_max) {
+// The whole network body: input conv (planes -> x), residual blocks (conv(x) -> t, conv(t) + x -> x; the last one
+// also emits the value / UBE head features), policy conv (x -> f32 logits).  `upto` < 0: all of it; otherwise only
+// the first `upto` convolutions (debug hook).  Fused: one launch (chunks of conv::MAX_LAYERS layers), else one
+// launch per layer.  Returns the number of launches.
+static int launch_network(tz_handle* h, const int* count_ptr, int count_max, int upto) {
     NnState* s = h->nn;
     std::vector<conv::Layer> all;
     all.push_back(conv_layer(s->input, s->planes, nullptr, s->act_x, nullptr, 1));
+    all.back().in_global = 1;
     for (int l = 0; l < 2 * s->blocks; l++)
         all.push_back((l & 1) ? conv_layer(s->tower[l], s->act_t, s->act_x, s->act_x, nullptr, 1)
                               : conv_layer(s->tower[l], s->act_x, nullptr, s->act_t, nullptr, 1));
+    all.back().head_w = s->head_w;
+    all.back().head_out = s->head_feat;
     all.push_back(conv_layer(s->policy, s->act_x, nullptr, nullptr, s->logits_full, 0));
+    if (upto >= 0 && (size_t)upto < all.size()) all.resize((size_t)upto);
     int launches = 0;
     for (size_t first = 0; first < all.size();) {
         const size_t left = all.size() - first;
@@ -691,7 +724,9 @@ static int launch_network(tz_handle* h, const int* count_ptr, int count_max) {
         conv::Params p;
         for (size_t i = 0; i < chunk; i++) p.layers[i] = all[first + i];
         p.n_layers = (int)chunk;
-        launch_layers(h, p, count_ptr, count_max);
+        // a chain cut into several launches (more than MAX_LAYERS layers) cannot keep chunks in flight across the
+        // cut: it then runs with one chunk (full-size sets are required, see nn_set_weights)
+        launch_layers(h, p, count_ptr, count_max, s->rows_set, s->chunk_min_tiles);
         first += chunk;
         launches++;
     }
@@ -713,40 +748,23 @@ int nn_forward(tz_handle* h, const TzState* states, const int* count_ptr, int co
                                                       conv::HALO, (long long)s->rows, s->f16);
     }
     const int limit = s->layer_limit;
-    if (limit >= 0) {  // debug hook: the first `limit` convolutions, one launch each
-        int done = 0;
-        auto more = [&]() { return done < limit; };
-        if (more()) {
-            launch_conv(h, s->input, s->planes, nullptr, s->act_x, nullptr, 1, count_ptr, count_max);
-            done++;
-        }
-        for (int b = 0; b < s->blocks; b++) {
-            if (more()) {
-                launch_conv(h, s->tower[2 * b], s->act_x, nullptr, s->act_t, nullptr, 1, count_ptr, count_max);
-                done++;
-            }
-            if (more()) {
-                launch_conv(h, s->tower[2 * b + 1], s->act_t, s->act_x, s->act_x, nullptr, 1, count_ptr, count_max);
-                done++;
-            }
-        }
-        h->launches += 1 + done;
-        return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
-    }
+    // the debug read-back shows one chunk: refuse more positions than run as a single chunk
+    if (limit >= 0 && (count_max * d.n * d.n + 2 * conv::TILE_M - 1) / (2 * conv::TILE_M) >= 2LL * s->chunk_min_tiles)
+        return TZ_EINVAL;
     {
         // input, tower and policy convolutions are one launch, so the sampled profile books all of it here
         ProfScope ps(h, TZ_PROF_CONV_TOWER);
-        h->launches += 1 + launch_network(h, count_ptr, count_max);
+        h->launches += 1 + launch_network(h, count_ptr, count_max, limit);
     }
+    if (limit >= 0) return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
     if (s->simhash_set)
         k_simhash<<<wblocks, 32 * WPB, 0, h->stream>>>(states, count_ptr, count_max, d.n, d.half_komi, s->simhash_matrix,
                                                        s->simhash_idx);
     {
         ProfScope ps(h, TZ_PROF_HEADS);
         k_heads_gather<<<wblocks, 32 * WPB, 0, h->stream>>>(
-            s->act_x, (long long)s->rows, s->logits_full, (long long)s->max_positions * d.n * d.n, s->head_w, s->head_misc,
-            actions, n_actions, count_ptr, count_max, d.n, d.M, conv::HALO, s->simhash_set, s->simhash_idx, logits, value,
-            variance, s->f16);
+            s->head_feat, s->logits_full, (long long)s->max_positions * d.n * d.n, s->head_misc, actions, n_actions,
+            count_ptr, count_max, d.n, d.M, s->simhash_set, s->simhash_idx, logits, value, variance);
     }
     h->launches += 1;
     return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
@@ -781,9 +799,13 @@ int nn_debug_read(tz_handle* h, int which, int count, float* out_dev) {
     if (!s) return TZ_ENOWEIGHTS;
     const __nv_bfloat16* buf = which == 0 ? s->act_x : which == 1 ? s->act_t : s->planes;
     const int channels = which == 2 ? CIN_PAD : FILTERS;
+    // the activation sets hold one chunk
+    if (which != 2 && (count * s->n * s->n + 2 * conv::TILE_M - 1) / (2 * conv::TILE_M) >= 2LL * s->chunk_min_tiles)
+        return TZ_EINVAL;
+    const size_t rows = which == 2 ? s->rows : s->rows_set;
     const size_t total = (size_t)count * s->n * s->n * channels;
     k_unpad<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(buf, channels, count, s->n, conv::HALO,
-                                                                    (long long)s->rows, s->f16, out_dev);
+                                                                    (long long)rows, s->f16, out_dev);
     return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
 }
 
@@ -806,25 +828,35 @@ int nn_time_tower(tz_handle* h, int count, int reps, double* ms_per_conv) {
     NnState* s = h->nn;
     if (!s) return TZ_ENOWEIGHTS;
     if (count <= 0 || count > s->max_positions || reps <= 0) return TZ_EINVAL;
-    if (!s->act_scratch) {
-        if (cudaMalloc((void**)&s->act_scratch, s->rows * FILTERS * 2) != cudaSuccess) return TZ_ENOMEM;
-        s->allocs.push_back(s->act_scratch);
-        cudaMemset(s->act_scratch, 0, s->rows * FILTERS * 2);
-    }
+    // own full-size buffers (the network's activation sets hold one chunk): X is filled by the input convolution
+    // from whatever positions the last tz_evaluate encoded -- realistic activations, which matters under the
+    // power cap -- and only read afterwards
+    for (int i = 0; i < 3; i++)
+        if (!s->tune_buf[i]) {
+            if (cudaMalloc((void**)&s->tune_buf[i], s->rows * FILTERS * 2) != cudaSuccess) return TZ_ENOMEM;
+            s->allocs.push_back(s->tune_buf[i]);
+            cudaMemset(s->tune_buf[i], 0, s->rows * FILTERS * 2);
+        }
+    __nv_bfloat16 *x = s->tune_buf[0], *t = s->tune_buf[1], *scratch = s->tune_buf[2];
+    conv::Layer first = conv_layer(s->input, s->planes, nullptr, x, nullptr, 1);
+    first.in_global = 1;
+    launch_conv(h, first, nullptr, count, s->rows);
+    const conv::Layer c1 = conv_layer(s->tower[0], x, nullptr, t, nullptr, 1);
+    const conv::Layer c2 = conv_layer(s->tower[1], t, x, scratch, nullptr, 1);
     cudaEvent_t a, b;
     cudaEventCreate(&a);
     cudaEventCreate(&b);
     for (int i = 0; i < 2; i++) {
-        launch_conv(h, s->tower[0], s->act_x, nullptr, s->act_t, nullptr, 1, nullptr, count);
-        launch_conv(h, s->tower[1], s->act_t, s->act_x, s->act_scratch, nullptr, 1, nullptr, count);
+        launch_conv(h, c1, nullptr, count, s->rows);
+        launch_conv(h, c2, nullptr, count, s->rows);
     }
     const char* gap_env = getenv("TZ_EXP_GAP_US");
     const long long gap_ns = gap_env ? 1000ll * atoll(gap_env) : 0;
     cudaEventRecord(a, h->stream);
     for (int i = 0; i < reps; i++) {
-        launch_conv(h, s->tower[0], s->act_x, nullptr, s->act_t, nullptr, 1, nullptr, count);
+        launch_conv(h, c1, nullptr, count, s->rows);
         if (gap_ns) k_idle<<<1, 1, 0, h->stream>>>(gap_ns);
-        launch_conv(h, s->tower[1], s->act_t, s->act_x, s->act_scratch, nullptr, 1, nullptr, count);
+        launch_conv(h, c2, nullptr, count, s->rows);
         if (gap_ns) k_idle<<<1, 1, 0, h->stream>>>(gap_ns);
     }
     cudaEventRecord(b, h->stream);
