@@ -197,6 +197,41 @@ def test_simhash_indices_and_uncertainty():
     m.close()
 
 
+@pytest.mark.parametrize("n,hk,count", [(4, 4, 701), (6, 4, 333), (5, 4, 97)])
+def test_chunked_fused_launch_equals_one_chunk_and_per_layer_launches(n, hk, count, monkeypatch):
+    """The network body runs as one persistent launch whose positions are cut into chunks that walk through all
+    layers on small L2-resident activation sets (conv_tcgen05.cuh).  Chunk and tile placement must not change a
+    single bit: many small chunks (fewer tiles than CTA pairs, partial last tile), one chunk, and one launch per
+    layer give identical logits / values, and they agree with the f32 reference."""
+    ref = net_ref.Net(n, seed=3, blocks=3, randomize_bn=True)
+    games = sample_positions(n, hk, count, 77)
+    actions = [O.possible_moves(g) for g in games]
+    states = games_to_states(games)
+    outs = {}
+    for name, env in (("chunks", {"TZ_NN_CHUNK_TILES": "3"}), ("one", {"TZ_NN_CHUNK_TILES": "0"}),
+                      ("layers", {"TZ_TOWER": "layers"})):
+        for k in ("TZ_NN_CHUNK_TILES", "TZ_TOWER"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        m = capi.BatchedMCTS(n, hk, count, arena_slots=4096)
+        network.set_weights(m, ref.tensors())  # the mode is read when the weights are set
+        outs[name] = network.evaluate(m, states, actions)
+        for _ in range(4 if name == "chunks" else 0):  # the cross-CTA hand-offs are timing dependent: repeat
+            again = network.evaluate(m, states, actions)
+            assert all(np.array_equal(a, b) for a, b in zip(outs[name][0], again[0]))
+            assert np.array_equal(outs[name][1], again[1])
+        assert m.status() == 0
+        m.close()
+    for name in ("one", "layers"):
+        for a, b in zip(outs["chunks"][0], outs[name][0]):
+            assert np.array_equal(a, b), name
+        assert np.array_equal(outs["chunks"][1], outs[name][1]), name
+    want_logits, want_values, _ = ref.policy_value_uncertainty(games, actions)
+    assert max(float(np.abs(a - b).max()) for a, b in zip(outs["chunks"][0], want_logits)) <= TOL
+    assert float(np.abs(outs["chunks"][1] - want_values).max()) <= TOL
+
+
 def test_load_model_from_tch_archive_with_bitvec_sidecar(tmp_path):
     """Net::load (network/mod.rs:20-27, net6_simhash.rs:164-181) from the reference's own files: a tch-named
     `model_latest.ot` plus the `bitvec.bin` SimHash set beside it give exactly the outputs of tz_set_weights +
