@@ -15,7 +15,8 @@ NCCL broadcasts the weights once per generation and sums the counters.
 `value`  : simulations/s with everything resident in HBM (tz_selfplay_move, no host buffers).
 `e2e`    : the same loop through the host-buffer C ABI (injected Gumbel noise H2D from pinned memory,
            moves / improved-policy targets / terminals D2H every step).
-`roofline`: the tower convolution kernel (tcgen05), sampled with CUDA events inside the timed region.
+`roofline`: the convolution kernel (tcgen05; one fused launch per network pass), sampled with CUDA events inside
+           the timed region.
 `cpu_baseline`: the restated reference (oracle C search + libtorch-CPU f32 forward, 128 games in
            lock-step like selfplay/src/main.rs:37) on this box's host cores, bounded sample.
 """
@@ -169,7 +170,8 @@ def workload_config(n_gpus: int) -> dict:
         "sampled_actions": SAMPLED_ACTIONS, "search_budget": SEARCH_BUDGET,
         "weights": "random init, torch seed 123, BN mean 0 / var 1, empty SimHash set",
         "sharding": f"games sharded over {n_gpus} GPU(s), no data-path collective",
-        "l2": "working set (node arenas, activations) far larger than the 126 MB L2; no explicit flush",
+        "l2": "inputs of every lock-step (node arenas, states, input planes, 302 MB of logits) far larger than the "
+              "126 MB L2, no explicit flush; the network's chunk activation sets are L2-resident by design",
     }
 
 
@@ -281,7 +283,8 @@ def main():
         with open(ncu_path) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
     roofline = {
-        "kernel": "conv::k_conv3x3_pair (bf16 implicit GEMM, tcgen05 cta_group::2 / TMEM)", "bound": "tensor", "achieved": achieved,
+        "kernel": "conv::k_conv3x3_pair (bf16 implicit GEMM, tcgen05 cta_group::2 / TMEM; one fused launch = the 34 "
+                  "convolutions of a network pass)", "bound": "tensor", "achieved": achieved,
         "peak": peak, "peak_kind": peak_kind, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
         "traffic": traffic,
         "sampled": {"locksteps": int(prof.locksteps), "positions": int(prof.positions),
