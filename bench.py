@@ -134,7 +134,7 @@ def cpu_lockstep_rate(batched, agent, betas, min_seconds: float, min_locksteps: 
     return CPU_GAMES * done / dt, done, dt
 
 
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -151,7 +151,7 @@ def run_reference(args):
     value = CPU_GAMES * per_step * args.steps / dt
     sample = (f"{per_step} lock-step simulations of {CPU_GAMES} games per step (of the {1 + SEARCH_BUDGET} one move "
               f"needs), oracle C search + libtorch-CPU f32 forward")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -159,7 +159,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "restated CPU baseline (oracle port), not the reference binary: no Rust toolchain in the image",
-    }))
+    })
 
 
 def workload_config(n_gpus: int) -> dict:
@@ -186,8 +186,20 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result: anything a library prints on the way (NCCL's version
+    # banner, torchrun notices) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(json_fd, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, emit)
         return
 
     import numpy as np
@@ -370,7 +382,7 @@ def main():
             "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "e2e": e2e,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(out))
+        emit(out)
     m.close()
     if dist is not None:
         dist.destroy_process_group()
