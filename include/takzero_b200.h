@@ -281,6 +281,12 @@ TZ_API int tz_encode_planes(tz_handle* h, const tz_state_t* states, int count, f
  * buffer (0 block stream, 1 block middle, 2 input planes) of the last tz_evaluate as f32 [count][N*N][ch] */
 TZ_API int tz_debug_layer_limit(tz_handle* h, int limit);
 TZ_API int tz_debug_activations(tz_handle* h, int which, int count, float* out);
+/* test hook, needs no GPU: the work-item schedule of the fused network launch (conv_tcgen05.cuh `Schedule`) for
+ * `count` positions -- out[0..3] = items, chunks, pair tiles per chunk, rows per chunk -- next to the bounds the
+ * host sizes buffers with for `count_max` positions -- out[4..6] = chunks, pair tiles per chunk, rows of one
+ * activation set; out_items receives (chunk, layer, pair tile) of the first `cap` items */
+TZ_API int tz_debug_schedule(int count, int count_max, int board_n, int chunk_min_tiles, int layers, long long* out,
+                      int* out_items, int cap);
 /* tuning hook: mean ms per tower-convolution launch over `count` positions (CUDA events, `reps` blocks) */
 TZ_API int tz_debug_time_tower(tz_handle* h, int count, int reps, double* ms_per_conv);
 

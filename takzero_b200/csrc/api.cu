@@ -968,6 +968,14 @@ extern "C" TZ_API int tz_debug_time_tower(tz_handle* h, int count, int reps, dou
     return TZ_OK;
 }
 
+extern "C" TZ_API int tz_debug_schedule(int count, int count_max, int board_n, int chunk_min_tiles, int layers,
+                                        long long* out, int* out_items, int cap) {
+    if (!out || count < 0 || count > count_max || board_n < 3 || board_n > 6 || chunk_min_tiles <= 0 || layers <= 0 ||
+        (cap > 0 && !out_items))
+        return fail(TZ_EINVAL, "bad argument");
+    return nn_debug_schedule(count, count_max, board_n, chunk_min_tiles, layers, out, out_items, cap);
+}
+
 extern "C" TZ_API int tz_set_simhash(tz_handle* h, const float* matrix, const uint8_t* bitset) {
     CHECK_H(h);
     if (!matrix) return fail(TZ_EINVAL, "null matrix");

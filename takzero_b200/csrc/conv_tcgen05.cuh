@@ -126,7 +126,7 @@ struct Schedule {
     int rows_used;    // rows of the launch
     int n_layers;
     int items;
-    __device__ __forceinline__ void init(int count, int nn, int chunk_min_tiles, int layers) {
+    __host__ __device__ __forceinline__ void init(int count, int nn, int chunk_min_tiles, int layers) {
         rows_used = count * nn;
         // balanced chunks of at least chunk_min_tiles pair tiles (fewer than about two tiles per CTA pair and the
         // pairs stall on each other's progress; a sliver of a last chunk would walk through the layers alone)
@@ -140,7 +140,7 @@ struct Schedule {
         const int full = rows_used / chunk_rows, rest = rows_used - full * chunk_rows;
         items = (full * chunk_tiles + (rest + 2 * TILE_M - 1) / (2 * TILE_M)) * layers;
     }
-    __device__ __forceinline__ Item at(int item) const {
+    __host__ __device__ __forceinline__ Item at(int item) const {
         Item it;
         const int per_chunk = chunk_tiles * n_layers;
         it.chunk = item / per_chunk;

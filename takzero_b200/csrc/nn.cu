@@ -270,6 +270,20 @@ static const HostTensor* find(const std::vector<HostTensor>& ts, const std::stri
     return nullptr;
 }
 
+// Upper bounds of what conv::Schedule::init derives from a device-side count <= count_max: number of chunks and
+// pair tiles of one chunk (a chunk has fewer than 2 * chunk_min_tiles tiles, + rounding).  The activation sets and
+// the progress counters are sized with these.
+struct ChunkBounds {
+    int chunks, chunk_tiles;
+};
+static ChunkBounds chunk_bounds(int count_max, int nn, int chunk_min_tiles) {
+    const int all_tiles = (int)(((long long)count_max * nn + 2 * conv::TILE_M - 1) / (2 * conv::TILE_M));
+    ChunkBounds b;
+    b.chunks = all_tiles >= 2LL * chunk_min_tiles ? all_tiles / chunk_min_tiles : 1;
+    b.chunk_tiles = b.chunks > 1 ? 2 * chunk_min_tiles + 2 : (all_tiles > 0 ? all_tiles : 1);
+    return b;
+}
+
 static uint16_t f32_to_bf16(float f) {
     uint32_t u;
     memcpy(&u, &f, 4);
@@ -532,17 +546,12 @@ int nn_set_weights(tz_handle* h, const char* const* names, const float* const* d
         const char* ct = getenv("TZ_NN_CHUNK_TILES");
         const int tiles = ct ? atoi(ct) : 150;
         const int all_tiles = (int)((used + 2 * conv::TILE_M - 1) / (2 * conv::TILE_M));
-        if (!s->fused || tiles <= 0 || all_tiles < 2 * tiles || 2 * s->blocks + 2 > conv::MAX_LAYERS) {
-            s->chunk_min_tiles = 1 << 28;
-            s->chunk_tiles = all_tiles > 0 ? all_tiles : 1;
-            s->max_chunks = 1;
-            s->chunk_positions = s->max_positions;
-        } else {
-            s->chunk_min_tiles = tiles;
-            s->chunk_tiles = 2 * tiles + 2;  // a chunk has fewer than 2 * tiles tiles (+ rounding)
-            s->max_chunks = all_tiles / tiles;
-            s->chunk_positions = (s->chunk_tiles - 1) * 2 * conv::TILE_M / nn;
-        }
+        s->chunk_min_tiles = (!s->fused || tiles <= 0 || all_tiles < 2 * tiles || 2 * s->blocks + 2 > conv::MAX_LAYERS)
+                                 ? (1 << 28) : tiles;
+        const ChunkBounds cb = chunk_bounds(s->max_positions, nn, s->chunk_min_tiles);
+        s->chunk_tiles = cb.chunk_tiles;
+        s->max_chunks = cb.chunks;
+        s->chunk_positions = cb.chunks > 1 ? (cb.chunk_tiles - 1) * 2 * conv::TILE_M / nn : s->max_positions;
         s->rows_set = conv::HALO + (size_t)s->chunk_tiles * (2 * conv::TILE_M) + 2 * conv::HALO;
     }
     const bool reuse = old.p && old.p->n == n && old.p->max_positions == h->d.Q && old.p->rows == s->rows &&
@@ -624,6 +633,32 @@ int nn_set_weights(tz_handle* h, const char* const* names, const float* const* d
     return TZ_OK;
 }
 
+// test hook (no GPU needed): the kernel's own work-item schedule for `count` positions, and the bounds the host
+// sizes the activation sets and progress counters with.  out[0..4] = items, chunks, chunk_tiles, chunk_rows of the
+// schedule; out[4..7] = host bounds: chunks, chunk_tiles, rows per activation set; triples (chunk, layer, pair tile)
+// of up to `cap` items go to out_items.
+int nn_debug_schedule(int count, int count_max, int n, int chunk_min_tiles, int layers, long long* out, int* out_items,
+                      int cap) {
+    const int nn = n * n;
+    conv::Schedule sc;
+    sc.init(count, nn, chunk_min_tiles, layers);
+    out[0] = sc.items;
+    out[1] = sc.rows_used > 0 ? (sc.rows_used + sc.chunk_rows - 1) / sc.chunk_rows : 0;
+    out[2] = sc.chunk_tiles;
+    out[3] = sc.chunk_rows;
+    const ChunkBounds cb = chunk_bounds(count_max, nn, chunk_min_tiles);
+    out[4] = cb.chunks;
+    out[5] = cb.chunk_tiles;
+    out[6] = conv::HALO + (long long)cb.chunk_tiles * (2 * conv::TILE_M) + 2 * conv::HALO;
+    for (int i = 0; i < sc.items && i < cap; i++) {
+        const conv::Item it = sc.at(i);
+        out_items[3 * i] = it.chunk;
+        out_items[3 * i + 1] = it.layer;
+        out_items[3 * i + 2] = it.pt;
+    }
+    return 0;
+}
+
 void nn_set_layer_limit(tz_handle* h, int limit) {
     if (h->nn) h->nn->layer_limit = limit;
 }
@@ -667,8 +702,8 @@ static cudaError_t launch_layers(tz_handle* h, conv::Params& p, const int* count
     p.f16 = s->f16;
     // upper bounds of what the kernel derives from the device-side count (conv::Schedule::init)
     const int all_tiles = (count_max * nn + 2 * conv::TILE_M - 1) / (2 * conv::TILE_M);
-    const int chunks = all_tiles >= 2 * chunk_min_tiles ? all_tiles / chunk_min_tiles : 1;
-    const int chunk_tiles = chunks > 1 ? 2 * chunk_min_tiles + 2 : (all_tiles > 0 ? all_tiles : 1);
+    const ChunkBounds cb = chunk_bounds(count_max, nn, chunk_min_tiles);
+    const int chunks = cb.chunks, chunk_tiles = cb.chunk_tiles;
     const size_t counters = (size_t)chunks * chunk_tiles + chunks;
     p.progress = s->progress;
     p.chunk_done = s->progress + (size_t)chunks * chunk_tiles;

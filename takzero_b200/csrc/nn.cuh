@@ -17,3 +17,5 @@ int nn_debug_read(tz_handle* h, int which, int count, float* out_dev);
 int nn_time_tower(tz_handle* h, int count, int reps, double* ms_per_conv);
 int nn_set_simhash(tz_handle* h, const float* matrix, const unsigned char* bitset);
 int nn_simhash_indices(tz_handle* h, const TzState* states, int count, uint32_t* out_dev);
+int nn_debug_schedule(int count, int count_max, int n, int chunk_min_tiles, int layers, long long* out, int* out_items,
+                      int cap);
