@@ -34,9 +34,10 @@
 // (layer, pair tile) are numbered layer-major and dealt round-robin to the persistent CTA pairs, so a pair gets
 // 15.57 tiles per layer on average instead of a whole number per launch, and the launch gap, prologue and
 // pipeline refill between layers disappear.  A 3x3 tap reaches at most HALO rows into the neighbouring tiles,
-// so item (L, t) depends only on items (L-1, t-1..t+1): the epilogue warps publish their finished tile with a
-// release increment of progress[t] and the A producer of a dependent item spins on an acquire load, then
-// crosses to the async proxy with fence.proxy.async before its bulk copies.  The same three waits also cover the
+// so item (L, t) depends only on items (L-1, t-1..t+1): the epilogue warps publish every 64 output channels of
+// their tile with a release increment of progress[t][block] and the A producer of a dependent item spins on an
+// acquire load before it fetches that 64-channel block, then crosses to the async proxy with fence.proxy.async
+// before its bulk copies (so the first MMAs of a layer overlap the tail of the previous layer's epilogues).  The same three waits also cover the
 // write-after-read hazards of the two ping-pong activation buffers (a layer's output buffer is the input buffer
 // of the layer before it).  The launch is cooperative: every pair must be resident, or the spin would deadlock.
 // Chunks: the positions of a launch are cut into equal chunks of at least Params::chunk_min_tiles pair tiles and the items are numbered
@@ -109,8 +110,9 @@ struct Params {
     int guard;                      // leading guard rows of the activation planes (= HALO)
     const uint4* masks;             // [n*n][9] disable-output-lane masks by (first tile row) mod n*n
     int f16;                        // 16-bit storage / operand type: 0 = bf16, 1 = IEEE fp16 (same UMMA kind::f16)
-    unsigned* progress;             // [chunks][pair tiles per chunk], zeroed before the launch: epilogue-warp
-                                    // arrivals per tile (8 per finished layer); may be null when n_layers == 1
+    unsigned* progress;             // [chunks][pair tiles per chunk][4], zeroed before the launch: epilogue-warp
+                                    // arrivals per tile and 64-channel block of the output (8 per finished
+                                    // layer); may be null when n_layers == 1
     unsigned* chunk_done;           // [chunks]: epilogue-warp arrivals of the last layer (8 per tile)
 };
 
@@ -323,6 +325,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
     sched.init(count, nn, p.chunk_min_tiles, p.n_layers);
     const int items = sched.items;
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    // With fewer than two tiles per pair and layer the launch is bound by the layer-to-layer dependency chain: the
+    // epilogues then publish every 64 output channels separately so that the next layer's first MMAs overlap the
+    // rest of the epilogue.  With more tiles that only costs (four device-wide fences per tile instead of one).
+    const bool fine = sched.chunk_tiles < 2 * npairs;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < A_STAGES; i++) {
@@ -364,20 +370,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                 const Item it = sched.at(item);
                 const int layer = it.layer, pt = it.pt;
                 const Layer& L = p.layers[layer];
-                if (layer > 0) {
-                    // rows [t*128 - HALO, t*128 + 128 + HALO) of the previous layer's output: CTA tiles t-1, t, t+1,
-                    // i.e. pair tiles {pt-1, pt} for rank 0 and {pt, pt+1} for rank 1
-                    const unsigned need = 8u * (unsigned)layer;
-                    const unsigned* prog = p.progress + (size_t)it.chunk * sched.chunk_tiles;
-                    const int lo = pt - 1 + (int)rank;
-                    for (int q = lo; q <= lo + 1; q++)
-                        if (q >= 0 && q < it.tiles)
-                            while (ld_acquire_gpu(prog + q) < need) __nanosleep(40);
-                    fence_proxy_async();
-                } else if (it.chunk >= 2 && p.n_layers > 1) {
+                // rows [t*128 - HALO, t*128 + 128 + HALO) of the previous layer's output: CTA tiles t-1, t, t+1, i.e.
+                // pair tiles {pt-1, pt} for rank 0 and {pt, pt+1} for rank 1; waited for per 64-channel block below
+                const unsigned need = 8u * (unsigned)layer;
+                const unsigned* prog = p.progress + ((size_t)it.chunk * sched.chunk_tiles) * 4;
+                const int lo = pt - 1 + (int)rank;
+                if (layer == 0 && it.chunk >= 2 && p.n_layers > 1) {
                     // this chunk's first layer overwrites the activation set of chunk - 2: all of it must be done
-                    const unsigned need = 8u * (unsigned)sched.chunk_tiles;
-                    while (ld_acquire_gpu(p.chunk_done + it.chunk - 2) < need) __nanosleep(40);
+                    const unsigned all_warps = 8u * (unsigned)sched.chunk_tiles;
+                    while (ld_acquire_gpu(p.chunk_done + it.chunk - 2) < all_warps) __nanosleep(40);
                 }
                 const int t = pt * 2 + (int)rank;
                 const size_t in_rows = L.in_global ? (size_t)p.rows_global : (size_t)p.rows_set;
@@ -387,6 +388,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                     reinterpret_cast<const uint8_t*>(in_base) + (in_first + (size_t)(p.guard + t * TILE_M - HALO)) * 16;
                 const int kblocks = L.cin >> 6;
                 for (int kb = 0; kb < kblocks; kb++) {
+                    if (layer > 0 && (fine || kb == 0)) {
+                        // fine: wait for this 64-channel block only; else for the whole tile (its last block)
+                        const int blk = fine ? kb : 3;
+                        for (int q = lo; q <= lo + 1; q++)
+                            if (q >= 0 && q < it.tiles)
+                                while (ld_acquire_gpu(prog + q * 4 + blk) < need) __nanosleep(40);
+                        fence_proxy_async();
+                    }
                     mbar_wait(a_empty + 8 * stage, phase ^ 1);
                     mbar_arrive_expect_tx(a_sig + 8 * stage, A_STAGE_BYTES);
                     const uint32_t dst = smem_u32(a_smem + stage * A_STAGE_BYTES);
@@ -566,8 +575,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
             // acquire per tile (on the counter that writer released) makes the plain loads below see them: it costs
             // an L1 invalidate per warp and tile, whereas L2-only (ld.cg) loads made the epilogue 1.8x slower
             // than the MMAs of a tile.
-            if (residual != nullptr && layer >= 2)
-                (void)ld_acquire_gpu(p.progress + (size_t)wi.chunk * sched.chunk_tiles + pt);
+            unsigned* prog_tile = p.progress + ((size_t)wi.chunk * sched.chunk_tiles + pt) * 4;
+            if (residual != nullptr && layer >= 2) (void)ld_acquire_gpu(prog_tile + 3);
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * N_OUT;
 #pragma unroll 1
             for (int c0 = 0; c0 < N_OUT; c0 += 32) {
@@ -616,17 +625,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                         }
                     }
                 }
+                if (p.n_layers > 1 && (fine ? (c0 & 32) != 0 : c0 == N_OUT - 32)) {
+                    // 64 more output channels (fine) or the whole tile of this warp's rows are visible device-wide
+                    __threadfence();
+                    __syncwarp();
+                    if (fine) {
+                        if (lane == 0) red_release_gpu_add(prog_tile + (c0 >> 6), 1u);
+                    } else if (lane < 4) {
+                        red_release_gpu_add(prog_tile + lane, 1u);
+                    }
+                }
             }
             if (head_w && valid) *reinterpret_cast<float2*>(L.head_out + grel * 2) = make_float2(head_v, head_u);
-            if (p.n_layers > 1) __threadfence();  // this thread's rows are visible device-wide before the tile is published
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive_cluster(t_empty_leader + 8 * acc);
-                if (p.n_layers > 1) {
-                    red_release_gpu_add(p.progress + (size_t)wi.chunk * sched.chunk_tiles + pt, 1u);
-                    if (layer == p.n_layers - 1) red_release_gpu_add(p.chunk_done + wi.chunk, 1u);
-                }
+                if (p.n_layers > 1 && layer == p.n_layers - 1) red_release_gpu_add(p.chunk_done + wi.chunk, 1u);
             }
         }
     }

@@ -618,7 +618,7 @@ int nn_set_weights(tz_handle* h, const char* const* names, const float* const* d
             s->max_pairs = clusters < s->sm_count / 2 ? clusters : s->sm_count / 2;
         else
             s->max_pairs = s->sm_count / 2;
-        const size_t tiles = (size_t)s->max_chunks * s->chunk_tiles + s->max_chunks + 16;
+        const size_t tiles = (size_t)s->max_chunks * s->chunk_tiles * 4 + s->max_chunks + 16;
         s->progress_len = tiles;
         if (reuse) {
             s->progress = static_cast<unsigned*>(old.take(old.p->progress));
@@ -704,9 +704,9 @@ static cudaError_t launch_layers(tz_handle* h, conv::Params& p, const int* count
     const int all_tiles = (count_max * nn + 2 * conv::TILE_M - 1) / (2 * conv::TILE_M);
     const ChunkBounds cb = chunk_bounds(count_max, nn, chunk_min_tiles);
     const int chunks = cb.chunks, chunk_tiles = cb.chunk_tiles;
-    const size_t counters = (size_t)chunks * chunk_tiles + chunks;
+    const size_t counters = (size_t)chunks * chunk_tiles * 4 + chunks;  // 4 channel blocks per tile, then the chunks
     p.progress = s->progress;
-    p.chunk_done = s->progress + (size_t)chunks * chunk_tiles;
+    p.chunk_done = s->progress + (size_t)chunks * chunk_tiles * 4;
     const long long items = (long long)all_tiles * p.n_layers;
     const int pairs = items < s->max_pairs ? (items > 0 ? (int)items : 1) : s->max_pairs;
     cudaLaunchConfig_t cfg = {};
