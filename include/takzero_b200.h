@@ -275,6 +275,10 @@ TZ_API int tz_evaluate(tz_handle* h, const tz_state_t* states, int count, const 
  * which the local uncertainty is MAXIMUM_VARIANCE = 4.0.  tz_simhash_indices = `get_indices` (parity hook). */
 TZ_API int tz_set_simhash(tz_handle* h, const float* matrix, const uint8_t* bitset);
 TZ_API int tz_simhash_indices(tz_handle* h, const tz_state_t* states, int count, uint32_t* out);
+/* LCG-hash novelty (net4_lcghash.rs:131-137,203-241): `lcghash_init` [C][N][N] f32 and the optional set; replaces
+ * the SimHash lookup of the handle.  tz_lcghash_indices = `get_indices` (integer hash: bit-exact parity hook). */
+TZ_API int tz_set_lcghash(tz_handle* h, const float* init, const uint8_t* bitset);
+TZ_API int tz_lcghash_indices(tz_handle* h, const tz_state_t* states, int count, uint32_t* out);
 /* game_repr (repr.rs:169-228): f32 planes [count][C][N][N] */
 TZ_API int tz_encode_planes(tz_handle* h, const tz_state_t* states, int count, float* out);
 /* test hooks: stop the tower after `limit` convolutions (-1 = full network); read back an activation

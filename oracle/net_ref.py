@@ -122,6 +122,34 @@ class Net(nn.Module):
         bits = (~(dots < 0.0)).astype(np.uint64)
         return (bits << np.arange(32, dtype=np.uint64)).sum(axis=1).astype(np.uint32)
 
+    @staticmethod
+    @torch.no_grad()
+    def lcghash_indices(xs: torch.Tensor, lcghash_init: torch.Tensor) -> np.ndarray:
+        """`get_indices` of the LCG-hash network (net4_lcghash.rs:203-241), the same tensor operations:
+        (xs * init) reinterpreted as i32, folded with acc = acc * MULTIPLIER + INCREMENT + x (wrapping i64) along
+        the columns, then the rows, then the channels; index = |acc| >> (63 - HASH_BITS)."""
+        MULTIPLIER, INCREMENT, HASH_BITS = 6_364_136_223_846_793_005, 1, 32
+        batch, channels, rows, _cols = xs.shape
+        parts = (xs * lcghash_init).view(torch.int32).split(1, 3)
+        acc = torch.zeros(batch, channels, rows, dtype=torch.int64)
+        for x in parts:
+            acc *= MULTIPLIER
+            acc += INCREMENT
+            acc += x.squeeze(3)
+        parts = acc.split(1, 2)
+        acc = torch.zeros(batch, channels, dtype=torch.int64)
+        for x in parts:
+            acc *= MULTIPLIER
+            acc += INCREMENT
+            acc += x.squeeze(2)
+        parts = acc.split(1, 1)
+        acc = torch.zeros(batch, dtype=torch.int64)
+        for x in parts:
+            acc *= MULTIPLIER
+            acc += INCREMENT
+            acc += x.squeeze(1)
+        return (acc.abs() >> (63 - HASH_BITS)).numpy().astype(np.uint32)
+
     def bitset_bytes(self) -> np.ndarray:
         """The reference's bitvec.bin image: 2^29 bytes, bit i of the set = byte i/8, bit i%8."""
         b = np.zeros(1 << 29, dtype=np.uint8)

@@ -1002,6 +1002,32 @@ extern "C" TZ_API int tz_simhash_indices(tz_handle* h, const tz_state_t* states,
     return TZ_OK;
 }
 
+extern "C" TZ_API int tz_set_lcghash(tz_handle* h, const float* init, const uint8_t* bitset) {
+    CHECK_H(h);
+    if (!init) return fail(TZ_EINVAL, "null init");
+    CU(cudaStreamSynchronize(h->stream));
+    const int rc = nn_set_lcghash(h, init, bitset);
+    if (rc) return fail(rc, "tz_set_lcghash failed (tz_set_weights first; the set needs 512 MiB of HBM)");
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_lcghash_indices(tz_handle* h, const tz_state_t* states, int count, uint32_t* out) {
+    CHECK_H(h);
+    if (!states || !out || count <= 0) return fail(TZ_EINVAL, "bad argument");
+    Scratch s;
+    TzState* ds;
+    uint32_t* dout;
+    CU(s.get(&ds, (size_t)count));
+    CU(s.get(&dout, (size_t)count));
+    CU(cudaMemcpyAsync(ds, states, (size_t)count * sizeof(TzState), cudaMemcpyHostToDevice, h->stream));
+    const int rc = nn_lcghash_indices(h, ds, count, dout);
+    if (rc) return fail(rc, "tz_lcghash_indices needs tz_set_lcghash first");
+    CU(cudaMemcpyAsync(out, dout, (size_t)count * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return TZ_OK;
+}
+
 // ---- single tree (tei / analysis): Node::simulate_simple, simulate_batch, descend, principal_variation ----
 // The tree is game 0 of the handle; batch_size <= n_games because the per-leaf paths reuse the per-game buffers.
 

@@ -565,9 +565,14 @@ extern "C" TZ_API int tz_load_model(tz_handle* h, const char* path) {
     for (const NamedTensor& t : ts) names.push_back(canonical_name(t.name));
     std::vector<tz_tensor_t> args;
     const NamedTensor* simhash = nullptr;
+    const NamedTensor* lcghash = nullptr;
     for (size_t i = 0; i < ts.size(); i++) {
         if (names[i] == "simhash_matrix") {
             simhash = &ts[i];
+            continue;
+        }
+        if (names[i] == "lcghash_init") {  // net4_lcghash.rs:131-137
+            lcghash = &ts[i];
             continue;
         }
         if (ts[i].shape.size() > 4) continue;
@@ -575,7 +580,7 @@ extern "C" TZ_API int tz_load_model(tz_handle* h, const char* path) {
     }
     int rc = tz_set_weights(h, args.data(), (int)args.size());
     if (rc != TZ_OK) return rc;
-    if (simhash) {
+    if (simhash || lcghash) {
         std::string dir = path;
         const size_t slash = dir.find_last_of('/');
         dir = slash == std::string::npos ? std::string() : dir.substr(0, slash + 1);
@@ -587,7 +592,8 @@ extern "C" TZ_API int tz_load_model(tz_handle* h, const char* path) {
             std::fclose(f);
             if (got != bits.size()) return model_fail(TZ_EINVAL, dir + "bitvec.bin: expected 2^29 bytes");
         }
-        rc = tz_set_simhash(h, simhash->data.data(), bits.empty() ? nullptr : bits.data());
+        rc = lcghash ? tz_set_lcghash(h, lcghash->data.data(), bits.empty() ? nullptr : bits.data())
+                     : tz_set_simhash(h, simhash->data.data(), bits.empty() ? nullptr : bits.data());
         if (rc != TZ_OK) return rc;
     }
     return TZ_OK;

@@ -49,6 +49,8 @@ struct NnState {
     float* head_feat = nullptr;       // [max_positions * n*n][2] value / UBE 1x1 convolution outputs per row
     float* logits_full = nullptr;     // [64][max_positions * n*n][4] policy logits, 4-channel planes
     uint4* masks = nullptr;           // [n*n][9] disable-output-lane masks (conv_tcgen05.cuh)
+    int novelty = 0;                  // which hash indexes the set: 0 none yet, 1 SimHash, 2 LCG hash (last one set)
+    float* lcghash_init = nullptr;    // [C][N][N] (net4_lcghash.rs:131-137), optional
     float* simhash_matrix = nullptr;  // [C*N*N][32] (net6_simhash.rs:136-139), optional
     uint32_t* simhash_set = nullptr;  // 2^32-bit set (bitvec.bin), optional; absent = empty set
     uint32_t* simhash_idx = nullptr;  // [max_positions] hash index of each queued position
@@ -138,18 +140,11 @@ __global__ void __launch_bounds__(32 * WPB) k_encode(const TzState* states, cons
 
 // One warp per position, lane = hash bit: dot of the f32 planes (side-to-move plane zeroed) with column
 // `lane` of the [C*N*N][32] matrix; bit set when the dot is >= 0; index = sum of 2^bit.
-__global__ void __launch_bounds__(32 * WPB) k_simhash(const TzState* states, const int* count_ptr, int count_max, int n,
-                                                       int half_komi, const float* matrix, uint32_t* out_idx) {
-    __shared__ TzState s_state[WPB];
-    __shared__ float s_planes[WPB][36 * 36];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = blockIdx.x * WPB + warp;
-    const int count = count_ptr ? *count_ptr : count_max;
-    if (q >= count) return;
-    TzState* st = &s_state[warp];
-    warp_load_state(st, &states[q], lane);
+// f32 input planes of one position into shared memory (x[plane * nn + square], `game_repr` order); the warp's
+// lanes own the squares.  zero_colour leaves the "black to move" plane at 0 (SimHash, net6_simhash.rs:209-222).
+__device__ __forceinline__ void warp_fill_planes(float* x, const TzState* st, int n, int half_komi, int lane,
+                                                 bool zero_colour) {
     const int nn = n * n, ss = 2 * n + 3, C = 2 * (ss + 2) + 2;
-    float* x = s_planes[warp];
     for (int i = lane; i < C * nn; i += 32) x[i] = 0.0f;
     __syncwarp();
     const int me = st->to_move, other = me ^ 1;
@@ -178,10 +173,25 @@ __global__ void __launch_bounds__(32 * WPB) k_simhash(const TzState* states, con
         x[(base + 1) * nn + sq] = r1;
         x[(base + 2) * nn + sq] = r2;
         x[(base + 3) * nn + sq] = r3;
-        // plane base + 4 (black to move) is zeroed for the hash (net6_simhash.rs:209-222)
+        if (!zero_colour && me == 1) x[(base + 4) * nn + sq] = 1.0f;
         x[(base + 5) * nn + sq] = fcd_sq;
     }
     __syncwarp();
+}
+
+__global__ void __launch_bounds__(32 * WPB) k_simhash(const TzState* states, const int* count_ptr, int count_max, int n,
+                                                       int half_komi, const float* matrix, uint32_t* out_idx) {
+    __shared__ TzState s_state[WPB];
+    __shared__ float s_planes[WPB][36 * 36];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * WPB + warp;
+    const int count = count_ptr ? *count_ptr : count_max;
+    if (q >= count) return;
+    TzState* st = &s_state[warp];
+    warp_load_state(st, &states[q], lane);
+    const int nn = n * n, C = 2 * (2 * n + 3 + 2) + 2;
+    float* x = s_planes[warp];
+    warp_fill_planes(x, st, n, half_komi, lane, true);
     float dot = 0.0f;
     const int total = C * nn;
     for (int j = 0; j < total; j++) dot = fmaf(x[j], matrix[(size_t)j * 32 + lane], dot);
@@ -197,6 +207,52 @@ __device__ __forceinline__ int move_channel(int n, uint16_t m) {
     if (pat == 0) return kind;  // flat 0, wall 1, cap 2
     const int dir_off = kind == 0 ? 0 : kind == 1 ? 2 : kind == 2 ? 3 : 1;  // Up, Right, Down, Left order of repr.rs:61-66
     return 3 + ((pat >> (8 - n)) - 1) + ((1 << n) - 2) * dir_off;
+}
+
+// ---- LCG-hash novelty index (net4_lcghash.rs:203-241 `get_indices`) -------------------------------------
+// planes * lcghash_init (f32, elementwise) reinterpreted as i32, folded with the 64-bit LCG
+// acc = acc * 6364136223846793005 + 1 + v  along the columns, then the rows, then the channels (wrapping i64);
+// index = |acc| >> 31.  Integer work: bit-exact.  One warp per position.
+__global__ void __launch_bounds__(32 * WPB) k_lcghash(const TzState* states, const int* count_ptr, int count_max, int n,
+                                                       int half_komi, const float* init, uint32_t* out_idx) {
+    __shared__ TzState s_state[WPB];
+    __shared__ float s_planes[WPB][36 * 36];
+    __shared__ unsigned long long s_rows[WPB][36 * 6];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * WPB + warp;
+    const int count = count_ptr ? *count_ptr : count_max;
+    if (q >= count) return;
+    TzState* st = &s_state[warp];
+    warp_load_state(st, &states[q], lane);
+    const int nn = n * n, C = 2 * (2 * n + 3 + 2) + 2;
+    float* x = s_planes[warp];
+    warp_fill_planes(x, st, n, half_komi, lane, false);
+    const unsigned long long MUL = 6364136223846793005ull;
+    unsigned long long* rows = s_rows[warp];
+    for (int cr = lane; cr < C * n; cr += 32) {  // (channel, row): fold the columns
+        unsigned long long acc = 0;
+        for (int j = 0; j < n; j++) {
+            const int at = cr * n + j;
+            const int v = __float_as_int(__fmul_rn(x[at], init[at]));
+            acc = acc * MUL + 1ull + (unsigned long long)(long long)v;
+        }
+        rows[cr] = acc;
+    }
+    __syncwarp();
+    for (int c = lane; c < C; c += 32) {  // channel: fold the rows (in place: slot c * n)
+        unsigned long long acc = 0;
+        for (int r = 0; r < n; r++) acc = acc * MUL + 1ull + rows[c * n + r];
+        __syncwarp();
+        rows[c * n] = acc;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        unsigned long long acc = 0;
+        for (int c = 0; c < C; c++) acc = acc * MUL + 1ull + rows[c * n];
+        long long sacc = (long long)acc;
+        if (sacc < 0) sacc = -sacc;  // i64::MIN stays negative, as a wrapping abs does
+        out_idx[q] = (uint32_t)((unsigned long long)sacc >> 31);
+    }
 }
 
 // One warp per position: value head (conv1x1 + ReLU + Linear + tanh), UBE head (same, no tanh),
@@ -569,6 +625,8 @@ int nn_set_weights(tz_handle* h, const char* const* names, const float* const* d
         steal(s->logits_full, old.p->logits_full);
         steal(s->masks, old.p->masks);
         steal(s->simhash_matrix, old.p->simhash_matrix);
+        steal(s->lcghash_init, old.p->lcghash_init);
+        s->novelty = old.p->novelty;
         steal(s->simhash_set, old.p->simhash_set);
         steal(s->simhash_idx, old.p->simhash_idx);
     }
@@ -792,7 +850,10 @@ int nn_forward(tz_handle* h, const TzState* states, const int* count_ptr, int co
         h->launches += 1 + launch_network(h, count_ptr, count_max, limit);
     }
     if (limit >= 0) return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
-    if (s->simhash_set)
+    if (s->simhash_set && s->novelty == 2)
+        k_lcghash<<<wblocks, 32 * WPB, 0, h->stream>>>(states, count_ptr, count_max, d.n, d.half_komi, s->lcghash_init,
+                                                       s->simhash_idx);
+    else if (s->simhash_set)
         k_simhash<<<wblocks, 32 * WPB, 0, h->stream>>>(states, count_ptr, count_max, d.n, d.half_komi, s->simhash_matrix,
                                                        s->simhash_idx);
     {
@@ -912,10 +973,13 @@ int nn_set_simhash(tz_handle* h, const float* matrix, const unsigned char* bitse
     if (!s->simhash_matrix) {
         if (cudaMalloc((void**)&s->simhash_matrix, rows * 32 * 4) != cudaSuccess) return TZ_ENOMEM;
         s->allocs.push_back(s->simhash_matrix);
+    }
+    if (!s->simhash_idx) {
         if (cudaMalloc((void**)&s->simhash_idx, (size_t)s->max_positions * 4) != cudaSuccess) return TZ_ENOMEM;
         s->allocs.push_back(s->simhash_idx);
     }
     if (cudaMemcpy(s->simhash_matrix, matrix, rows * 32 * 4, cudaMemcpyHostToDevice) != cudaSuccess) return TZ_ECUDA;
+    s->novelty = 1;
     if (bitset) {
         const size_t bytes = (size_t)1 << 29;
         if (!s->simhash_set) {
@@ -927,6 +991,42 @@ int nn_set_simhash(tz_handle* h, const float* matrix, const unsigned char* bitse
         s->simhash_set = nullptr;  // empty set: local uncertainty is MAXIMUM_VARIANCE everywhere
     }
     return TZ_OK;
+}
+
+// LCG-hash novelty (net4_lcghash.rs): the per-cell multipliers and the optional 2^32-bit set; replaces SimHash
+int nn_set_lcghash(tz_handle* h, const float* init, const unsigned char* bitset) {
+    NnState* s = h->nn;
+    if (!s) return TZ_ENOWEIGHTS;
+    const size_t cells = (size_t)s->in_channels * s->n * s->n;
+    if (!s->lcghash_init) {
+        if (cudaMalloc((void**)&s->lcghash_init, cells * 4) != cudaSuccess) return TZ_ENOMEM;
+        s->allocs.push_back(s->lcghash_init);
+    }
+    if (!s->simhash_idx) {
+        if (cudaMalloc((void**)&s->simhash_idx, (size_t)s->max_positions * 4) != cudaSuccess) return TZ_ENOMEM;
+        s->allocs.push_back(s->simhash_idx);
+    }
+    if (cudaMemcpy(s->lcghash_init, init, cells * 4, cudaMemcpyHostToDevice) != cudaSuccess) return TZ_ECUDA;
+    s->novelty = 2;
+    if (bitset) {
+        const size_t bytes = (size_t)1 << 29;
+        if (!s->simhash_set) {
+            if (cudaMalloc((void**)&s->simhash_set, bytes) != cudaSuccess) return TZ_ENOMEM;
+            s->allocs.push_back(s->simhash_set);
+        }
+        if (cudaMemcpy(s->simhash_set, bitset, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return TZ_ECUDA;
+    } else {
+        s->simhash_set = nullptr;
+    }
+    return TZ_OK;
+}
+
+int nn_lcghash_indices(tz_handle* h, const TzState* states, int count, uint32_t* out_dev) {
+    NnState* s = h->nn;
+    if (!s || !s->lcghash_init) return TZ_ENOWEIGHTS;
+    k_lcghash<<<(count + WPB - 1) / WPB, 32 * WPB, 0, h->stream>>>(states, nullptr, count, h->d.n, h->d.half_komi,
+                                                                   s->lcghash_init, out_dev);
+    return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
 }
 
 int nn_simhash_indices(tz_handle* h, const TzState* states, int count, uint32_t* out_dev) {

@@ -19,3 +19,5 @@ int nn_set_simhash(tz_handle* h, const float* matrix, const unsigned char* bitse
 int nn_simhash_indices(tz_handle* h, const TzState* states, int count, uint32_t* out_dev);
 int nn_debug_schedule(int count, int count_max, int n, int chunk_min_tiles, int layers, long long* out, int* out_items,
                       int cap);
+int nn_set_lcghash(tz_handle* h, const float* init, const unsigned char* bitset);
+int nn_lcghash_indices(tz_handle* h, const TzState* states, int count, uint32_t* out_dev);

@@ -33,6 +33,8 @@ def _declare():
     capi.declare("tz_set_network_dtype", [vp, i32], i32)
     capi.declare("tz_set_simhash", [vp, vp, vp], i32)
     capi.declare("tz_simhash_indices", [vp, vp, i32, vp], i32)
+    capi.declare("tz_set_lcghash", [vp, vp, vp], i32)
+    capi.declare("tz_lcghash_indices", [vp, vp, i32, vp], i32)
     capi.declare("tz_debug_layer_limit", [vp, i32], i32)
     capi.declare("tz_debug_activations", [vp, i32, i32, vp], i32)
     capi.declare("tz_debug_time_tower", [vp, i32, i32, C.POINTER(C.c_double)], i32)
@@ -150,4 +152,24 @@ def simhash_indices(mcts: capi.BatchedMCTS, states: np.ndarray) -> np.ndarray:
     states = np.ascontiguousarray(states, dtype=capi.STATE_DTYPE)
     out = np.zeros(len(states), dtype=np.uint32)
     capi._check(capi.lib().tz_simhash_indices(mcts.handle, capi._ptr(states), len(states), capi._ptr(out)))
+    return out
+
+
+def set_lcghash(mcts: capi.BatchedMCTS, init: np.ndarray, bitset: np.ndarray | None = None) -> None:
+    """LCG-hash novelty (net4_lcghash.rs): `lcghash_init` [C, N, N] and optionally the 2^32-bit set."""
+    _declare()
+    a = np.ascontiguousarray(init, dtype=np.float32)
+    assert a.shape == (mcts.input_channels, mcts.n, mcts.n)
+    b = None
+    if bitset is not None:
+        b = np.ascontiguousarray(bitset, dtype=np.uint8)
+        assert b.size == 1 << 29
+    capi._check(capi.lib().tz_set_lcghash(mcts.handle, capi._ptr(a), capi._ptr(b)))
+
+
+def lcghash_indices(mcts: capi.BatchedMCTS, states: np.ndarray) -> np.ndarray:
+    _declare()
+    states = np.ascontiguousarray(states, dtype=capi.STATE_DTYPE)
+    out = np.zeros(len(states), dtype=np.uint32)
+    capi._check(capi.lib().tz_lcghash_indices(mcts.handle, capi._ptr(states), len(states), capi._ptr(out)))
     return out

@@ -277,6 +277,50 @@ def test_load_model_from_tch_archive_with_bitvec_sidecar(tmp_path):
         h.close()
 
 
+@pytest.mark.parametrize("n,hk", [(4, 4), (6, 4)])
+def test_lcghash_indices_bit_exact_and_uncertainty(n, hk, tmp_path):
+    """LCG-hash novelty of the reference's net4_lcghash.rs:203-261: an integer hash of the planes, so the index is
+    bit-exact against the tensor-op restatement; the set lookup then works like SimHash's.  Also through
+    tz_load_model (`lcghash_init` in the archive + bitvec.bin)."""
+    from takzero_b200 import weights
+
+    count = 96
+    ref = net_ref.Net(n, seed=4, blocks=1)
+    games = sample_positions(n, hk, count, 41)
+    actions = [O.possible_moves(g) for g in games]
+    states = games_to_states(games)
+    init = torch.empty(ref.cin, n, n).uniform_(-100.0, 100.0, generator=torch.Generator().manual_seed(5))
+    xs = torch.from_numpy(np.stack([O.game_repr(g).reshape(ref.cin, n, n) for g in games]))
+    want = net_ref.Net.lcghash_indices(xs, init)
+    m = capi.BatchedMCTS(n, hk, count, arena_slots=4096)
+    network.set_weights(m, ref.tensors())
+    network.set_lcghash(m, init.numpy())
+    got = network.lcghash_indices(m, states)
+    assert np.array_equal(got, want)
+    assert len(set(got.tolist())) > count // 2  # it does hash
+    # mark every other position as seen: its local uncertainty drops to 0
+    ref.simhash_set = {int(x) for x in got[::2]}
+    bits = ref.bitset_bytes()
+    network.set_lcghash(m, init.numpy(), bits)
+    _, _, variances = network.evaluate(m, states, actions)
+    with torch.no_grad():
+        ube = ref.ube(ref.core(xs)).view(-1).numpy()
+    seen = np.array([int(x) in ref.simhash_set for x in got])
+    want_var = np.where(seen, np.clip(np.exp(ube), 0.0, 4.0), 4.0)
+    assert np.abs(variances - want_var).max() <= 2e-2 and (variances[~seen] == 4.0).all()
+    # the same through the model file
+    tensors = dict(ref.tensors())
+    tensors["lcghash_init"] = init.numpy()
+    weights.save_ot(str(tmp_path / "model_latest.ot"), tensors)
+    np.asarray(bits, dtype=np.uint8).tofile(str(tmp_path / "bitvec.bin"))
+    b = capi.BatchedMCTS(n, hk, count, arena_slots=4096)
+    network.load_model(b, str(tmp_path / "model_latest.ot"))
+    assert np.array_equal(network.lcghash_indices(b, states), want)
+    assert np.array_equal(network.evaluate(b, states, actions)[2], variances)
+    for h in (m, b):
+        h.close()
+
+
 def test_model_reload_replaces_weights_and_keeps_buffers():
     """Net::load before every move (selfplay/src/main.rs:107): a second tz_set_weights takes effect for the
     next evaluation (activation buffers are reused, only the folded weights change)."""
