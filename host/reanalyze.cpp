@@ -58,14 +58,15 @@ static void fill_buffer(BatchedMCTS& mcts, std::vector<tz_state_t>& buffer, std:
     if (!f) return;
     f.seekg(*seek);
     std::string line;
+    std::vector<Replay> replays;
     while (std::getline(f, line)) {
         if (f.eof() && !line.empty()) break;  // a line still being written: read it next time
         *seek += (std::streamoff)line.size() + 1;
         Replay r;
-        if (!Replay::parse(line, board, &r)) continue;
-        const std::vector<tz_state_t> st = mcts.replay_states(r);
-        buffer.insert(buffer.end(), st.begin(), st.end());
+        if (Replay::parse(line, board, &r)) replays.push_back(std::move(r));
     }
+    const std::vector<tz_state_t> st = mcts.replay_states(replays);
+    buffer.insert(buffer.end(), st.begin(), st.end());
 }
 
 static const size_t MAX_REANALYZE_BUFFER_LEN = 32000;  // main.rs:41

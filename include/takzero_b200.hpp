@@ -10,6 +10,7 @@
 // All search / rules / network math happens in the CUDA library; this header only marshals and formats.
 #pragma once
 
+#include <algorithm>
 #include <charconv>
 #include <cmath>
 #include <cstdint>
@@ -437,18 +438,49 @@ class BatchedMCTS {
         return out;
     }
     void step(const std::vector<Move>& actions) { check(tz_step(h_, actions.data())); }
-    // Replay::states (target.rs:205-212): the position before every action, by applying the moves on the device
-    std::vector<tz_state_t> replay_states(const Replay& r) {
-        std::vector<tz_state_t> out;
-        tz_state_t cur = r.env;
-        for (Move m : r.actions) {
-            out.push_back(cur);
-            int ok = 0;
-            check(tz_apply(h_, &cur, &m, 1, &ok));
-            if (!ok) throw std::runtime_error("Action should be valid: " + move_to_string(m));
+    // Replay::states (target.rs:205-212) of many replays at once: the position before every action, replay by
+    // replay in file order.  The moves are applied on the device, all replays in lock-step by ply (one tz_apply per
+    // ply index instead of one per position).
+    std::vector<tz_state_t> replay_states(const std::vector<Replay>& replays) {
+        std::vector<size_t> first(replays.size() + 1, 0);
+        size_t longest = 0;
+        for (size_t r = 0; r < replays.size(); r++) {
+            first[r + 1] = first[r] + replays[r].actions.size();
+            longest = std::max(longest, replays[r].actions.size());
+        }
+        std::vector<tz_state_t> out(first.back());
+        std::vector<tz_state_t> cur;
+        std::vector<size_t> who;
+        for (size_t r = 0; r < replays.size(); r++)
+            if (!replays[r].actions.empty()) {
+                who.push_back(r);
+                cur.push_back(replays[r].env);
+            }
+        std::vector<Move> moves;
+        std::vector<int> ok;
+        for (size_t ply = 0; ply < longest && !who.empty(); ply++) {
+            moves.resize(who.size());
+            ok.assign(who.size(), 0);
+            for (size_t i = 0; i < who.size(); i++) {
+                out[first[who[i]] + ply] = cur[i];
+                moves[i] = replays[who[i]].actions[ply];
+            }
+            check(tz_apply(h_, cur.data(), moves.data(), (int)who.size(), ok.data()));
+            size_t keep = 0;
+            for (size_t i = 0; i < who.size(); i++) {
+                if (!ok[i]) throw std::runtime_error("Action should be valid: " + move_to_string(moves[i]));
+                if (ply + 1 < replays[who[i]].actions.size()) {
+                    who[keep] = who[i];
+                    cur[keep] = cur[i];
+                    keep++;
+                }
+            }
+            who.resize(keep);
+            cur.resize(keep);
         }
         return out;
     }
+    std::vector<tz_state_t> replay_states(const Replay& r) { return replay_states(std::vector<Replay>(1, r)); }
 
     struct RootTargets {
         std::vector<float> policy;  // [games][stride]
