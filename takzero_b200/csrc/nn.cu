@@ -787,17 +787,18 @@ static cudaError_t launch_layers(tz_handle* h, conv::Params& p, const int* count
 }
 
 // one convolution over `count_max` positions that all sit in ONE activation set of `rows_set` rows
-static void launch_conv(tz_handle* h, const conv::Layer& layer, const int* count_ptr, int count_max, size_t rows_set) {
+static cudaError_t launch_conv(tz_handle* h, const conv::Layer& layer, const int* count_ptr, int count_max,
+                               size_t rows_set) {
     conv::Params p;
     p.layers[0] = layer;
     p.n_layers = 1;
-    launch_layers(h, p, count_ptr, count_max, rows_set, 1 << 28);
+    return launch_layers(h, p, count_ptr, count_max, rows_set, 1 << 28);
 }
 
 // The whole network body: input conv (planes -> x), residual blocks (conv(x) -> t, conv(t) + x -> x; the last one
 // also emits the value / UBE head features), policy conv (x -> f32 logits).  `upto` < 0: all of it; otherwise only
 // the first `upto` convolutions (debug hook).  Fused: one launch (chunks of conv::MAX_LAYERS layers), else one
-// launch per layer.  Returns the number of launches.
+// launch per layer.  Returns the number of launches, or -1 when a launch was refused.
 static int launch_network(tz_handle* h, const int* count_ptr, int count_max, int upto) {
     NnState* s = h->nn;
     std::vector<conv::Layer> all;
@@ -819,7 +820,7 @@ static int launch_network(tz_handle* h, const int* count_ptr, int count_max, int
         p.n_layers = (int)chunk;
         // a chain cut into several launches (more than MAX_LAYERS layers) cannot keep chunks in flight across the
         // cut: it then runs with one chunk (full-size sets are required, see nn_set_weights)
-        launch_layers(h, p, count_ptr, count_max, s->rows_set, s->chunk_min_tiles);
+        if (launch_layers(h, p, count_ptr, count_max, s->rows_set, s->chunk_min_tiles) != cudaSuccess) return -1;
         first += chunk;
         launches++;
     }
@@ -847,7 +848,12 @@ int nn_forward(tz_handle* h, const TzState* states, const int* count_ptr, int co
     {
         // input, tower and policy convolutions are one launch, so the sampled profile books all of it here
         ProfScope ps(h, TZ_PROF_CONV_TOWER);
-        h->launches += 1 + launch_network(h, count_ptr, count_max, limit);
+        const int launched = launch_network(h, count_ptr, count_max, limit);
+        if (launched < 0) {
+            cudaGetLastError();
+            return TZ_ECUDA;
+        }
+        h->launches += 1 + launched;
     }
     if (limit >= 0) return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
     if (s->simhash_set && s->novelty == 2)
