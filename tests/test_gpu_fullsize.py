@@ -77,3 +77,24 @@ def test_config_6x6_8192_games_256_sims():
 
 def test_config_5x5_20_blocks():
     run_config(5, 4, 512, 16, 128, 2)
+
+
+@pytest.mark.parametrize("n,hk,G", [(3, 0, 1), (3, 0, 3), (4, 4, 5)])
+def test_tiny_batches_play_whole_games_with_the_device_network(n, hk, G):
+    """A handful of games played to the end (and restarted) with the device network: leaf batches of 0..G positions,
+    including lock-steps where every leaf is already known and the fused network launch has nothing to do."""
+    m = capi.BatchedMCTS(n, hk, G, arena_slots=1 << 14)
+    network.set_weights(m, weights.random_init(n, seed=5, blocks=1))
+    m.set_agent(capi.AGENT_NETWORK)
+    m.new_openings(seed=3)
+    finished = 0
+    for mv in range(80):
+        selected = m.gumbel_sequential_halving(None, 4, 16, None, seed=mv)
+        assert m.status() == 0
+        m.step(selected)
+        finished += int((m.restart_terminal_envs(seed=100 + mv) != 0).sum())
+    c = m.counters()
+    assert c.simulations == G * 80 * 17 and c.evaluations + c.known == c.simulations
+    assert finished >= 1 and c.known > 0
+    assert m.status() == 0
+    m.close()
