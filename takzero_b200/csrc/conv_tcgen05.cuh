@@ -30,23 +30,27 @@
 //   t_empty[acc]            leader, count 8: epilogue warps of both CTAs
 // Warp roles per CTA: warps 0-3 epilogue (tcgen05.ld -> bias, residual, ReLU -> stores), warp 4 A producer,
 // warp 5 B producer, warp 6 MMA issuer (leader) / A relay (peer), warp 7 TMEM allocator / B relay (peer).
-// Fused tower: one launch can run a CHAIN of layers (Params::layers[0..n_layers)).  The work items
-// (layer, pair tile) are numbered layer-major and dealt round-robin to the persistent CTA pairs, so a pair gets
-// 15.57 tiles per layer on average instead of a whole number per launch, and the launch gap, prologue and
-// pipeline refill between layers disappear.  A 3x3 tap reaches at most HALO rows into the neighbouring tiles,
-// so item (L, t) depends only on items (L-1, t-1..t+1): the epilogue warps publish every 64 output channels of
-// their tile with a release increment of progress[t][block] and the A producer of a dependent item spins on an
-// acquire load before it fetches that 64-channel block, then crosses to the async proxy with fence.proxy.async
-// before its bulk copies (so the first MMAs of a layer overlap the tail of the previous layer's epilogues).  The same three waits also cover the
-// write-after-read hazards of the two ping-pong activation buffers (a layer's output buffer is the input buffer
-// of the layer before it).  The launch is cooperative: every pair must be resident, or the spin would deadlock.
-// Chunks: the positions of a launch are cut into equal chunks of at least Params::chunk_min_tiles pair tiles and the items are numbered
-// chunk-major, so a chunk runs through ALL its layers before the next one starts.  Activations live in two small
-// ping-pong sets (even / odd chunks) that stay resident in the 126 MB L2 -- the layer-to-layer traffic never
-// reaches HBM, which under the power cap is worth ~7 % of throughput.  Only the input planes, the policy logits
-// and the two head features per row (the value / UBE 1x1 convolutions, folded into the last tower layer's
-// epilogue) use global rows.  A chunk's first layer waits until the chunk two before it has completely finished
-// (chunk_done), because it overwrites that chunk's activation set.
+//
+// Layer chain: one launch runs a CHAIN of layers (Params::layers[0..n_layers)) -- the whole network body: input
+// convolution, residual tower, policy convolution.  The work items (layer, pair tile) are dealt round-robin to the
+// persistent CTA pairs, so a pair gets 15.57 tiles per layer on average instead of a whole number per launch, and
+// the launch gaps, prologues and pipeline refills between layers disappear.  A 3x3 tap reaches at most HALO rows
+// into the neighbouring tiles, so item (L, t) depends only on items (L-1, t-1..t+1): the epilogue warps publish
+// their tile with release increments of progress[t][0..3] (per 64 output channels when a layer has fewer than
+// two tiles per pair, so that the next layer's first MMAs overlap the rest of the epilogue; else once per tile),
+// the A producer of a dependent item spins on an acquire load before it fetches a 64-channel block and crosses to
+// the async proxy with fence.proxy.async before its bulk copies.  The same waits cover the write-after-read
+// hazards of the two ping-pong activation buffers (a layer's output buffer is the input buffer of the layer
+// before it).  The launch is cooperative: every pair must be resident, or the spin would deadlock.
+//
+// Chunks: the positions of a launch are cut into equal chunks of at least Params::chunk_min_tiles pair tiles and
+// the items are numbered chunk-major, so a chunk runs through ALL its layers before the next one starts.
+// Activations live in two small ping-pong sets (even / odd chunks) that stay resident in the 126 MB L2: the
+// layer-to-layer traffic never reaches HBM, which under the power cap is worth ~5 % of throughput.  Only the input
+// planes, the policy logits and the two head features per row (the value / UBE 1x1 convolutions, folded into
+// the last tower layer's epilogue) use rows of all positions.  A chunk's first layer waits until the chunk two
+// before it has completely finished (chunk_done), because it overwrites that chunk's activation set.
+//
 // TZ_DEBUG_TIMING is a compile-time tuning experiment (tools/build_variant.sh); the numbers it produced for
 // the earlier row-major one-CTA / pair kernels are in profiles/r1_conv_timing.txt.
 #pragma once
