@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(32 * WPB) k_lcghash(const TzState* states, con
     if (q >= count) return;
     TzState* st = &s_state[warp];
     warp_load_state(st, &states[q], lane);
-    const int nn = n * n, C = 2 * (2 * n + 3 + 2) + 2;
+    const int C = 2 * (2 * n + 3 + 2) + 2;
     float* x = s_planes[warp];
     warp_fill_planes(x, st, n, half_komi, lane, false);
     const unsigned long long MUL = 6364136223846793005ull;
