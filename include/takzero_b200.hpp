@@ -413,6 +413,14 @@ class BatchedMCTS {
     void set_agent(int kind, tz_agent_fn fn = nullptr, void* ctx = nullptr) { check(tz_set_agent(h_, kind, fn, ctx)); }
     void new_openings(uint64_t seed) { check(tz_new_openings(h_, nullptr, nullptr, nullptr, seed)); }
     void set_positions(const std::vector<tz_state_t>& envs) { check(tz_set_positions(h_, envs.data(), nullptr)); }
+    // only the games with mask[g] != 0: `*node = Node::default(); *env = envs[g]`
+    void set_positions(const std::vector<tz_state_t>& envs, const std::vector<uint8_t>& mask) {
+        check(tz_set_positions(h_, envs.data(), mask.data()));
+    }
+    // the random part of Env::new_opening_with_random_steps (env.rs:81-96) for the masked games (all: empty mask)
+    void random_steps(int steps, uint64_t seed, const std::vector<uint8_t>& mask = {}) {
+        check(tz_random_steps(h_, mask.empty() ? nullptr : mask.data(), steps, seed));
+    }
     std::vector<tz_state_t> envs() const {
         std::vector<tz_state_t> out(games_);
         check(tz_get_positions(h_, out.data()));
