@@ -26,6 +26,7 @@ pub const TZ_STATUS_BAD_MOVE: u32 = 16;
 pub const TZ_STATUS_NAN: u32 = 32;
 pub const TZ_STATUS_SET_EMPTY: u32 = 64;
 pub const TZ_STATUS_REPLAY_FULL: u32 = 128;
+pub const TZ_STATUS_NETWORK_STALL: u32 = 256;
 pub const TZ_AGENT_SYNTHETIC: u32 = 0;
 pub const TZ_AGENT_HOST: u32 = 1;
 pub const TZ_AGENT_NETWORK: u32 = 2;

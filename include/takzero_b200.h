@@ -51,6 +51,8 @@ enum {
     TZ_STATUS_NAN = 32,            /* NaN logit / value (net6_simhash.rs:304) */
     TZ_STATUS_SET_EMPTY = 64,      /* sequential halving on a root without children */
     TZ_STATUS_REPLAY_FULL = 128,
+    TZ_STATUS_NETWORK_STALL = 256, /* a CTA pair of the fused network launch waited > ~1 s for another pair's
+                                      tile (never seen; the watchdog turns a would-be hang into this error) */
 };
 
 /* Move (takparse `Move`, 2 bytes):

@@ -72,6 +72,7 @@ enum {
     TZ_ERR_NAN = 32,
     TZ_ERR_SET_EMPTY = 64,
     TZ_ERR_REPLAY_FULL = 128,
+    TZ_ERR_NETWORK_STALL = 256,
 };
 
 // Device-side view of one handle, passed by value to every kernel.

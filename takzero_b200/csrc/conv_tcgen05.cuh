@@ -118,6 +118,7 @@ struct Params {
                                     // arrivals per tile and 64-channel block of the output (8 per finished
                                     // layer); may be null when n_layers == 1
     unsigned* chunk_done;           // [chunks]: epilogue-warp arrivals of the last layer (8 per tile)
+    unsigned* status;               // the handle's sticky error word (watchdog of the dependency waits)
 };
 
 // work item -> (chunk, layer, pair tile); every role of the kernel walks the same sequence
@@ -208,6 +209,23 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
 }
 __device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Waits until *counter >= need.  Watchdog: the launch is cooperative, so the awaited pair is resident and a wait
+// lasts microseconds; should one ever exceed ~1 s (2^22 polls of >= 0.25 us each), the error bit is raised, every other
+// wait of the launch gives up at once and the host sees TZ_STATUS_NETWORK_STALL instead of a hung GPU.
+constexpr unsigned STALL_BIT = 256;  // TZ_ERR_NETWORK_STALL
+__device__ __forceinline__ void wait_counter(const unsigned* counter, unsigned need, unsigned* status) {
+    unsigned polls = 0;
+    while (ld_acquire_gpu(counter) < need) {
+        __nanosleep(32);
+        if ((++polls & 1023u) == 0) {
+            if (*reinterpret_cast<volatile unsigned*>(status) & STALL_BIT) return;
+            if (polls >= (1u << 22)) {
+                atomicOr(status, STALL_BIT);
+                return;
+            }
+        }
+    }
 }
 // generic-proxy writes (observed through the acquire above) -> async-proxy reads of this thread's bulk copies
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -382,7 +400,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                 if (layer == 0 && it.chunk >= 2 && p.n_layers > 1) {
                     // this chunk's first layer overwrites the activation set of chunk - 2: all of it must be done
                     const unsigned all_warps = 8u * (unsigned)sched.chunk_tiles;
-                    while (ld_acquire_gpu(p.chunk_done + it.chunk - 2) < all_warps) __nanosleep(40);
+                    wait_counter(p.chunk_done + it.chunk - 2, all_warps, p.status);
                 }
                 const int t = pt * 2 + (int)rank;
                 const size_t in_rows = L.in_global ? (size_t)p.rows_global : (size_t)p.rows_set;
@@ -396,8 +414,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                         // fine: wait for this 64-channel block only; else for the whole tile (its last block)
                         const int blk = fine ? kb : 3;
                         for (int q = lo; q <= lo + 1; q++)
-                            if (q >= 0 && q < it.tiles)
-                                while (ld_acquire_gpu(prog + q * 4 + blk) < need) __nanosleep(40);
+                            if (q >= 0 && q < it.tiles) wait_counter(prog + q * 4 + blk, need, p.status);
                         fence_proxy_async();
                     }
                     mbar_wait(a_empty + 8 * stage, phase ^ 1);
