@@ -119,6 +119,7 @@ struct Params {
                                     // layer); may be null when n_layers == 1
     unsigned* chunk_done;           // [chunks]: epilogue-warp arrivals of the last layer (8 per tile)
     unsigned* status;               // the handle's sticky error word (watchdog of the dependency waits)
+    int debug_drop_progress;        // test hook: CTA pair 0 never publishes its tiles (exercises the watchdog)
 };
 
 // work item -> (chunk, layer, pair tile); every role of the kernel walks the same sequence
@@ -646,7 +647,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                         }
                     }
                 }
-                if (p.n_layers > 1 && (fine ? (c0 & 32) != 0 : c0 == N_OUT - 32)) {
+                if (p.n_layers > 1 && (fine ? (c0 & 32) != 0 : c0 == N_OUT - 32) && !(p.debug_drop_progress && pair == 0)) {
                     // 64 more output channels (fine) or the whole tile of this warp's rows are visible device-wide
                     __threadfence();
                     __syncwarp();

@@ -766,6 +766,7 @@ static cudaError_t launch_layers(tz_handle* h, conv::Params& p, const int* count
     p.progress = s->progress;
     p.chunk_done = s->progress + (size_t)chunks * chunk_tiles * 4;
     p.status = h->d.status;
+    p.debug_drop_progress = getenv("TZ_EXP_DROP_PROGRESS") != nullptr;  // watchdog test only
     const long long items = (long long)all_tiles * p.n_layers;
     const int pairs = items < s->max_pairs ? (items > 0 ? (int)items : 1) : s->max_pairs;
     cudaLaunchConfig_t cfg = {};

@@ -232,6 +232,37 @@ def test_chunked_fused_launch_equals_one_chunk_and_per_layer_launches(n, hk, cou
     assert float(np.abs(outs["chunks"][1] - want_values).max()) <= TOL
 
 
+def test_watchdog_turns_a_stalled_dependency_into_a_status_bit(monkeypatch):
+    """The fused launch waits on other CTA pairs' progress counters.  With the test hook that makes pair 0 withhold
+    its tiles, the dependent pairs must not spin forever: the watchdog raises TZ_STATUS_NETWORK_STALL (256), the
+    launch ends, and the handle reports the error instead of hanging the GPU."""
+    import time
+
+    n, hk, count = 4, 4, 256
+    ref = net_ref.Net(n, seed=2, blocks=2)
+    games = sample_positions(n, hk, count, 5)
+    actions = [O.possible_moves(g) for g in games]
+    m = capi.BatchedMCTS(n, hk, count, arena_slots=4096)
+    network.set_weights(m, ref.tensors())
+    good = network.evaluate(m, games_to_states(games), actions)
+    assert m.status() == 0
+    monkeypatch.setenv("TZ_EXP_DROP_PROGRESS", "1")
+    t0 = time.perf_counter()
+    try:
+        network.evaluate(m, games_to_states(games), actions)
+    except capi.TakzeroError:
+        pass
+    assert time.perf_counter() - t0 < 60.0
+    assert m.status() & 256
+    m.close()
+    monkeypatch.delenv("TZ_EXP_DROP_PROGRESS")
+    m = capi.BatchedMCTS(n, hk, count, arena_slots=4096)  # a fresh handle works as before
+    network.set_weights(m, ref.tensors())
+    again = network.evaluate(m, games_to_states(games), actions)
+    assert m.status() == 0 and np.array_equal(good[1], again[1])
+    m.close()
+
+
 def test_load_model_from_tch_archive_with_bitvec_sidecar(tmp_path):
     """Net::load (network/mod.rs:20-27, net6_simhash.rs:164-181) from the reference's own files: a tch-named
     `model_latest.ot` plus the `bitvec.bin` SimHash set beside it give exactly the outputs of tz_set_weights +
