@@ -252,7 +252,8 @@ TZ_API int tz_set_weights(tz_handle* h, const tz_tensor_t* tensors, int count);
 /* Net::load (network/mod.rs:20-27, net6_simhash.rs:164-181) from the reference's own model file: `path` is a tch
  * `VarStore::save` archive (`model_latest.ot`, written by learn/src/main.rs:166,257 and re-read before every move
  * by selfplay/src/main.rs:107 and reanalyze/src/main.rs:93), parsed here without libtorch (ZIP + pickle); a
- * `torch.save` state dict or this repository's TZW1 container work too.  tch variable names are mapped to the
+ * `torch.save` state dict, a safetensors file (what tch writes for a ".safetensors" path) or this repository's
+ * TZW1 container work too.  tch variable names are mapped to the
  * names above: the two SmallBlocks of a ResidualBlock share one path (residual.rs:52-54), so the file holds
  * `core.res_block_B.conv2d.weight` (block half 0) and `core.res_block_B.conv2d.weight__K` (half 1).  When the file
  * has a `simhash_matrix`, it and the sidecar `bitvec.bin` next to the file (absent = empty set) go through

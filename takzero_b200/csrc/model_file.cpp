@@ -8,13 +8,15 @@
 // pickle of the module object whose state dict maps every variable name to
 // `torch._utils._rebuild_tensor_v2(storage, offset, shape, stride, ...)` -- and one raw little-endian blob
 // `<stem>/data/<key>` per storage.  `torch.save(state_dict)` files have the same layout (`data.pkl` is the dict),
-// so both are accepted, as is this repository's own TZW1 container (takzero_b200/weights.py::save_tzw).
+// so both are accepted, as are safetensors files (what tch writes when the path ends in ".safetensors") and this
+// repository's own TZW1 container (takzero_b200/weights.py::save_tzw).
 //
 // Host-only code: a ZIP central-directory walk, a small pickle stack machine (the opcodes libtorch and
 // `torch.save` emit) and a strided gather to contiguous f32.
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -487,12 +489,169 @@ std::vector<NamedTensor> read_tzw(const std::vector<uint8_t>& b, const std::stri
     return out;
 }
 
+// ---- safetensors (what tch's `VarStore::save` writes for a path ending in ".safetensors") -------------------------
+// u64 little-endian header length, a JSON object {"name": {"dtype": "F32", "shape": [..], "data_offsets": [a, b]},
+// ..., "__metadata__": {..}}, then the raw little-endian tensor bytes.  Only what that format needs of JSON.
+struct Json {
+    const char* p;
+    const char* end;
+    void ws() {
+        while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) p++;
+    }
+    char peek() {
+        ws();
+        if (p >= end) throw Fail("safetensors header: unexpected end");
+        return *p;
+    }
+    void expect(char c) {
+        if (peek() != c) throw Fail(std::string("safetensors header: expected '") + c + "'");
+        p++;
+    }
+    std::string string() {
+        expect('"');
+        std::string out;
+        while (p < end && *p != '"') {
+            if (*p == '\\' && p + 1 < end) {
+                p++;
+                if (*p == 'u') {  // names are ASCII in practice: keep \uXXXX below 0x80, replace the rest
+                    if (p + 4 >= end) throw Fail("safetensors header: bad escape");
+                    const unsigned v = (unsigned)std::strtoul(std::string(p + 1, p + 5).c_str(), nullptr, 16);
+                    out += v < 0x80 ? (char)v : '?';
+                    p += 5;
+                    continue;
+                }
+                out += *p == 'n' ? '\n' : *p == 't' ? '\t' : *p;
+                p++;
+                continue;
+            }
+            out += *p++;
+        }
+        expect('"');
+        return out;
+    }
+    long long integer() {
+        ws();
+        char* e = nullptr;
+        const long long v = std::strtoll(p, &e, 10);
+        if (e == p) throw Fail("safetensors header: number expected");
+        p = e;
+        return v;
+    }
+    void skip_value() {  // any JSON value
+        const char c = peek();
+        if (c == '"') {
+            string();
+        } else if (c == '{' || c == '[') {
+            const char close = c == '{' ? '}' : ']';
+            p++;
+            while (peek() != close) {
+                if (c == '{') {
+                    string();
+                    expect(':');
+                }
+                skip_value();
+                if (peek() == ',') p++;
+            }
+            p++;
+        } else {
+            while (p < end && *p != ',' && *p != '}' && *p != ']') p++;
+        }
+    }
+};
+
+std::vector<NamedTensor> read_safetensors(const std::vector<uint8_t>& b, const std::string& path) {
+    if (b.size() < 8) throw Fail(path + ": truncated");
+    const uint64_t hlen = le<uint64_t>(b.data());
+    if (hlen > b.size() - 8) throw Fail(path + ": safetensors header out of range");
+    const uint8_t* data = b.data() + 8 + hlen;
+    const uint64_t data_len = b.size() - 8 - hlen;
+    Json j{(const char*)b.data() + 8, (const char*)b.data() + 8 + hlen};
+    struct Entry {
+        NamedTensor t;
+        uint64_t begin;
+    };
+    std::vector<Entry> entries;
+    j.expect('{');
+    while (j.peek() != '}') {
+        const std::string name = j.string();
+        j.expect(':');
+        if (name == "__metadata__") {
+            j.skip_value();
+        } else {
+            std::string dtype;
+            std::vector<int64_t> shape;
+            long long begin = -1, stop = -1;
+            j.expect('{');
+            while (j.peek() != '}') {
+                const std::string key = j.string();
+                j.expect(':');
+                if (key == "dtype") {
+                    dtype = j.string();
+                } else if (key == "shape") {
+                    j.expect('[');
+                    while (j.peek() != ']') {
+                        shape.push_back(j.integer());
+                        if (j.peek() == ',') j.p++;
+                    }
+                    j.expect(']');
+                } else if (key == "data_offsets") {
+                    j.expect('[');
+                    begin = j.integer();
+                    j.expect(',');
+                    stop = j.integer();
+                    j.expect(']');
+                } else {
+                    j.skip_value();
+                }
+                if (j.peek() == ',') j.p++;
+            }
+            j.expect('}');
+            const int esize = dtype == "F32" || dtype == "I32" ? 4 : dtype == "F64" || dtype == "I64" ? 8
+                              : dtype == "F16" || dtype == "BF16" ? 2 : 0;
+            size_t numel = 1;
+            for (int64_t d : shape) {
+                if (d < 0 || (numel *= (size_t)d) > (size_t(1) << 34)) throw Fail(path + ": bad shape of " + name);
+            }
+            if (esize != 0) {
+                if (begin < 0 || stop < begin || (uint64_t)stop > data_len || (uint64_t)(stop - begin) != numel * (uint64_t)esize)
+                    throw Fail(path + ": data_offsets of " + name + " do not match its shape");
+                Entry e;
+                e.t.name = name;
+                e.t.shape = shape;
+                e.t.data.resize(numel);
+                const uint8_t* q = data + begin;
+                for (size_t k = 0; k < numel; k++, q += esize) {
+                    float v;
+                    if (dtype == "F32") v = le<float>(q);
+                    else if (dtype == "F64") v = (float)le<double>(q);
+                    else if (dtype == "F16") v = half_to_float(le<uint16_t>(q));
+                    else if (dtype == "BF16") { const uint32_t w = (uint32_t)le<uint16_t>(q) << 16; std::memcpy(&v, &w, 4); }
+                    else if (dtype == "I64") v = (float)le<int64_t>(q);
+                    else v = (float)le<int32_t>(q);
+                    e.t.data[k] = v;
+                }
+                e.begin = (uint64_t)begin;
+                entries.push_back(std::move(e));
+            }
+        }
+        if (j.peek() == ',') j.p++;
+    }
+    // file order = order of the data, as a reader of the raw bytes sees the tensors
+    std::stable_sort(entries.begin(), entries.end(), [](const Entry& a, const Entry& c) { return a.begin < c.begin; });
+    std::vector<NamedTensor> out;
+    for (Entry& e : entries) out.push_back(std::move(e.t));
+    if (out.empty()) throw Fail(path + ": no tensors found");
+    return out;
+}
+
 std::vector<NamedTensor> read_model(const std::string& path) {
     Archive ar;
     ar.bytes = read_file(path);
     if (ar.bytes.size() >= 8 && std::memcmp(ar.bytes.data(), "TZW1", 4) == 0) return read_tzw(ar.bytes, path);
+    if (ar.bytes.size() >= 10 && ar.bytes[8] == '{' && le<uint64_t>(ar.bytes.data()) <= ar.bytes.size() - 8)
+        return read_safetensors(ar.bytes, path);
     if (ar.bytes.size() < 4 || le<uint32_t>(ar.bytes.data()) != 0x04034b50u)
-        throw Fail(path + ": neither a libtorch archive (.ot / .pt zip) nor a TZW1 file");
+        throw Fail(path + ": neither a libtorch archive (.ot / .pt zip), a safetensors file nor a TZW1 file");
     ar.entries = zip_entries(ar.bytes);
     const ZipEntry* pkl = ar.find_suffix("/data.pkl", "data.pkl");
     if (!pkl || pkl->size == UINT64_MAX) throw Fail(path + ": no data.pkl in the archive");

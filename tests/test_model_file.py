@@ -101,3 +101,29 @@ def test_bad_files_fail_with_a_message(tmp_path):
     (tmp_path / "cut.tzw").write_bytes(b"TZW1" + (3).to_bytes(4, "little") + b"\x05\x00\x00\x00ab")
     with pytest.raises(capi.TakzeroError, match="truncated"):
         network.read_model_file(str(tmp_path / "cut.tzw"))
+
+
+def test_safetensors_files(tmp_path):
+    """tch's `VarStore::save` writes safetensors when the path ends in ".safetensors": u64 header length, JSON header,
+    raw little-endian data.  Read by the same entry point, names mapped like the `.ot` ones."""
+    from safetensors.numpy import save_file
+    from safetensors.torch import save_file as save_torch
+
+    w = weights.random_init(4, seed=3, blocks=2)
+    save_file({k: np.ascontiguousarray(v) for k, v in weights.tch_names(w).items()}, str(tmp_path / "m.safetensors"),
+              metadata={"format": "pt", "note": 'a "quoted" value, {braces} and [brackets]'})
+    got = network.read_model_file(str(tmp_path / "m.safetensors"))
+    assert set(got) == set(w)
+    for k in w:
+        assert got[k].shape == w[k].shape and np.array_equal(got[k], w[k]), k
+    t = {"h": torch.randn(5).half(), "b": torch.randn(2, 3).bfloat16(), "d": torch.randn(3).double(),
+         "i": torch.arange(4), "e": torch.zeros(0), "s": torch.tensor(1.5)}
+    save_torch(t, str(tmp_path / "t.safetensors"))
+    got = network.read_model_file(str(tmp_path / "t.safetensors"))
+    assert set(got) == set(t)
+    for k, v in t.items():
+        assert got[k].shape == tuple(v.shape) and np.array_equal(got[k], v.float().numpy()), k
+    blob = open(tmp_path / "m.safetensors", "rb").read()
+    (tmp_path / "cut.safetensors").write_bytes(blob[: len(blob) - 1000])
+    with pytest.raises(capi.TakzeroError, match="data_offsets"):
+        network.read_model_file(str(tmp_path / "cut.safetensors"))
