@@ -574,4 +574,59 @@ class BatchedMCTS {
     int n_, games_, stride_ = 0;
 };
 
+// ---- `impl Display for Node` (search/node/debug.rs:11-95): the table the `analysis` REPL prints -------------------
+
+inline std::string center(const std::string& s, size_t width) {  // Rust `{: ^width}`: the odd space goes right
+    if (s.size() >= width) return s;
+    const size_t pad = width - s.size(), left = pad / 2;
+    return std::string(left, ' ') + s + std::string(pad - left, ' ');
+}
+inline std::string fixed4(float v, bool plus) {  // `{:.4}` / `{:+.4}` of an f32
+    char buf[64];
+    std::snprintf(buf, sizeof(buf), plus ? "%+.4f" : "%.4f", (double)v);
+    return buf;
+}
+inline std::string eval_display(uint32_t tag, uint32_t bits) {  // `{:+.4}` of an Eval (eval.rs:15-24)
+    if (tag == 0) {
+        float v;
+        std::memcpy(&v, &bits, 4);
+        return fixed4(v, true);
+    }
+    return std::string(tag == 1 ? "Win(" : tag == 2 ? "Loss(" : "Draw(") + std::to_string(bits) + ")";
+}
+// game `g` of the handle: children sorted by visit count (stable), one `ActionInfo` row each, header, node line
+inline std::string node_display(BatchedMCTS& mcts, int g = 0) {
+    const BatchedMCTS::Children ch = mcts.root_children();
+    const std::vector<tz_root_t> roots = mcts.root_stats();
+    const tz_root_t& root = roots[g];
+    std::string out;
+    float std_dev;
+    std::memcpy(&std_dev, &root.std_dev_bits, 4);
+    const size_t base = (size_t)g * ch.stride;
+    const int n = ch.n[g];
+    if (n == 0 && root.eval_tag == 0) {  // needs_initialization: no children and not known
+        out += "--- This node still needs to be initialized! ---\n";
+    } else {
+        const BatchedMCTS::RootTargets rt = mcts.targets(-1.0f, 0.0f);  // improved_policy(most_visited_count())
+        std::vector<int> order(n);
+        for (int i = 0; i < n; i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ch.visits[base + a] < ch.visits[base + b]; });
+        const float parent = (float)root.visit_count;
+        // exploration_rate(N) * P * sqrt(N) / (1 + n)   (policy.rs:143-156)
+        const float rate = std::log((1.0f + parent + 500.0f) / 500.0f) + 4.0f;
+        for (int i : order) {
+            const float puct = rate * ch.prob[base + i] * std::sqrt(parent) / (1.0f + (float)ch.visits[base + i]);
+            out += center(move_to_string(ch.moves[base + i]), 10) + ' ' + center(std::to_string(ch.visits[base + i]), 9) + ' ' +
+                   center(fixed4(ch.logit[base + i], true), 9) + ' ' + center(fixed4(ch.prob[base + i], false), 9) + ' ' +
+                   center(fixed4(rt.policy[base + i], false), 9) + ' ' + center(fixed4(puct, false), 8) + ' ' +
+                   center(fixed4(ch.std_dev[base + i], false), 9) + ' ' +
+                   center(eval_display(ch.eval_tag[base + i], ch.eval_bits[base + i]), 14) + '\n';
+        }
+        out += "[ action ] [ count ] [ logit ] [ proba ] [ impol ] [ puct ] [ stdev ] [ evaluation ]\n";
+    }
+    out += "((node))  [count: " + std::to_string(root.visit_count) + "]  [std_dev: " + fixed4(std_dev, false) +
+           "]  [eval: " + eval_display(root.eval_tag, root.eval_bits) + "]\n";
+    return out;
+}
+
 }  // namespace takzero

@@ -64,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
-HOSTS = ["selfplay", "reanalyze", "evaluation", "tei", "format_check"]
+HOSTS = ["selfplay", "reanalyze", "evaluation", "tei", "analysis", "format_check"]
 
 
 def build_hosts() -> None:
