@@ -419,12 +419,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                         fence_proxy_async();
                     }
                     mbar_wait(a_empty + 8 * stage, phase ^ 1);
+#ifdef TZ_EXP_DOUBLE_A  // energy experiment: every activation block is fetched twice
+                    mbar_arrive_expect_tx(a_sig + 8 * stage, 2 * A_STAGE_BYTES);
+#else
                     mbar_arrive_expect_tx(a_sig + 8 * stage, A_STAGE_BYTES);
+#endif
                     const uint32_t dst = smem_u32(a_smem + stage * A_STAGE_BYTES);
 #pragma unroll
                     for (int kc = 0; kc < 8; kc++)
                         bulk_g2s(dst + kc * A_KC_BYTES, src_tile + (size_t)(kb * 8 + kc) * in_rows * 16, A_KC_BYTES,
                                  a_sig + 8 * stage);
+#ifdef TZ_EXP_DOUBLE_A
+#pragma unroll
+                    for (int kc = 0; kc < 8; kc++)
+                        bulk_g2s(dst + kc * A_KC_BYTES, src_tile + (size_t)(kb * 8 + kc) * in_rows * 16, A_KC_BYTES,
+                                 a_sig + 8 * stage);
+#endif
                     if (++stage == A_STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -442,8 +452,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                 const int blocks = (L.cin >> 6) * 9;
                 for (int blk = 0; blk < blocks; blk++) {
                     mbar_wait(b_empty + 8 * stage, phase ^ 1);
-#ifdef TZ_EXP_NO_B  // energy experiment (INVALID results): only the first B_STAGES weight blocks are ever copied
+#if defined(TZ_EXP_NO_B) || defined(TZ_EXP_HALF_B)
+                    // energy experiments (INVALID results): only the first B_STAGES weight blocks are ever copied
+                    // (NO_B), or every other one (HALF_B)
+#ifdef TZ_EXP_HALF_B
+                    if (blk & 1) {
+#else
                     if (item != pair || blk >= B_STAGES) {
+#endif
                         mbar_arrive(b_sig + 8 * stage);
                     } else
 #endif

@@ -200,9 +200,29 @@ __device__ __forceinline__ void warp_expand(const TzDev& d, int g, int q, const 
     const uint16_t* act = d.actions + (size_t)q * d.M;
     for (int i = lane; i < n; i += 32) p[i] = lg[i];
     __syncwarp();
-    const float value = d.value[q], variance = d.variance[q];
-    if (!warp_softmax_inplace(p, n, lane) || value != value || variance != variance)
+    float value = d.value[q], variance = d.variance[q];
+    // NaN / infinite network outputs: the reference panics (net6_simhash.rs:304, NotNan).  Here the error bit is
+    // raised and the outputs are replaced by finite ones (uniform priors, zero logits / value / variance), so that no
+    // NaN ever enters a tree: comparisons against NaN would derail the argmax / ranking code that indexes the arena.
+    bool priors_ok = warp_softmax_inplace(p, n, lane);
+    {
+        bool finite = true;
+        for (int i = lane; i < n; i += 32) finite = finite && p[i] >= 0.0f && p[i] <= 1.0f;  // false for NaN
+        priors_ok = priors_ok && __all_sync(FULL_MASK, finite);
+    }
+    const bool value_ok = fabsf(value) <= 3.0e38f && variance >= 0.0f && variance <= 3.0e38f;  // false for NaN
+    if (!priors_ok || !value_ok) {
         flag_error(d, TZ_ERR_NAN, lane);
+        if (!priors_ok) {
+            const float uniform = fdiv(1.0f, (float)(n > 0 ? n : 1));
+            for (int i = lane; i < n; i += 32) p[i] = uniform;
+            __syncwarp();
+        }
+        if (!value_ok) {
+            value = 0.0f;
+            variance = 0.0f;
+        }
+    }
 
     // leaf: running mean / std (mcts.rs:190-197); the leaf's evaluation is a Value here
     const uint32_t leaf = traj[len - 1];
@@ -235,7 +255,7 @@ __device__ __forceinline__ void warp_expand(const TzDev& d, int g, int q, const 
         t.visits[c] = 0;
         t.prob[c] = p[i];
         t.std_dev[c] = sd;
-        t.logit[c] = lg[i];
+        t.logit[c] = priors_ok ? lg[i] : 0.0f;
         t.first[c] = 0;
     }
     if (lane == 0) {

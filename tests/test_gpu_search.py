@@ -274,3 +274,32 @@ def test_single_game_and_odd_batch_sizes():
         assert list(got) == want
         assert_roots_equal(m, ob, f"G={G}")
         m.close()
+
+
+def test_nan_and_infinite_network_outputs_raise_the_nan_bit_without_faulting():
+    """The reference panics on a NaN logit / value (net6_simhash.rs:304, NotNan).  Here the device raises
+    TZ_STATUS_NAN and replaces the outputs by finite ones before anything enters a tree -- a NaN in the arena would
+    derail the argmax / ranking code that indexes it (this used to end in a CUDA `misaligned address` fault)."""
+    n, hk, G = 4, 4, 8
+    m = capi.BatchedMCTS(n, hk, G, arena_slots=1 << 14)
+    calls = [0]
+
+    def cb(ctx, batch, envs, actions, n_actions, stride, logits, values, variances):
+        calls[0] += 1
+        lg = np.ctypeslib.as_array(logits, shape=(batch, stride))
+        lg[:] = 0.1
+        if calls[0] >= 3:
+            lg[0::2, 0] = np.nan
+            lg[1::2, :] = np.inf
+        np.ctypeslib.as_array(values, shape=(batch,))[:] = np.nan if calls[0] >= 5 else 0.2
+        np.ctypeslib.as_array(variances, shape=(batch,))[:] = -1.0 if calls[0] >= 7 else 1.0
+
+    m.set_agent(capi.AGENT_HOST, cb)
+    m.new_openings(seed=1)
+    with pytest.raises(capi.TakzeroError, match="nan"):
+        m.gumbel_sequential_halving(None, 8, 24, None, seed=0)
+    assert m.status() == 32  # TZ_STATUS_NAN only: no other invariant broke, no CUDA error
+    assert calls[0] >= 20    # the search ran to the end
+    tbl = m.root_children()
+    assert np.isfinite(tbl["prob"]).all() and np.isfinite(tbl["logit"]).all() and np.isfinite(tbl["std_dev"]).all()
+    m.close()
