@@ -976,10 +976,17 @@ __global__ void __launch_bounds__(32 * WPB) k_set_root_priors(TzDev d, int strid
     int n = (int)tz_meta_nchild(t.meta[0]);
     if (n > stride) n = stride;
     const uint32_t first = t.first[0];
+    bool bad = false;
     for (int i = lane; i < n; i += 32) {
-        t.prob[first + i] = prob[(size_t)g * stride + i];
-        t.logit[first + i] = logit[(size_t)g * stride + i];
+        const float p = prob[(size_t)g * stride + i], l = logit[(size_t)g * stride + i];
+        if (p != p || l != l || p < 0.0f) {  // NotNan in the reference; -inf logits (ln 0) are fine
+            bad = true;
+            continue;
+        }
+        t.prob[first + i] = p;
+        t.logit[first + i] = l;
     }
+    if (__any_sync(FULL_MASK, bad)) flag_error(d, TZ_ERR_NAN, lane);
 }
 
 // ---- rules parity hooks --------------------------------------------------------------------
