@@ -377,7 +377,9 @@ __global__ void __launch_bounds__(32 * WPB) k_gumbel_init(TzDev d, int k, const 
     for (int i = lane; i < n; i += 32) {
         const float key = fadd(t.logit[first + i], gumbel[(size_t)g * stride + i]);
         bad = bad || key != key;
-        keys[i] = key;
+        // a NaN key (NaN noise, or -inf logit + inf noise) would give several children the same rank and leave
+        // slots of the candidate set unwritten: order it last instead (the error bit is raised below)
+        keys[i] = key != key ? -__int_as_float(0x7f800000) : key;
     }
     if (__any_sync(FULL_MASK, bad)) flag_error(d, TZ_ERR_NAN, lane);
     __syncwarp();
@@ -413,7 +415,9 @@ __global__ void __launch_bounds__(32 * WPB) k_halve(TzDev d, const float* betas,
             const float q = ev_notnan(ev_negate(node_eval(t, c)));
             // sigma_select (policy.rs:121-128)
             const float sig = fmul(fadd(q, fmul(t.std_dev[c], beta)), fadd(50.0f, visits));
-            keys[j] = fadd(base[r], sig);
+            const float key = fadd(base[r], sig);
+            if (key != key) flag_error(d, TZ_ERR_NAN, 0);  // e.g. a NaN beta from the host
+            keys[j] = key != key ? -__int_as_float(0x7f800000) : key;
         }
     }
     __syncwarp();

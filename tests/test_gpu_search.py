@@ -303,3 +303,24 @@ def test_nan_and_infinite_network_outputs_raise_the_nan_bit_without_faulting():
     tbl = m.root_children()
     assert np.isfinite(tbl["prob"]).all() and np.isfinite(tbl["logit"]).all() and np.isfinite(tbl["std_dev"]).all()
     m.close()
+
+
+def test_nan_noise_and_betas_from_the_host_are_reported_not_fatal():
+    """Injected Gumbel noise / betas are host data: a NaN in them must end in TZ_STATUS_NAN with a complete
+    candidate set, not in colliding ranks and stale child indices."""
+    n, hk, G = 4, 4, 8
+    m = capi.BatchedMCTS(n, hk, G, arena_slots=1 << 14)
+    m.new_openings(seed=2)
+    gumbel = np.random.default_rng(0).gumbel(size=(G, m.move_stride)).astype(np.float32)
+    gumbel[::2, :6] = np.nan
+    with pytest.raises(capi.TakzeroError, match="nan"):
+        m.gumbel_sequential_halving(None, 8, 24, gumbel)
+    assert m.status() == 32
+    m.close()
+    m = capi.BatchedMCTS(n, hk, G, arena_slots=1 << 14)
+    m.new_openings(seed=2)
+    betas = np.full(G, np.nan, dtype=np.float32)
+    with pytest.raises(capi.TakzeroError, match="nan"):
+        m.gumbel_sequential_halving(betas, 8, 24, None, seed=1)
+    assert m.status() == 32
+    m.close()
