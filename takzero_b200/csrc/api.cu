@@ -64,6 +64,36 @@ static cudaError_t dmalloc(tz_handle* h, T** p, size_t count) {
     return e;
 }
 
+// Host states come from outside (the reference's `Game` cannot hold an impossible position; a C struct can):
+// refuse anything the device code does not expect -- stacks taller than the 64-bit colour mask, unknown piece
+// types, pieces outside the board, more pieces than a player owns.  Returns the index of the first bad state or -1.
+static int first_invalid_state(const tz_state_t* states, int count, int n, const uint8_t* mask = nullptr) {
+    static const int STONES[7] = {0, 0, 0, 10, 15, 21, 30}, CAPS[7] = {0, 0, 0, 0, 0, 1, 1};
+    const int nn = n * n;
+    for (int i = 0; i < count; i++) {
+        if (mask && !mask[i]) continue;
+        const tz_state_t& s = states[i];
+        bool ok = s.to_move <= 1 && s.stones[0] <= STONES[n] && s.stones[1] <= STONES[n] && s.caps[0] <= CAPS[n] &&
+                  s.caps[1] <= CAPS[n];
+        int pieces = 0;
+        for (int sq = 0; sq < TZ_MAX_SQ && ok; sq++) {
+            if (sq >= nn) {
+                ok = s.height[sq] == 0;
+            } else if (s.height[sq] > 0) {
+                ok = s.height[sq] <= 64 && s.top[sq] <= 2;
+                pieces += s.height[sq];
+            }
+        }
+        if (!ok || pieces > 2 * (STONES[n] + CAPS[n])) return i;
+    }
+    return -1;
+}
+#define CHECK_STATES(states, count, mask)                                                           \
+    do {                                                                                            \
+        const int bad_ = first_invalid_state((states), (count), h->d.n, (mask));                     \
+        if (bad_ >= 0) return fail(TZ_EINVAL, "state %d is not a possible position of this board", bad_); \
+    } while (0)
+
 static int default_stride(int n) { return n <= 3 ? 128 : n == 4 ? 256 : n == 5 ? 512 : 1024; }
 
 extern "C" TZ_API int tz_create(const tz_config_t* cfg, tz_handle** out) {
@@ -304,6 +334,7 @@ extern "C" TZ_API int tz_legal_moves(tz_handle* h, const tz_state_t* states, int
                               int* out_n) {
     CHECK_H(h);
     if (!states || count < 0 || stride <= 0 || !out_moves || !out_n) return fail(TZ_EINVAL, "bad argument");
+    if (count > 0) CHECK_STATES(states, count, nullptr);
     if (count == 0) return TZ_OK;
     Scratch s;
     TzState* ds;
@@ -324,6 +355,7 @@ extern "C" TZ_API int tz_legal_moves(tz_handle* h, const tz_state_t* states, int
 extern "C" TZ_API int tz_result(tz_handle* h, const tz_state_t* states, int count, int* out_terminal) {
     CHECK_H(h);
     if (!states || count < 0 || !out_terminal) return fail(TZ_EINVAL, "bad argument");
+    if (count > 0) CHECK_STATES(states, count, nullptr);
     if (count == 0) return TZ_OK;
     Scratch s;
     TzState* ds;
@@ -341,6 +373,7 @@ extern "C" TZ_API int tz_result(tz_handle* h, const tz_state_t* states, int coun
 extern "C" TZ_API int tz_game_result(tz_handle* h, const tz_state_t* states, int count, int* out_result) {
     CHECK_H(h);
     if (!states || count < 0 || !out_result) return fail(TZ_EINVAL, "bad argument");
+    if (count > 0) CHECK_STATES(states, count, nullptr);
     if (count == 0) return TZ_OK;
     Scratch s;
     TzState* ds;
@@ -358,6 +391,7 @@ extern "C" TZ_API int tz_game_result(tz_handle* h, const tz_state_t* states, int
 extern "C" TZ_API int tz_apply(tz_handle* h, tz_state_t* states, const tz_move_t* moves, int count, int* out_ok) {
     CHECK_H(h);
     if (!states || !moves || count < 0) return fail(TZ_EINVAL, "bad argument");
+    if (count > 0) CHECK_STATES(states, count, nullptr);
     if (count == 0) return TZ_OK;
     Scratch s;
     TzState* ds;
@@ -390,6 +424,7 @@ static int upload_mask(tz_handle* h, const uint8_t* mask, const uint8_t** dmask)
 extern "C" TZ_API int tz_set_positions(tz_handle* h, const tz_state_t* states, const uint8_t* mask) {
     CHECK_H(h);
     if (!states) return fail(TZ_EINVAL, "null states");
+    CHECK_STATES(states, h->d.G, mask);
     const uint8_t* dmask;
     int rc = upload_mask(h, mask, &dmask);
     if (rc) return rc;
@@ -802,6 +837,7 @@ extern "C" TZ_API int tz_evaluate(tz_handle* h, const tz_state_t* states, int co
     const TzDev& d = h->d;
     if (!nn_ready(h)) return fail(TZ_ENOWEIGHTS, "tz_evaluate needs tz_set_weights first");
     if (!states || !actions || !n_actions || !logits || !values || !variances) return fail(TZ_EINVAL, "null argument");
+    if (count > 0) CHECK_STATES(states, count, nullptr);
     if (count <= 0 || count > d.Q) return fail(TZ_EINVAL, "count must be 1..max(n_games, tree_batch)");
     if (stride != d.M) return fail(TZ_EINVAL, "stride must equal move_stride (%d)", d.M);
     for (int i = 0; i < count; i++)
@@ -823,6 +859,7 @@ extern "C" TZ_API int tz_evaluate(tz_handle* h, const tz_state_t* states, int co
 extern "C" TZ_API int tz_encode_planes(tz_handle* h, const tz_state_t* states, int count, float* out) {
     CHECK_H(h);
     if (!states || !out || count < 0) return fail(TZ_EINVAL, "bad argument");
+    if (count > 0) CHECK_STATES(states, count, nullptr);
     if (count == 0) return TZ_OK;
     const int n = h->d.n, C = 2 * (2 * n + 3 + 2) + 2;
     Scratch s;
@@ -988,6 +1025,7 @@ extern "C" TZ_API int tz_set_simhash(tz_handle* h, const float* matrix, const ui
 extern "C" TZ_API int tz_simhash_indices(tz_handle* h, const tz_state_t* states, int count, uint32_t* out) {
     CHECK_H(h);
     if (!states || !out || count <= 0) return fail(TZ_EINVAL, "bad argument");
+    if (count > 0) CHECK_STATES(states, count, nullptr);
     Scratch s;
     TzState* ds;
     uint32_t* dout;
@@ -1014,6 +1052,7 @@ extern "C" TZ_API int tz_set_lcghash(tz_handle* h, const float* init, const uint
 extern "C" TZ_API int tz_lcghash_indices(tz_handle* h, const tz_state_t* states, int count, uint32_t* out) {
     CHECK_H(h);
     if (!states || !out || count <= 0) return fail(TZ_EINVAL, "bad argument");
+    if (count > 0) CHECK_STATES(states, count, nullptr);
     Scratch s;
     TzState* ds;
     uint32_t* dout;

@@ -107,3 +107,28 @@ def test_random_steps_are_legal_playouts(handles):
         prev = cur
     assert len({bytes(p["height"]) for p in prev}) > 20  # the games diverged
     m.close()
+
+
+def test_impossible_host_states_are_refused():
+    """A `tz_state_t` can describe what the reference's `Game` cannot (a C struct has no invariants): stacks taller
+    than the 64-bit colour mask, unknown piece types, pieces off the board.  Refused at the ABI with TZ_EINVAL."""
+    n = 5
+    m = capi.BatchedMCTS(n, 4, 4, arena_slots=4096)
+    good = m.positions()
+    assert m.legal_moves(good)[1].min() > 0
+    for field, sq, value in (("height", 3, 65), ("top", 3, 7), ("height", 30, 1), ("to_move", None, 2), ("caps", 0, 9)):
+        bad = good.copy()
+        if field in ("height", "top"):
+            bad["height"][1, sq] = max(1, int(bad["height"][1, sq]))
+            bad[field][1, sq] = value
+        elif field == "caps":
+            bad["caps"][1, 0] = value
+        else:
+            bad[field][1] = value
+        with pytest.raises(capi.TakzeroError, match="state 1 is not a possible position"):
+            m.legal_moves(bad)
+        with pytest.raises(capi.TakzeroError, match="state 1 is not a possible position"):
+            m.set_positions(bad)
+    m.set_positions(good)
+    assert m.status() == 0
+    m.close()
