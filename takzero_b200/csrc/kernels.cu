@@ -510,8 +510,20 @@ __device__ __forceinline__ void copy_node(const GameTree& dst, uint32_t to, cons
     dst.first[to] = src.first[from];
 }
 
+// `Game::play` of a move that came from the host: legal iff it is one of `possible_moves` (warp_apply itself
+// trusts its move, as the search only ever applies generated ones).  Leaves the position untouched when illegal.
+__device__ __forceinline__ bool warp_apply_checked(TzState* st, int n, uint16_t mv, uint16_t* scratch, int lane) {
+    const int cnt = warp_movegen(st, n, scratch, lane);
+    __syncwarp();
+    bool found = false;
+    for (int i = lane; i < cnt; i += 32) found = found || scratch[i] == mv;
+    if (!__any_sync(FULL_MASK, found)) return false;
+    return warp_apply(st, n, mv, lane);
+}
+
 __global__ void __launch_bounds__(32 * WPB) k_step(TzDev d, const uint16_t* moves, int only_game) {
     __shared__ TzState s_state[WPB];
+    __shared__ uint16_t s_moves[WPB][TZ_MAX_MOVES];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.x * WPB + warp;
     if (g >= d.G || (only_game >= 0 && g != only_game)) return;
@@ -520,6 +532,20 @@ __global__ void __launch_bounds__(32 * WPB) k_step(TzDev d, const uint16_t* move
     const uint32_t rmeta = src.meta[0];
     if (tz_meta_tag(rmeta) != TZ_E_VALUE && src.eval[0] == 0) return;  // terminal root: batched.rs:139
     const uint16_t mv = moves[g];
+    // the move comes from the host: "Action should be valid" (env.rs:44).  Checked before the tree is touched, so an
+    // illegal move leaves tree and position as they were.
+    TzState* st = &s_state[warp];
+    warp_load_state(st, &d.env[g], lane);
+    {
+        const int cnt = warp_movegen(st, d.n, s_moves[warp], lane);
+        __syncwarp();
+        bool legal = false;
+        for (int i = lane; i < cnt; i += 32) legal = legal || s_moves[warp][i] == mv;
+        if (!__any_sync(FULL_MASK, legal)) {
+            flag_error(d, TZ_ERR_BAD_MOVE, lane);
+            return;
+        }
+    }
     // Node::descend (node/mod.rs:95-102)
     const int n = (int)tz_meta_nchild(rmeta);
     const uint32_t first = src.first[0];
@@ -575,8 +601,6 @@ __global__ void __launch_bounds__(32 * WPB) k_step(TzDev d, const uint16_t* move
         }
     }
     // replay.push(action); env.step(action)
-    TzState* st = &s_state[warp];
-    warp_load_state(st, &d.env[g], lane);
     if (!warp_apply(st, d.n, mv, lane)) flag_error(d, TZ_ERR_BAD_MOVE, lane);
     warp_store_state(&d.env[g], st, lane);
     if (lane == 0) {
@@ -1024,13 +1048,14 @@ __global__ void __launch_bounds__(32 * WPB) k_rules_probe(TzDev d, const TzState
 __global__ void __launch_bounds__(32 * WPB) k_apply_moves(TzDev d, TzState* states, const uint16_t* moves, int count,
                                                           int* out_ok) {
     __shared__ TzState s_state[WPB];
+    __shared__ uint16_t s_moves[WPB][TZ_MAX_MOVES];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * WPB + warp;
     if (i >= count) return;
     TzState* st = &s_state[warp];
     warp_load_state(st, &states[i], lane);
-    const bool ok = warp_apply(st, d.n, moves[i], lane);
-    warp_store_state(&states[i], st, lane);
+    const bool ok = warp_apply_checked(st, d.n, moves[i], s_moves[warp], lane);
+    if (ok) warp_store_state(&states[i], st, lane);
     if (lane == 0 && out_ok) out_ok[i] = ok ? 1 : 0;
 }
 

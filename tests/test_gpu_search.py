@@ -324,3 +324,30 @@ def test_nan_noise_and_betas_from_the_host_are_reported_not_fatal():
         m.gumbel_sequential_halving(betas, 8, 24, None, seed=1)
     assert m.status() == 32
     m.close()
+
+
+def test_invalid_move_in_step_is_reported():
+    """`env.step(action)` with an illegal action: the reference panics ("Action should be valid", env.rs:44); here
+    TZ_STATUS_BAD_MOVE is raised and the position is left alone."""
+    n, hk, G = 4, 4, 4
+    m = capi.BatchedMCTS(n, hk, G, arena_slots=1 << 12)
+    m.new_openings(seed=4)
+    before = m.positions()
+    moves = m.legal_moves(before)[0][:, 0].copy()
+    moves[2] = 2 << 6  # Ca1: there are no capstones on 4x4
+    m.simulate(None)
+    roots_before = m.root_stats()
+    try:
+        m.step(moves)
+    except capi.TakzeroError:
+        pass
+    assert m.status() == 16  # TZ_STATUS_BAD_MOVE
+    after = m.positions()
+    assert after[2].tobytes() == before[2].tobytes()           # the position of the offending game stays
+    assert m.root_stats()[2] == roots_before[2]                  # and so does its tree
+    assert after[0]["ply"] == before[0]["ply"] + 1             # the others moved on
+    # an illegal spread that the move encoding allows (onto nothing, from an empty square) is refused by tz_apply too
+    states, ok = m.apply(before, np.array([moves[0], 1 | (1 << 6) | (0x80 << 8), moves[2], moves[3]], dtype=np.uint16))
+    assert list(ok) == [1, 0, 0, 1]
+    assert states[1].tobytes() == before[1].tobytes() and states[2].tobytes() == before[2].tobytes()
+    m.close()
