@@ -9,7 +9,8 @@
 // `learn` writes, read without libtorch; a TZW1 file `model_latest.tzw` is the second choice), re-read before a
 // move whenever the file changed (the reference reloads unconditionally every move, main.rs:107); the
 // `buffer_lengths.txt` throttle with its checksum (main.rs:93-104,371-387) is honoured when that file exists;
-// the loop stops after --moves iterations.
+// the loop stops after --moves iterations.  Several GPUs: one process per GPU with `--device d --game-base d*games`,
+// all appending to the same files like the reference's independent processes (README.md:128-130).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -34,6 +35,7 @@ struct Args {
     std::string directory = ".";
     std::string weights;  // empty: synthetic agent (deterministic hash, for tests)
     int board = 6, half_komi = 4, games = 128, device = 0, moves = 1;
+    int game_base = 0;  // global id of game 0: one process per GPU, each with its own range (distinct RNG streams)
     int sampled_actions = 64, weighted_random_plies = 10;
     unsigned budget = 768;
     unsigned long long seed = 1;
@@ -59,6 +61,7 @@ static Args parse(int argc, char** argv) {
         else if (k == "--half-komi") a.half_komi = std::atoi(val());
         else if (k == "--games") a.games = std::atoi(val());
         else if (k == "--device") a.device = std::atoi(val());
+        else if (k == "--game-base") a.game_base = std::atoi(val());
         else if (k == "--moves") a.moves = std::atoi(val());
         else if (k == "--sampled-actions") a.sampled_actions = std::atoi(val());
         else if (k == "--budget") a.budget = (unsigned)std::atoi(val());
@@ -84,7 +87,7 @@ static void append(const std::string& path, const std::string& contents) {
 int main(int argc, char** argv) {
     Args args = parse(argc, argv);
     try {
-        BatchedMCTS mcts(args.board, args.half_komi, args.games, args.device, 0, args.arena_slots);
+        BatchedMCTS mcts(args.board, args.half_komi, args.games, args.device, args.game_base, args.arena_slots);
         for (const char* name : {"/model_latest.ot", "/model_latest.tzw"})
             if (args.weights.empty() && mtime_ns(args.directory + name) >= 0) args.weights = args.directory + name;
         long long model_stamp = -1;
