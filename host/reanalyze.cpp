@@ -194,8 +194,7 @@ int main(int argc, char** argv) {
                 t.ube = rt.ube[g];
                 contents += t.to_string(board);
             }
-            std::ofstream out(directory + "/targets-reanalyze.txt", std::ios::app | std::ios::binary);
-            if (!out || !(out << contents))
+            if (!append_file(directory + "/targets-reanalyze.txt", contents))
                 std::fprintf(stderr, "Could not save targets to file, so here they are instead:\n%s", contents.c_str());
             b++;
         }

@@ -80,8 +80,8 @@ static Args parse(int argc, char** argv) {
 static const size_t MAX_SELFPLAY_BUFFER_LEN = 32000;  // main.rs:43
 
 static void append(const std::string& path, const std::string& contents) {
-    std::ofstream f(path, std::ios::app | std::ios::binary);
-    if (!f || !(f << contents)) std::fprintf(stderr, "Could not save to %s, so here it is instead:\n%s", path.c_str(), contents.c_str());
+    if (!append_file(path, contents))
+        std::fprintf(stderr, "Could not save to %s, so here it is instead:\n%s", path.c_str(), contents.c_str());
 }
 
 int main(int argc, char** argv) {

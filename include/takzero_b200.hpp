@@ -24,7 +24,9 @@
 #include <utility>
 #include <vector>
 
+#include <fcntl.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include "takzero_b200.h"
 
@@ -343,6 +345,22 @@ inline BufferLengths read_buffer_lengths(const std::string& directory) {
     out.selfplay = (size_t)nums[0];
     out.reanalyze = (size_t)nums[1];
     return out;
+}
+
+// Appends `contents` with ONE write() on an O_APPEND descriptor, so that several processes (one per GPU) can share
+// `targets-*.txt` / `replays.txt` without tearing each other's lines (save_targets_to_file, selfplay/src/main.rs:
+// 332-346).  Returns false when the file cannot be written.
+inline bool append_file(const std::string& path, const std::string& contents) {
+    const int fd = ::open(path.c_str(), O_WRONLY | O_CREAT | O_APPEND, 0644);
+    if (fd < 0) return false;
+    size_t done = 0;
+    while (done < contents.size()) {
+        const ssize_t n = ::write(fd, contents.data() + done, contents.size() - done);
+        if (n <= 0) break;
+        done += (size_t)n;
+    }
+    ::close(fd);
+    return done == contents.size();
 }
 
 inline long long mtime_ns(const std::string& path) {
