@@ -4,6 +4,7 @@
 //   move <text>           -> round trip parse_move / move_to_string, prints "<u16> <text>"
 //   f32 <hex bits>        -> format_f32 of the float with these bits
 //   replay <n> <line...>  -> Replay::parse then to_string (no result suffix)
+//   target <n> <line...>  -> Target::parse then to_string, then " | <value bits> <ube bits> <policy bits...>"
 //   eval <tag> <ply> <negations> -> Eval walk-back: negate k times, print f32 bits
 #include <cstdio>
 #include <cstring>
@@ -54,6 +55,28 @@ int main() {
             Replay r;
             if (!Replay::parse(rest, n, &r)) std::cout << "ERR" << std::endl;
             else std::cout << r.to_string(n, 0);
+        } else if (cmd == "target") {
+            int n;
+            in >> n;
+            std::string rest;
+            std::getline(in, rest);
+            rest = rest.substr(rest.find_first_not_of(' '));
+            Target t;
+            if (!Target::parse(rest, n, &t)) {
+                std::cout << "ERR" << std::endl;
+                continue;
+            }
+            std::string text = t.to_string(n);
+            text.pop_back();
+            auto bits = [](float v) {
+                unsigned b;
+                std::memcpy(&b, &v, 4);
+                return b;
+            };
+            std::printf("%s |%08x %08x", text.c_str(), bits(t.value), bits(t.ube));
+            for (auto& mp : t.policy) std::printf(" %u:%08x", (unsigned)mp.first, bits(mp.second));
+            std::printf("\n");
+            std::fflush(stdout);
         } else if (cmd == "eval") {
             unsigned tag, ply;
             int k;

@@ -280,6 +280,43 @@ struct Target {
         s += '\n';
         return s;
     }
+    // Target FromStr (target.rs:98-140) up to the check against the position's legal moves (that needs the rules,
+    // i.e. tz_legal_moves; callers with a handle do it): "{tps};{value};{ube};{move:p,...}"
+    static bool parse(const std::string& line, int n, Target* out) {
+        std::string s = line;
+        while (!s.empty() && (s.back() == '\n' || s.back() == '\r' || s.back() == ' ')) s.pop_back();
+        std::vector<std::string> parts;
+        for (size_t pos = 0;;) {
+            const size_t end = s.find(';', pos);
+            parts.push_back(s.substr(pos, end == std::string::npos ? std::string::npos : end - pos));
+            if (end == std::string::npos) break;
+            pos = end + 1;
+        }
+        if (parts.size() < 4) return false;  // MissingTps / MissingValue / MissingUbe / MissingPolicy
+        if (!parse_tps(parts[0], n, &out->env)) return false;
+        auto parse_float = [](const std::string& t, float* v) {
+            if (t.empty()) return false;
+            char* end = nullptr;
+            *v = std::strtof(t.c_str(), &end);
+            return end == t.c_str() + t.size();
+        };
+        if (!parse_float(parts[1], &out->value) || !parse_float(parts[2], &out->ube)) return false;
+        out->policy.clear();
+        for (size_t pos = 0; pos <= parts[3].size();) {
+            size_t end = parts[3].find(',', pos);
+            if (end == std::string::npos) end = parts[3].size();
+            const std::string item = parts[3].substr(pos, end - pos);
+            const size_t colon = item.find(':');
+            if (colon == std::string::npos) return false;  // WrongPolicyFormat
+            Move m;
+            float p;
+            if (!parse_move(item.substr(0, colon), &m) || !parse_float(item.substr(colon + 1), &p) || std::isnan(p))
+                return false;
+            out->policy.emplace_back(m, p);
+            pos = end + 1;
+        }
+        return true;
+    }
 };
 
 struct Replay {

@@ -178,6 +178,32 @@ class Net(nn.Module):
         unc = torch.clamp(torch.maximum(torch.exp(ube.view(-1)), local), 0.0, MAXIMUM_VARIANCE)
         return out_logits, values.view(-1).numpy().astype(np.float32), unc.numpy().astype(np.float32)
 
+    def as_array_agent(self, device: str = "cpu"):
+        """The same agent for bulk use (oracle.array_agent): planes and move indices come from the batched C
+        helpers, the f32 forward runs on `device` (on "cuda" with TF32 off: plain f32 like the CPU path) and the
+        legal logits are gathered with one index op.  Empty SimHash set only (variance = 4.0 like a fresh network)."""
+        assert not self.simhash_set
+        dev = torch.device(device)
+        if dev.type == "cuda":
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+        net = self.to(dev)
+        L = O.lib()
+        n = self.n
+
+        @torch.no_grad()
+        def fn(games, batch, act, na):
+            xs = torch.from_numpy(O.game_repr_batch(games, batch)).to(dev)
+            idx = np.zeros(act.shape, dtype=np.int32)
+            L.tk_move_index_batch(n, act.ctypes.data, na.ctypes.data, act.shape[1], batch, idx.ctypes.data)
+            policy, values, ube = net.forward(xs)
+            lg = torch.gather(policy.reshape(batch, -1), 1, torch.from_numpy(idx).to(dev).long())
+            unc = torch.clamp(torch.maximum(torch.exp(ube.view(-1)), torch.full((batch,), MAXIMUM_VARIANCE, device=dev)),
+                              0.0, MAXIMUM_VARIANCE)
+            return lg.float().cpu().numpy(), values.view(-1).float().cpu().numpy(), unc.float().cpu().numpy()
+
+        return O.array_agent(fn)
+
     def as_oracle_agent(self):
         """Adapter to oracle.py_agent: (envs, actions) -> (logits, values, variances)."""
         return O.py_agent(lambda envs, acts: self.policy_value_uncertainty(envs, acts))

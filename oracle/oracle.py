@@ -25,7 +25,7 @@ E_VALUE, E_WIN, E_LOSS, E_DRAW = 0, 1, 2, 3
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("tak_rules.c", "tak_search.c", "tak_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("tak_rules.c", "tak_search.c", "tak_batch.c", "tak_oracle.h")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
     )
@@ -189,6 +189,20 @@ def lib():
     L.tk_batched_replay_actions.argtypes = [C.c_void_p, C.c_int]
     L.tk_batched_replay_actions.restype = P(C.c_uint16)
     L.tk_batched_select_best_actions.argtypes = [C.c_void_p, P(C.c_uint16)]
+    L.tk_games_pack.argtypes = [P(Game), C.c_int, C.c_void_p]
+    L.tk_games_unpack.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, P(Game)]
+    L.tk_game_repr_batch.argtypes = [P(Game), C.c_int, C.c_void_p]
+    L.tk_move_index_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.tk_game_result5.argtypes = [P(Game)]
+    L.tk_game_result5.restype = C.c_int
+    L.tk_has_road.argtypes = [P(Game), C.c_int]
+    L.tk_has_road.restype = C.c_int
+    L.tk_playout_positions.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, P(Game),
+                                       C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, P(Game)]
+    L.tk_playout_positions.restype = C.c_int
+    L.tk_expf_compare.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, P(C.c_longlong), P(C.c_float)]
+    L.tk_expf_compare.restype = C.c_longlong
+    L.tk_expf_restated_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     _lib = L
     return L
 
@@ -290,6 +304,56 @@ def make_eval(tag: int, payload) -> Eval:
     return e
 
 
+# ---------------------------------------------------------------- bulk helpers (tak_batch.c)
+
+
+def pack_games(games, count: Optional[int] = None) -> np.ndarray:
+    """`count` oracle Games (a ctypes array or a list) as tz_state_t records: uint8 [count, 384]."""
+    if not isinstance(games, C.Array):
+        games = (Game * len(games))(*games)
+    count = len(games) if count is None else count
+    out = np.zeros((count, 384), dtype=np.uint8)
+    lib().tk_games_pack(games, count, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def unpack_games(states: np.ndarray, n: int, half_komi: int, reversible_limit: int = 100):
+    """tz_state_t records (any dtype of itemsize 384, or uint8 [count, 384]) -> ctypes array of Games."""
+    raw = np.ascontiguousarray(states).view(np.uint8).reshape(-1, 384)
+    games = (Game * len(raw))()
+    lib().tk_games_unpack(raw.ctypes.data_as(C.c_void_p), len(raw), n, half_komi, reversible_limit, games)
+    return games
+
+
+def game_repr_batch(games, count: Optional[int] = None) -> np.ndarray:
+    if not isinstance(games, C.Array):
+        games = (Game * len(games))(*games)
+    count = len(games) if count is None else count
+    n = games[0].n
+    out = np.zeros((count, lib().tk_input_channels(n), n, n), dtype=np.float32)
+    lib().tk_game_repr_batch(games, count, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def playout_positions(n: int, half_komi: int, seed: int, policy: int, max_positions: int, reversible_limit: int = 100,
+                      max_plies: int = 1000, stride: int = MAX_MOVES) -> dict:
+    """Seeded playouts (tak_batch.c `tk_playout_positions`): every visited position with its ordered legal moves,
+    terminal code, absolute result, the move played and the position after it."""
+    games = (Game * max_positions)()
+    nexts = (Game * max_positions)()
+    n_moves = np.zeros(max_positions, dtype=np.int32)
+    moves = np.zeros((max_positions, stride), dtype=np.uint16)
+    terminal_ = np.zeros(max_positions, dtype=np.int32)
+    result_ = np.zeros(max_positions, dtype=np.int32)
+    chosen = np.zeros(max_positions, dtype=np.uint16)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    k = lib().tk_playout_positions(n, half_komi, reversible_limit, seed, policy, max_positions, max_plies, games,
+                                   p(n_moves), p(moves), stride, p(terminal_), p(result_), p(chosen), nexts)
+    assert k == max_positions
+    return {"games": games, "states": pack_games(games), "next_states": pack_games(nexts), "n_moves": n_moves,
+            "moves": moves, "terminal": terminal_, "result": result_, "chosen": chosen}
+
+
 # ---------------------------------------------------------------- agents
 
 
@@ -318,6 +382,22 @@ def py_agent(fn: PyAgent):
 
     cb = AGENT_FN(tramp)
     return cb
+
+
+def array_agent(fn):
+    """Like py_agent without a Python loop per position: fn(games: ctypes Game array view, batch, actions uint16
+    [batch, stride], n_actions int32 [batch]) -> (logits float32 [batch, stride], values [batch], variances [batch])."""
+
+    def tramp(_ctx, batch, envs, actions, n_actions, stride, logits, values, variances):
+        games = C.cast(envs, C.POINTER(Game * batch)).contents
+        act = np.ctypeslib.as_array(actions, shape=(batch, stride))
+        na = np.ctypeslib.as_array(n_actions, shape=(batch,))
+        lg, v, u = fn(games, batch, act, na)
+        np.ctypeslib.as_array(logits, shape=(batch, stride))[:] = lg
+        np.ctypeslib.as_array(values, shape=(batch,))[:] = v
+        np.ctypeslib.as_array(variances, shape=(batch,))[:] = u
+
+    return AGENT_FN(tramp)
 
 
 def _agent_ptr(agent):

@@ -68,6 +68,7 @@ int tk_possible_moves(const tk_game* g, tk_move* out);
 int tk_play(tk_game* g, tk_move m);
 void tk_play_unchecked(tk_game* g, tk_move m);
 int tk_result(const tk_game* g);
+int tk_has_road(const tk_game* g, int color);
 int tk_terminal(const tk_game* g);
 int tk_flat_diff(const tk_game* g);
 uint64_t tk_state_hash(const tk_game* g);
@@ -126,6 +127,12 @@ void tk_agent_simple(void*, int, const tk_game*, const tk_move*, const int*, int
 void tk_agent_synthetic(void*, int, const tk_game*, const tk_move*, const int*, int, float*,
                         float*, float*);
 
+/* The search is generic over `Environment` (env.rs:11-25).  0 (default): Tak.  1: the reference's test
+ * environment SafeCrack (env.rs:108-209) with its agent SafeCracker, for mcts.rs:413-445. */
+void tk_set_environment(int safecrack);
+void tk_safecrack_new(tk_game* g, const uint8_t* key, int key_len);
+void tk_agent_safecracker(void*, int, const tk_game*, const tk_move*, const int*, int, float*, float*, float*);
+
 tk_node* tk_node_new(void);
 void tk_node_free(tk_node* node);
 void tk_node_reset(tk_node* node);
@@ -177,6 +184,18 @@ void tk_batched_restart_terminal_envs(tk_batched* b, const int* opening_sym,
 int tk_batched_replay_len(const tk_batched* b, int i);
 const tk_move* tk_batched_replay_actions(const tk_batched* b, int i);
 void tk_batched_select_best_actions(tk_batched* b, tk_move* out);
+
+/* tak_batch.c: loops of the functions above for the bulk parity tests */
+void tk_games_pack(const tk_game* games, int count, uint8_t* out384);
+void tk_games_unpack(const uint8_t* in384, int count, int n, int half_komi, int reversible_limit, tk_game* games);
+void tk_game_repr_batch(const tk_game* games, int count, float* out);
+void tk_move_index_batch(int n, const tk_move* actions, const int* n_actions, int stride, int count, int32_t* out);
+int tk_game_result5(const tk_game* g);
+long long tk_expf_compare(uint32_t lo_bits, uint32_t hi_bits, uint32_t step, long long* tested, float* first_bad);
+void tk_expf_restated_batch(const float* in, int count, float* out);
+int tk_playout_positions(int n, int half_komi, int reversible_limit, uint64_t seed, int policy, int max_positions,
+                         int max_plies, tk_game* out_games, int32_t* out_n_moves, tk_move* out_moves, int stride,
+                         int32_t* out_terminal, int32_t* out_result, tk_move* out_chosen, tk_game* out_next);
 
 #ifdef __cplusplus
 }

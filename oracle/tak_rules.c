@@ -193,7 +193,7 @@ void tk_play_unchecked(tk_game* g, tk_move m) {
     }
 }
 
-static int has_road(const tk_game* g, int color) {
+int tk_has_road(const tk_game* g, int color) {
     const int n = g->n;
     uint8_t road[TK_MAX_SQ];
     for (int sq = 0; sq < n * n; sq++)
@@ -239,8 +239,8 @@ int tk_flat_diff(const tk_game* g) {
  * player who just moved is checked for a road first. */
 int tk_result(const tk_game* g) {
     const int mover = g->to_move ^ 1;
-    if (has_road(g, mover)) return mover == TK_WHITE ? TK_WHITE_WIN : TK_BLACK_WIN;
-    if (has_road(g, g->to_move)) return g->to_move == TK_WHITE ? TK_WHITE_WIN : TK_BLACK_WIN;
+    if (tk_has_road(g, mover)) return mover == TK_WHITE ? TK_WHITE_WIN : TK_BLACK_WIN;
+    if (tk_has_road(g, g->to_move)) return g->to_move == TK_WHITE ? TK_WHITE_WIN : TK_BLACK_WIN;
     int full = 1;
     for (int sq = 0; sq < g->n * g->n; sq++)
         if (g->height[sq] == 0) full = 0;

@@ -82,6 +82,64 @@ float tk_expf_restated(float x) {
     return (float)y;
 }
 
+/* ---- Environment (env.rs:11-25) ------------------------------------------------------
+ * The reference's search is generic over `Environment`; Tak (env.rs:33-96) is the instance every caller uses and
+ * the default here.  The second instance is the reference's own test environment `SafeCrack` (env.rs:108-209),
+ * needed to reproduce `safe_cracker_value_propagation` (mcts.rs:413-445); it keeps its state in the bytes of a
+ * tk_game: to_move = !active, ply = tried.len(), stack bytes = tried, top[] = key, caps[0] = key.len(). */
+typedef struct {
+    int (*terminal)(const tk_game*);
+    int (*populate_actions)(const tk_game*, tk_move*);
+    void (*step)(tk_game*, tk_move);
+} env_ops;
+
+static int sc_terminal(const tk_game* g) {
+    (void)g;
+    return TK_T_NONE; /* "The game never ends." */
+}
+static int sc_populate(const tk_game* g, tk_move* out) {
+    if (g->to_move == 0) { /* active */
+        for (int i = 0; i <= 9; i++) out[i] = (tk_move)i; /* Some(i) */
+        return 10;
+    }
+    out[0] = 0xffff; /* None */
+    return 1;
+}
+static void sc_step(tk_game* g, tk_move m) {
+    if (g->to_move == 0) {
+        if (m > 9 || g->ply >= 8 * TK_MAX_SQ) abort(); /* "All actions should be Some()" */
+        ((uint8_t*)g->stack)[g->ply++] = (uint8_t)m;
+    } else if (m != 0xffff) {
+        abort();
+    }
+    g->to_move ^= 1;
+}
+static const env_ops TAK_ENV = {tk_terminal, tk_possible_moves, tk_play_unchecked};
+static const env_ops SAFECRACK_ENV = {sc_terminal, sc_populate, sc_step};
+static const env_ops* g_env = &TAK_ENV;
+void tk_set_environment(int safecrack) { g_env = safecrack ? &SAFECRACK_ENV : &TAK_ENV; }
+
+void tk_safecrack_new(tk_game* g, const uint8_t* key, int key_len) { /* SafeCrack::new */
+    memset(g, 0, sizeof(*g));
+    for (int i = 0; i < key_len && i < TK_MAX_SQ; i++) g->top[i] = key[i];
+    g->caps[0] = (uint8_t)key_len;
+}
+static int sc_solved(const tk_game* g) { /* tried.starts_with(&key) */
+    if (g->ply < g->caps[0]) return 0;
+    return memcmp(g->stack, g->top, g->caps[0]) == 0;
+}
+/* `SafeCracker` (env.rs:190-209): logit 1.0 for every action, value = +-1 * solved, uncertainty 0 */
+void tk_agent_safecracker(void* ctx, int batch, const tk_game* envs, const tk_move* actions, const int* n_actions,
+                          int stride, float* logits, float* values, float* variances) {
+    (void)ctx;
+    (void)actions;
+    for (int b = 0; b < batch; b++) {
+        for (int i = 0; i < n_actions[b]; i++) logits[(size_t)b * stride + i] = 1.0f;
+        values[b] = (envs[b].to_move == 0 ? 1.0f : -1.0f) * (float)sc_solved(&envs[b]);
+        variances[b] = 0.0f;
+    }
+}
+
 static inline float f_exp(float x) { return g_exact_math ? tk_expf_restated(x) : expf(x); }
 static inline float f_ln(float x) { return logf(x); }
 
@@ -336,7 +394,7 @@ static int node_forward(tk_node* root, trajectory* traj, tk_game* env, float bet
             return 1;
         }
         if (tk_node_needs_initialization(node)) {
-            const int t = tk_terminal(env);
+            const int t = g_env->terminal(env);
             if (t != TK_T_NONE) {
                 node->evaluation =
                     ev_known(t == TK_T_WIN ? TK_E_WIN : t == TK_T_LOSS ? TK_E_LOSS : TK_E_DRAW, 0);
@@ -352,7 +410,7 @@ static int node_forward(tk_node* root, trajectory* traj, tk_game* env, float bet
             abort();
         }
         traj->idx[traj->len++] = (uint32_t)index;
-        tk_play_unchecked(env, node->actions[index]);
+        g_env->step(env, node->actions[index]);
         node = &node->children[index];
     }
 }
@@ -409,7 +467,7 @@ int tk_node_simulate_simple(tk_node* root, const tk_game* env0, float beta, tk_a
     } else {
         static _Thread_local tk_move actions[TK_MAX_MOVES];
         static _Thread_local float logits[TK_MAX_MOVES], probs[TK_MAX_MOVES];
-        const int n = tk_possible_moves(&env, actions);
+        const int n = g_env->populate_actions(&env, actions);
         float value, variance;
         agent(ctx, 1, &env, actions, &n, TK_MAX_MOVES, logits, &value, &variance);
         tk_softmax(logits, n, probs);
@@ -431,7 +489,7 @@ void tk_node_simulate_batch(tk_node* root, const tk_game* env0, float beta, int 
         if (node_forward(root, &trajs[filled], &env, beta, &known)) {
             backward_known_eval(root, &trajs[filled], 0, known);
         } else {
-            n_actions[filled] = tk_possible_moves(&env, actions + (size_t)filled * TK_MAX_MOVES);
+            n_actions[filled] = g_env->populate_actions(&env, actions + (size_t)filled * TK_MAX_MOVES);
             envs[filled] = env;
             filled++;
         }
@@ -735,7 +793,7 @@ static void lockstep_simulation(tk_batched* b, tk_node** sim_nodes, const tk_gam
             backward_known_eval(sim_nodes[i], &b->trajectories[i], 0, known);
             b->counters.known++;
         } else {
-            b->n_actions[filled] = tk_possible_moves(&env, b->actions_batch + (size_t)filled * TK_MAX_MOVES);
+            b->n_actions[filled] = g_env->populate_actions(&env, b->actions_batch + (size_t)filled * TK_MAX_MOVES);
             b->env_batch[filled] = env;
             b->game_of[filled] = i;
             filled++;
@@ -772,14 +830,14 @@ void tk_batched_step(tk_batched* b, const tk_move* actions) { /* batched.rs:131-
                 (tk_move*)realloc(b->replay_actions[i], sizeof(tk_move) * (size_t)b->replay_cap[i]);
         }
         b->replay_actions[i][b->replay_len[i]++] = actions[i];
-        tk_play_unchecked(&b->envs[i], actions[i]);
+        g_env->step(&b->envs[i], actions[i]);
     }
 }
 
 void tk_batched_restart_terminal_envs(tk_batched* b, const int* opening_sym, const int* opening_adj,
                                       int* out_terminal) { /* batched.rs:185-203 */
     for (int i = 0; i < b->batch; i++) {
-        const int t = tk_terminal(&b->envs[i]);
+        const int t = g_env->terminal(&b->envs[i]);
         out_terminal[i] = t;
         if (t == TK_T_NONE) continue;
         const uint16_t limit = b->envs[i].reversible_limit;
@@ -871,7 +929,7 @@ void tk_batched_gumbel_sequential_halving(tk_batched* b, tk_agent_fn agent, void
                 }
                 const int child = sets[g][i % set_len[g]].child;
                 sim_envs[g] = b->envs[g];
-                tk_play_unchecked(&sim_envs[g], b->nodes[g].actions[child]);
+                g_env->step(&sim_envs[g], b->nodes[g].actions[child]);
                 sim_nodes[g] = &b->nodes[g].children[child];
             }
             for (uint32_t v = 0; v < visits_per_action; v++)

@@ -57,6 +57,21 @@ def states_equal(a, b) -> bool:
     return np.array_equal(a["top"][occupied], b["top"][occupied])
 
 
+def states_equal_bulk(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """Vectorised `states_equal` over arrays of STATE_DTYPE: bool per record."""
+    ok = np.ones(len(a), dtype=bool)
+    for f in ("to_move", "ply", "reversible_plies"):
+        ok &= a[f] == b[f]
+    for f in ("height", "stones", "caps"):
+        ok &= (a[f] == b[f]).all(axis=1)
+    h = a["height"].astype(np.uint64)
+    mask = np.where(h >= 64, np.uint64(0xFFFFFFFFFFFFFFFF), (np.uint64(1) << np.minimum(h, np.uint64(63))) - np.uint64(1))
+    ok &= ((a["stack"] & mask) == (b["stack"] & mask)).all(axis=1)
+    occupied = a["height"] > 0
+    ok &= ((a["top"] == b["top"]) | ~occupied).all(axis=1)
+    return ok
+
+
 def random_playout_states(n: int, half_komi: int, seed: int, max_plies: int = 400, keep_terminal: bool = True):
     """Uniform random legal playout from a random opening; returns the list of oracle Games visited."""
     rng = np.random.default_rng(seed)

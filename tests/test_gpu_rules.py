@@ -8,7 +8,7 @@ import pytest
 from oracle import oracle as O
 from takzero_b200 import capi
 
-from helpers import games_to_states, random_playout_states, state_to_game, states_equal
+from helpers import games_to_states, random_playout_states, state_to_game, states_equal, states_equal_bulk
 
 pytestmark = pytest.mark.gpu
 
@@ -54,6 +54,51 @@ def test_rules_random_playouts(handles, n, half_komi, games):
     for i in range(len(positions)):
         assert states_equal(after[i], expect[i]), f"apply mismatch at {O.to_tps(positions[i])} {O.move_str(int(chosen[i]))}"
     assert n_terminal >= games // 2  # playouts really reach finished games (roads / flat wins)
+
+
+@pytest.mark.parametrize("n,half_komi", [(3, 0), (4, 4), (5, 4), (6, 4)])
+def test_rules_bulk_playouts(n, half_komi):
+    """>= 10^5 positions per board size (SURVEY 7's plan), generated and answered by the oracle's batched C entry
+    (oracle/tak_batch.c) and compared in bulk: ordered legal-move lists, terminal codes, absolute results and the
+    position after the played move, bit for bit.  The playout policies make every way a game can end show up in
+    quantity: roads, flat wins on a full board, flat wins by empty reserves, the reversible-ply draw."""
+    per_policy = 24_000
+    ends = {"road": 0, "flat_full": 0, "flat_out": 0, "rev_draw": 0}
+    total = 0
+    for policy, rev_limit in ((0, 100), (1, 100), (2, 100), (3, 12), (4, 100)):
+        h = capi.BatchedMCTS(n, half_komi, 4, arena_slots=4096, reversible_limit=rev_limit)
+        d = O.playout_positions(n, half_komi, 77 * n + policy, policy, per_policy, reversible_limit=rev_limit)
+        states = d["states"].view(capi.STATE_DTYPE).reshape(-1)
+        stride = int(d["n_moves"].max())
+        for lo in range(0, per_policy, 8192):
+            sl = slice(lo, min(lo + 8192, per_policy))
+            st = states[sl]
+            moves, counts = h.legal_moves(st, stride=stride)
+            assert np.array_equal(counts, d["n_moves"][sl]), f"N={n} policy {policy}: legal-move counts"
+            cols = np.arange(stride)[None, :] < counts[:, None]
+            assert np.array_equal(np.where(cols, moves, 0), np.where(cols, d["moves"][sl, :stride], 0)), \
+                f"N={n} policy {policy}: legal-move lists / order"
+            assert np.array_equal(h.result(st), d["terminal"][sl]), f"N={n} policy {policy}: terminal"
+            assert np.array_equal(h.game_result(st), d["result"][sl]), f"N={n} policy {policy}: result"
+            live = d["chosen"][sl] != 0xFFFF
+            after, ok = h.apply(st[live], d["chosen"][sl][live])
+            assert ok.all()
+            want = d["next_states"][sl].view(capi.STATE_DTYPE).reshape(-1)[live]
+            assert states_equal_bulk(after, want).all(), f"N={n} policy {policy}: play"
+        term = d["terminal"] != 0
+        full = (states["height"][:, : n * n] > 0).all(axis=1)
+        out = ((states["stones"].astype(int) + states["caps"]) == 0).any(axis=1)
+        res = d["result"]
+        ends["road"] += int(((res == 1) | (res == 2)).sum())
+        ends["flat_full"] += int((term & full & (res >= 3)).sum())
+        ends["flat_out"] += int((term & out & ~full & (res >= 3)).sum())
+        ends["rev_draw"] += int((term & ~full & ~out & (res == 5)).sum())
+        total += per_policy
+        h.close()
+    print(f"N={n}: {total} positions, finished games by kind {ends}")
+    assert total >= 100_000
+    assert ends["road"] >= 100 and ends["flat_full"] >= 100 and ends["rev_draw"] >= 100
+    assert ends["flat_out"] >= (5 if n == 3 else 50)
 
 
 def test_rules_golden_position(handles):

@@ -95,8 +95,14 @@ def test_solver_finds_tinue():
     m.close()
 
 
-def run_selfplay_pair(n, half_komi, G, k, budget, moves, seed, agent="synthetic"):
-    m, ob, rng = make_pair(n, half_komi, G, seed)
+def run_selfplay_pair(n, half_komi, G, k, budget, moves, seed, agent="synthetic", games=None):
+    if games is None:
+        m, ob, rng = make_pair(n, half_komi, G, seed)
+    else:
+        rng = np.random.default_rng(seed)
+        ob = O.Batched(games)
+        m = capi.BatchedMCTS(n, half_komi, G, arena_slots=1 << 16)
+        m.set_positions(games_to_states(games))
     if agent != "synthetic":
         m.set_agent(capi.AGENT_HOST, host_agent_from_oracle(agent, n, half_komi))
     stride = m.move_stride
@@ -170,6 +176,21 @@ def test_gumbel_selfplay_5x5():
 
 def test_gumbel_selfplay_6x6():
     run_selfplay_pair(6, 4, 8, 16, 128, 4, seed=4)
+
+
+def test_gumbel_selfplay_6x6_full_budget_with_restarts():
+    """BASELINE configs[2]'s search parameters (k = 16, 256 simulations per move) bit-exact over 12 moves, started
+    from late-game 6x6 positions (boards with at most four empty squares) so that games end inside the run: roots,
+    selected moves, targets, replays and the restarted positions all equal the oracle's."""
+    n, hk, G = 6, 4, 12
+    d = O.playout_positions(n, hk, 4242, 1, 40_000)
+    st = d["states"].view(capi.STATE_DTYPE).reshape(-1)
+    late = np.flatnonzero((d["terminal"] == 0) & ((st["height"][:, : n * n] == 0).sum(axis=1) <= 4))
+    assert len(late) >= G
+    picks = late[np.linspace(0, len(late) - 1, G).astype(int)]
+    games = [d["games"][int(i)].copy() for i in picks]
+    finished = run_selfplay_pair(n, hk, G, 16, 256, 12, seed=6, games=games)
+    assert finished >= 3
 
 
 def test_gumbel_selfplay_simple_agent():

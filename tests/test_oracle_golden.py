@@ -370,3 +370,140 @@ def test_unvisited_children_carry_parent_eval(oracle):
     assert len(vals) == 1
     (v, s), = vals
     assert np.float32(v) == -np.float32(root.evaluation.u.value) and np.float32(s) == np.float32(root.std_dev)
+
+
+# ---------------------------------------------------------------- search/node/mcts.rs:413-445, search/env.rs:108-209
+
+
+def test_safe_cracker_value_propagation(oracle):
+    """mcts.rs:413-445 `safe_cracker_value_propagation`: the reference's generic-environment KAT.  100 000
+    simulate_simple calls on the never-ending SafeCrack environment (env.rs:108-188; key 0,1,2,3,4) with the
+    SafeCracker agent (env.rs:190-209; value = +-1 once the tried digits start with the key): along the key the
+    root stays positive, the key digit's child is negative and every other child is exactly 0 -- i.e. the sign
+    alternation of negate/propagate and the zero-initialised children are as in the reference."""
+    L = oracle.lib()
+    L.tk_set_environment.argtypes = [C.c_int]
+    L.tk_safecrack_new.argtypes = [C.POINTER(oracle.Game), C.c_char_p, C.c_int]
+    key = [0, 1, 2, 3, 4]
+    L.tk_set_environment(1)
+    try:
+        env = oracle.Game()
+        L.tk_safecrack_new(C.byref(env), bytes(key), len(key))
+        tree = oracle.Tree()
+        agent = C.cast(L.tk_agent_safecracker, C.c_void_p)
+        assert L.tk_eval_to_f32(tree.node.evaluation) == 0.0
+        for _ in range(100_000):
+            L.tk_node_simulate_simple(tree.ptr, C.byref(env), 0.0, agent, None)
+        NONE = 0xFFFF
+        for k in key:
+            root = tree.node
+            assert L.tk_eval_to_f32(root.evaluation) > 0.0
+            assert root.n_children == 10
+            for action, child in oracle.node_children(root):
+                v = L.tk_eval_to_f32(child.evaluation)
+                if action == k:
+                    assert v < 0.0, (k, action, v)
+                else:
+                    assert v == 0.0, (k, action, v)
+            tree.descend(k)
+            tree.descend(NONE)
+        assert L.tk_eval_to_f32(tree.node.evaluation) > 0.0
+    finally:
+        L.tk_set_environment(0)
+
+
+# ---------------------------------------------------------------- search/node/policy.rs:10-19 exp, math modes
+
+
+def test_restated_expf_equals_host_libm(oracle):
+    """The GPU parity tests run the oracle in math mode 1 (`tk_set_exact_math(1)`: expf restated from glibc's
+    algorithm, the exact operation sequence the CUDA library executes).  The reference calls the host libm
+    (`f32::exp`, policy.rs:14 = mode 0).  The two agree bit for bit on every sampled input: > 5*10^7 f32 bit patterns
+    covering the whole finite range of expf and, densely, the ranges the search feeds it (softmax arguments
+    x - max in [-30, 0], improved-policy logits)."""
+    L = oracle.lib()
+
+    def bits(x):
+        return int(np.float32(x).view(np.uint32))
+
+    total = 0
+    for lo, hi, step in ((bits(-0.0), bits(-104.0), 89), (0, bits(89.0), 89), (bits(-1e-3), bits(-30.0), 5),
+                         (bits(1e-3), bits(4.0), 11)):
+        tested, first_bad = C.c_longlong(), C.c_float()
+        bad = L.tk_expf_compare(lo, hi, step, C.byref(tested), C.byref(first_bad))
+        assert bad == 0, f"{bad} of {tested.value} inputs differ, first at {first_bad.value!r}"
+        total += tested.value
+    assert total >= 50_000_000
+    # special values
+    for x in (np.inf, -np.inf, 0.0, -0.0, 88.72284, 88.72283, -103.97208, -103.972, 1e-45, -1e-45):
+        a = np.array([x], dtype=np.float32)
+        out = np.zeros(1, dtype=np.float32)
+        L.tk_expf_restated_batch(a.ctypes.data, 1, out.ctypes.data)
+        with np.errstate(over="ignore"):
+            assert out.view(np.uint32)[0] == np.exp(a).astype(np.float32).view(np.uint32)[0], x
+
+
+# ---------------------------------------------------------------- target.rs:313-377 (Display / FromStr round trips)
+
+
+def _format_check(lines):
+    import subprocess
+
+    from takzero_b200 import build as tz_build
+
+    tz_build.build()
+    exe = os.path.join(os.path.dirname(tz_build.LIB), "bin", "format_check")
+    out = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    return out.stdout.splitlines()
+
+
+def _rust_f32(v) -> str:
+    return np.format_float_positional(np.float32(v), unique=True, trim="-")
+
+
+def test_target_consistency(oracle):
+    """target.rs:313-348 `target_consistency`: along a random 5x5 game (komi 2) every position becomes a Target
+    with random policy / value / ube; Display -> FromStr -> Display is the identity and the recovered fields are
+    bit-identical.  The text is produced here from the oracle (TPS, PTN moves, Rust-style shortest f32), parsed and
+    re-printed by the host layer (include/takzero_b200.hpp `Target::parse` / `to_string`)."""
+    rng = np.random.default_rng(123)
+    g = oracle.new_game(5, 4)
+    lines, want_bits = [], []
+    while oracle.terminal(g) == oracle.T_NONE:
+        actions = oracle.possible_moves(g)
+        probs = rng.random(len(actions), dtype=np.float32)
+        value, ube = rng.random(2, dtype=np.float32)
+        policy = ",".join(f"{oracle.move_str(a)}:{_rust_f32(p)}" for a, p in zip(actions, probs))
+        lines.append(f"{oracle.to_tps(g)};{_rust_f32(value)};{_rust_f32(ube)};{policy}")
+        want_bits.append(" ".join([f"{int(value.view(np.uint32)):08x}", f"{int(ube.view(np.uint32)):08x}"] +
+                                  [f"{a}:{int(p.view(np.uint32)):08x}" for a, p in zip(actions, probs)]))
+        oracle.play(g, actions[int(rng.integers(len(actions)))])
+    assert len(lines) > 20
+    got = _format_check([f"target 5 {line}" for line in lines])
+    assert len(got) == len(lines)
+    for line, bits, out in zip(lines, want_bits, got):
+        text, recovered = out.split(" |")
+        assert text == line          # string == string_again
+        assert recovered == bits     # target == recovered
+
+
+def test_replay_consistency(oracle):
+    """target.rs:350-377 `replay_consistency`: 100 random 5x5 games from `new_opening`; after every move the
+    Replay's Display -> FromStr -> Display is the identity."""
+    rng = np.random.default_rng(123)
+    lines = []
+    for _ in range(100):
+        g = oracle.new_opening(5, 4, int(rng.integers(8)), int(rng.integers(2)))
+        text = f'[TPS "{oracle.to_tps(g)}"]'
+        while True:
+            actions = oracle.possible_moves(g)
+            a = actions[int(rng.integers(len(actions)))]
+            text += " " + oracle.move_str(a)
+            oracle.play(g, a)
+            lines.append(text)
+            if oracle.terminal(g) != oracle.T_NONE:
+                break
+    sample = lines[:: max(1, len(lines) // 3000)]
+    got = _format_check([f"replay 5 {line}" for line in sample])
+    assert got == sample and len(sample) > 1000
