@@ -236,7 +236,7 @@ def main():
     tensors = weights.random_init(BOARD_N, seed=123 + rank)
     if world > 1:
         tensors = tzd.broadcast_weights(tensors, src=0, device=cuda_dev)
-    net_dtype = network.DTYPE_F16 if os.environ.get("TZ_BENCH_DTYPE", "bf16") == "f16" else network.DTYPE_BF16
+    net_dtype = network.DTYPE_BF16 if os.environ.get("TZ_BENCH_DTYPE", "f16") == "bf16" else network.DTYPE_F16
     network.set_weights(m, tensors, net_dtype)
     weight_load_s = time.perf_counter() - t_w
     m.set_agent(capi.AGENT_NETWORK)

@@ -99,7 +99,7 @@ typedef void (*tz_agent_fn)(void* ctx, int batch, const tz_state_t* envs, const 
 enum {
     TZ_AGENT_SYNTHETIC = 0, /* deterministic integer-hash agent, bit-identical to the oracle's */
     TZ_AGENT_HOST = 1,      /* tz_agent_fn callback ("reference network outputs injected") */
-    TZ_AGENT_NETWORK = 2,   /* the bf16 ResNet on the device (tz_set_weights first) */
+    TZ_AGENT_NETWORK = 2,   /* the 16-bit tcgen05 ResNet on the device (tz_set_weights first) */
 };
 
 /* One named f32 tensor of the network (host memory), see tz_set_weights. */
@@ -247,7 +247,7 @@ TZ_API int tz_tree_principal_variation(tz_handle* h, tz_move_t* out_moves, int c
  *   policy.conv2d.{weight [O,256,3,3], bias [O]}; {value,ube}.conv2d.{weight [1,256,1,1], bias [1]};
  *   {value,ube}.linear.{weight [1,N*N], bias [1]}.
  * The number of residual blocks is taken from the names (16 for net4/net6, 20 for net5).  BatchNorm is
- * folded (eval mode, eps 1e-5) and the convolutions are converted to bf16 here. */
+ * folded (eval mode, eps 1e-5) and the convolutions are converted to the 16-bit network type here. */
 TZ_API int tz_set_weights(tz_handle* h, const tz_tensor_t* tensors, int count);
 /* Net::load (network/mod.rs:20-27, net6_simhash.rs:164-181) from the reference's own model file: `path` is a tch
  * `VarStore::save` archive (`model_latest.ot`, written by learn/src/main.rs:166,257 and re-read before every move
@@ -264,9 +264,11 @@ TZ_API int tz_load_model(tz_handle* h, const char* path);
 typedef void (*tz_model_tensor_fn)(void* ctx, const char* name, const char* stored_name, const float* data,
                                    const int64_t* shape, int ndim);
 TZ_API int tz_read_model_file(const char* path, tz_model_tensor_fn fn, void* ctx);
-/* 16-bit type the NEXT tz_set_weights converts weights and activations to.  TZ_DTYPE_BF16 (default) is what
- * the design targets; TZ_DTYPE_F16 runs the same tcgen05 kind::f16 kernels on IEEE half (3 more mantissa
- * bits, ~8x smaller error against the f32 reference, but 65504 range: an overflow surfaces as TZ_STATUS_NAN). */
+/* 16-bit type the NEXT tz_set_weights / tz_load_model converts weights and activations to; both run the same tcgen05
+ * kind::f16 kernels.  TZ_DTYPE_F16 (IEEE half, the default) is the mode whose whole searches choose the same move as
+ * the f32 reference network on >= 99 % of positions (tests/test_gpu_agreement.py); range 65504: an overflow surfaces
+ * as TZ_STATUS_NAN.  TZ_DTYPE_BF16 has 3 fewer mantissa bits (~8x the error, ~97.5 % agreement) and is a few per
+ * cent faster under the power cap. */
 enum { TZ_DTYPE_BF16 = 0, TZ_DTYPE_F16 = 1 };
 TZ_API int tz_set_network_dtype(tz_handle* h, int dtype);
 /* `impl Agent for Net`::policy_value_uncertainty (net6_simhash.rs:259-324) on host buffers:
@@ -294,6 +296,8 @@ TZ_API int tz_debug_activations(tz_handle* h, int which, int count, float* out);
  * activation set; out_items receives (chunk, layer, pair tile) of the first `cap` items */
 TZ_API int tz_debug_schedule(int count, int count_max, int board_n, int chunk_min_tiles, int layers, long long* out,
                       int* out_items, int cap);
+/* parity hook: the exp of the device's softmax (policy.rs:10-19; glibc's expf algorithm restated) */
+TZ_API int tz_debug_expf(tz_handle* h, const float* in, int count, float* out);
 /* tuning hook: mean ms per tower-convolution launch over `count` positions (CUDA events, `reps` blocks) */
 TZ_API int tz_debug_time_tower(tz_handle* h, int count, int reps, double* ms_per_conv);
 

@@ -1005,6 +1005,22 @@ extern "C" TZ_API int tz_debug_time_tower(tz_handle* h, int count, int reps, dou
     return TZ_OK;
 }
 
+extern "C" TZ_API int tz_debug_expf(tz_handle* h, const float* in, int count, float* out) {
+    CHECK_H(h);
+    if (!in || !out || count < 0) return fail(TZ_EINVAL, "bad argument");
+    if (count == 0) return TZ_OK;
+    Scratch s;
+    float *din, *dout;
+    CU(s.get(&din, (size_t)count));
+    CU(s.get(&dout, (size_t)count));
+    CU(cudaMemcpyAsync(din, in, (size_t)count * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    launch_debug_expf(din, count, dout, h->stream);
+    CU(cudaMemcpyAsync(out, dout, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return TZ_OK;
+}
+
 extern "C" TZ_API int tz_debug_schedule(int count, int count_max, int board_n, int chunk_min_tiles, int layers,
                                         long long* out, int* out_items, int cap) {
     if (!out || count < 0 || count > count_max || board_n < 3 || board_n > 6 || chunk_min_tiles <= 0 || layers <= 0 ||

@@ -17,7 +17,7 @@ struct tz_handle {
     tz_agent_fn agent_fn = nullptr;
     void* agent_ctx = nullptr;
     NnState* nn = nullptr;
-    int nn_f16 = 0;  // 16-bit type the next tz_set_weights converts to: 0 bf16, 1 fp16
+    int nn_f16 = 1;  // 16-bit type the next tz_set_weights converts to: 1 fp16 (default), 0 bf16
     // device staging of host-facing arguments / results
     float* betas = nullptr;
     float* gumbel = nullptr;

@@ -1059,6 +1059,12 @@ __global__ void __launch_bounds__(32 * WPB) k_apply_moves(TzDev d, TzState* stat
     if (lane == 0 && out_ok) out_ok[i] = ok ? 1 : 0;
 }
 
+// parity hook: the device's expf (tree.cuh `expf_libm`, the softmax's exp) on arbitrary inputs
+__global__ void k_debug_expf(const float* in, int count, float* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = expf_libm(in[i]);
+}
+
 // ---- launchers -------------------------------------------------------------------------------
 
 static inline int blocks_for(int items) { return (items + WPB - 1) / WPB; }
@@ -1134,6 +1140,9 @@ void launch_select_actions(const TzDev& d, int weighted_random_plies, uint32_t t
 void launch_merge_moves(const TzDev& d, int weighted_random_plies, const uint16_t* sampled, uint16_t* moves,
                         cudaStream_t st) {
     k_merge_moves<<<(d.G + 127) / 128, 128, 0, st>>>(d, weighted_random_plies, sampled, moves);
+}
+void launch_debug_expf(const float* in, int count, float* out, cudaStream_t st) {
+    k_debug_expf<<<(count + 255) / 256, 256, 0, st>>>(in, count, out);
 }
 void launch_rules_probe(const TzDev& d, const TzState* states, int count, int stride, uint16_t* out_moves, int* out_n,
                         int* out_terminal, int* out_result, cudaStream_t st) {

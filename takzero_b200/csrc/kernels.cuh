@@ -36,3 +36,5 @@ void launch_merge_moves(const TzDev& d, int weighted_random_plies, const uint16_
                         cudaStream_t st);
 void launch_set_root_priors(const TzDev& d, int stride, const float* prob, const float* logit, cudaStream_t st);
 void launch_random_steps(const TzDev& d, const uint8_t* mask, int steps, unsigned long long seed, cudaStream_t st);
+
+void launch_debug_expf(const float* in, int count, float* out, cudaStream_t st);

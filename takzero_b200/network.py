@@ -44,11 +44,12 @@ def _declare():
 
 
 DTYPE_BF16, DTYPE_F16 = 0, 1
+DTYPE_DEFAULT = DTYPE_F16  # the library's default: the mode that meets the >= 99 % chosen-move agreement bar
 
 
-def set_weights(mcts: capi.BatchedMCTS, tensors: Dict[str, np.ndarray], dtype: int = DTYPE_BF16) -> None:
+def set_weights(mcts: capi.BatchedMCTS, tensors: Dict[str, np.ndarray], dtype: int = DTYPE_DEFAULT) -> None:
     """`Net::load`: upload named f32 tensors (PyTorch layout, names in include/takzero_b200.h); `dtype` is the
-    16-bit type of weights and activations on the device (bf16 by default)."""
+    16-bit type of weights and activations on the device (fp16 by default)."""
     _declare()
     capi._check(capi.lib().tz_set_network_dtype(mcts.handle, dtype))
     keep = []
@@ -61,7 +62,7 @@ def set_weights(mcts: capi.BatchedMCTS, tensors: Dict[str, np.ndarray], dtype: i
     capi._check(capi.lib().tz_set_weights(mcts.handle, arr, len(tensors)))
 
 
-def load_model(mcts: capi.BatchedMCTS, path: str, dtype: int = DTYPE_BF16) -> None:
+def load_model(mcts: capi.BatchedMCTS, path: str, dtype: int = DTYPE_DEFAULT) -> None:
     """`Net::load(path, device)` (network/mod.rs:20-27, net6_simhash.rs:164-181): read the reference's
     `model_latest.ot` (tch VarStore archive; also a `torch.save` state dict or a TZW1 file) inside the library,
     upload it, and take the SimHash matrix / `bitvec.bin` sidecar when the file has them."""

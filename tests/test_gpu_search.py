@@ -372,3 +372,32 @@ def test_invalid_move_in_step_is_reported():
     assert list(ok) == [1, 0, 0, 1]
     assert states[1].tobytes() == before[1].tobytes() and states[2].tobytes() == before[2].tobytes()
     m.close()
+
+
+def test_device_expf_is_the_restated_glibc_expf():
+    """The softmax's exp on the device (tree.cuh `expf_libm`) against the oracle's `tk_expf_restated` -- the same
+    glibc algorithm, which tests/test_oracle_golden.py shows equal to the host libm -- on 1.2*10^7 inputs: every
+    8th f32 bit pattern of the softmax range [-104, 0] plus a sweep of the positive range.  Bit-exact."""
+    import ctypes as C
+
+    L = capi.lib()
+    L.tz_debug_expf.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.tz_debug_expf.restype = C.c_int
+    m = capi.BatchedMCTS(4, 4, 4, arena_slots=4096)
+    lo, hi = int(np.float32(-1e-30).view(np.uint32)), int(np.float32(-104.0).view(np.uint32))
+    neg = np.arange(lo, hi, 41, dtype=np.uint32).view(np.float32)
+    pos = np.arange(0, int(np.float32(89.0).view(np.uint32)), 257, dtype=np.uint32).view(np.float32)
+    special = np.array([0.0, -0.0, np.inf, -np.inf, 88.72284, 88.72283, -103.97208, -103.972, np.nan], dtype=np.float32)
+    xs = np.ascontiguousarray(np.concatenate([neg, pos, special]))
+    assert len(xs) >= 12_000_000
+    got = np.zeros_like(xs)
+    want = np.zeros_like(xs)
+    for a in range(0, len(xs), 1 << 22):
+        chunk = np.ascontiguousarray(xs[a:a + (1 << 22)])
+        out = np.zeros_like(chunk)
+        assert L.tz_debug_expf(m.handle, chunk.ctypes.data, len(chunk), out.ctypes.data) == 0
+        got[a:a + len(chunk)] = out
+    O.lib().tk_expf_restated_batch(xs.ctypes.data, len(xs), want.ctypes.data)
+    ok = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+    assert ok.all(), f"{(~ok).sum()} mismatches, first at {xs[~ok][0]!r}"
+    m.close()
