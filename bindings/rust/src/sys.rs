@@ -27,6 +27,7 @@ pub const TZ_STATUS_NAN: u32 = 32;
 pub const TZ_STATUS_SET_EMPTY: u32 = 64;
 pub const TZ_STATUS_REPLAY_FULL: u32 = 128;
 pub const TZ_STATUS_NETWORK_STALL: u32 = 256;
+pub const TZ_STATUS_WEIGHTS_MISMATCH: u32 = 512;
 pub const TZ_AGENT_SYNTHETIC: u32 = 0;
 pub const TZ_AGENT_HOST: u32 = 1;
 pub const TZ_AGENT_NETWORK: u32 = 2;
@@ -157,7 +158,14 @@ extern "C" {
     pub fn tz_tree_descend(h: *mut tz_handle, move_: tz_move_t) -> c_int;
     pub fn tz_tree_principal_variation(h: *mut tz_handle, out_moves: *mut tz_move_t, cap: c_int) -> c_int;
     pub fn tz_set_weights(h: *mut tz_handle, tensors: *const tz_tensor_t, count: c_int) -> c_int;
+    pub fn tz_comm_unique_id(out_id128: *mut c_void) -> c_int;
+    pub fn tz_comm_init(h: *mut tz_handle, id128: *const c_void, nranks: c_int, rank: c_int) -> c_int;
+    pub fn tz_comm_destroy(h: *mut tz_handle) -> c_int;
+    pub fn tz_broadcast_weights(h: *mut tz_handle, tensors: *const tz_tensor_t, count: c_int, res_blocks: c_int, root: c_int) -> c_int;
+    pub fn tz_weight_generation(h: *mut tz_handle, out_generation: *mut u64, out_ms: *mut f64) -> c_int;
+    pub fn tz_allreduce_sum(h: *mut tz_handle, values: *mut u64, count: c_int) -> c_int;
     pub fn tz_load_model(h: *mut tz_handle, path: *const c_char) -> c_int;
+    pub fn tz_load_model_ex(h: *mut tz_handle, path: *const c_char, allow_missing_set: c_int) -> c_int;
     pub fn tz_read_model_file(path: *const c_char, fn_: tz_model_tensor_fn, ctx: *mut c_void) -> c_int;
     pub fn tz_set_network_dtype(h: *mut tz_handle, dtype: c_int) -> c_int;
     pub fn tz_evaluate(h: *mut tz_handle, states: *const tz_state_t, count: c_int, actions: *const tz_move_t, n_actions: *const c_int, stride: c_int, logits: *mut f32, values: *mut f32, variances: *mut f32) -> c_int;
@@ -169,6 +177,8 @@ extern "C" {
     pub fn tz_debug_layer_limit(h: *mut tz_handle, limit: c_int) -> c_int;
     pub fn tz_debug_activations(h: *mut tz_handle, which: c_int, count: c_int, out: *mut f32) -> c_int;
     pub fn tz_debug_schedule(count: c_int, count_max: c_int, board_n: c_int, chunk_min_tiles: c_int, layers: c_int, out: *mut c_longlong, out_items: *mut c_int, cap: c_int) -> c_int;
+    pub fn tz_debug_network_mode(h: *mut tz_handle, per_layer_launches: c_int, chunk_min_tiles: c_int, drop_progress: c_int) -> c_int;
+    pub fn tz_debug_weight_set(h: *mut tz_handle, out: *mut u8, cap: usize, out_size: *mut usize) -> c_int;
     pub fn tz_debug_expf(h: *mut tz_handle, in_: *const f32, count: c_int, out: *mut f32) -> c_int;
     pub fn tz_debug_time_tower(h: *mut tz_handle, count: c_int, reps: c_int, ms_per_conv: *mut f64) -> c_int;
 }

@@ -53,6 +53,8 @@ enum {
     TZ_STATUS_REPLAY_FULL = 128,
     TZ_STATUS_NETWORK_STALL = 256, /* a CTA pair of the fused network launch waited > ~1 s for another pair's
                                       tile (never seen; the watchdog turns a would-be hang into this error) */
+    TZ_STATUS_WEIGHTS_MISMATCH = 512, /* a broadcast weight set describes another network (board size, residual
+                                         blocks or 16-bit type differ between the ranks) */
 };
 
 /* Move (takparse `Move`, 2 bytes):
@@ -249,6 +251,29 @@ TZ_API int tz_tree_principal_variation(tz_handle* h, tz_move_t* out_moves, int c
  * The number of residual blocks is taken from the names (16 for net4/net6, 20 for net5).  BatchNorm is
  * folded (eval mode, eps 1e-5) and the convolutions are converted to the 16-bit network type here. */
 TZ_API int tz_set_weights(tz_handle* h, const tz_tensor_t* tensors, int count);
+
+/* ---- multi-GPU (one process per GPU; games shard by contiguous global id, tz_config_t::game_base) ------------
+ * The reference scales by independent `selfplay` processes that share files (README.md:128-130): each re-reads
+ * `model_latest.ot` before every move (selfplay/src/main.rs:107) and `learn` adds up what they produced through
+ * `buffer_lengths.txt` (learn/src/main.rs:195-209).  Here those two exchanges are NCCL collectives over NVLink; there
+ * is none inside a simulation.  NCCL is opened at run time (TZ_NCCL_LIB or libnccl.so.2); a single-GPU host needs none.
+ *
+ * tz_comm_unique_id: 128 bytes (an ncclUniqueId) made by one rank and handed to the others by the host's own means;
+ * tz_comm_init: collective over all `nranks` ranks (nranks == 1: no NCCL involved). */
+TZ_API int tz_comm_unique_id(void* out_id128);
+TZ_API int tz_comm_init(tz_handle* h, const void* id128, int nranks, int rank);
+TZ_API int tz_comm_destroy(tz_handle* h);
+/* One weight GENERATION on every rank of the communicator (collective; also valid without one = Net::load on a single
+ * GPU): the root rank passes the model's tensors (as tz_set_weights), folds BatchNorm and arranges the 16-bit weight
+ * image on its GPU, ncclBroadcast sends that image (39 MB for the 6x6 network) into the inactive one of every rank's two
+ * weight sets, and every rank swaps sets for the launches it enqueues from then on -- i.e. between two moves.  All of
+ * it runs on a side stream beside the search.  The other ranks pass tensors = NULL and the number of residual blocks
+ * (0 = the board's default: 20 for 5x5, else 16); every rank must use the same tz_set_network_dtype. */
+TZ_API int tz_broadcast_weights(tz_handle* h, const tz_tensor_t* tensors, int count, int res_blocks, int root);
+/* number of generations so far and the device time of the last one (upload + fold + broadcast); waits for it */
+TZ_API int tz_weight_generation(tz_handle* h, uint64_t* out_generation, double* out_ms);
+/* in-place sum over all ranks of up to 64 counters (simulations, positions, targets, finished games ...) */
+TZ_API int tz_allreduce_sum(tz_handle* h, uint64_t* values, int count);
 /* Net::load (network/mod.rs:20-27, net6_simhash.rs:164-181) from the reference's own model file: `path` is a tch
  * `VarStore::save` archive (`model_latest.ot`, written by learn/src/main.rs:166,257 and re-read before every move
  * by selfplay/src/main.rs:107 and reanalyze/src/main.rs:93), parsed here without libtorch (ZIP + pickle); a
@@ -256,9 +281,12 @@ TZ_API int tz_set_weights(tz_handle* h, const tz_tensor_t* tensors, int count);
  * TZW1 container work too.  tch variable names are mapped to the
  * names above: the two SmallBlocks of a ResidualBlock share one path (residual.rs:52-54), so the file holds
  * `core.res_block_B.conv2d.weight` (block half 0) and `core.res_block_B.conv2d.weight__K` (half 1).  When the file
- * has a `simhash_matrix`, it and the sidecar `bitvec.bin` next to the file (absent = empty set) go through
- * tz_set_simhash. */
+ * has a `simhash_matrix` (or `lcghash_init`), it and the sidecar `bitvec.bin` next to the file go through
+ * tz_set_simhash (tz_set_lcghash).  Like Net::load, tz_load_model fails when the sidecar is missing;
+ * tz_load_model_ex(allow_missing_set = 1) takes a missing sidecar as the empty set of a freshly initialised network
+ * (every local uncertainty is then MAXIMUM_VARIANCE = 4.0). */
 TZ_API int tz_load_model(tz_handle* h, const char* path);
+TZ_API int tz_load_model_ex(tz_handle* h, const char* path, int allow_missing_set);
 /* Tensor::load_multi: calls fn for every tensor of the file (converted to contiguous f32) with the mapped and the
  * stored name; returns the tensor count or a negative code.  Needs no GPU. */
 typedef void (*tz_model_tensor_fn)(void* ctx, const char* name, const char* stored_name, const float* data,
@@ -287,7 +315,8 @@ TZ_API int tz_lcghash_indices(tz_handle* h, const tz_state_t* states, int count,
 /* game_repr (repr.rs:169-228): f32 planes [count][C][N][N] */
 TZ_API int tz_encode_planes(tz_handle* h, const tz_state_t* states, int count, float* out);
 /* test hooks: stop the tower after `limit` convolutions (-1 = full network); read back an activation
- * buffer (0 block stream, 1 block middle, 2 input planes) of the last tz_evaluate as f32 [count][N*N][ch] */
+ * buffer (0 block stream, 1 block middle: f32 [count][N*N][256]) of the last tz_evaluate, or (2) the 16-bit input
+ * planes the first convolution encodes from those positions, f32 [count][N*N][64] */
 TZ_API int tz_debug_layer_limit(tz_handle* h, int limit);
 TZ_API int tz_debug_activations(tz_handle* h, int which, int count, float* out);
 /* test hook, needs no GPU: the work-item schedule of the fused network launch (conv_tcgen05.cuh `Schedule`) for
@@ -296,6 +325,14 @@ TZ_API int tz_debug_activations(tz_handle* h, int which, int count, float* out);
  * activation set; out_items receives (chunk, layer, pair tile) of the first `cap` items */
 TZ_API int tz_debug_schedule(int count, int count_max, int board_n, int chunk_min_tiles, int layers, long long* out,
                       int* out_items, int cap);
+/* test / measurement hook, read by the NEXT tz_set_weights (launch structure) or at once (drop_progress):
+ * per_layer_launches = 1: one launch per convolution instead of the fused launch; chunk_min_tiles: minimum pair tiles
+ * per chunk (-1 = default 150, 0 = one chunk); drop_progress = 1: CTA pair 0 withholds its tiles so that the watchdog
+ * (TZ_STATUS_NETWORK_STALL) can be tested.  The defaults (0, -1, 0) are the product. */
+TZ_API int tz_debug_network_mode(tz_handle* h, int per_layer_launches, int chunk_min_tiles, int drop_progress);
+/* parity hook: the active weight set (folded, arranged 16-bit weights + biases; layout in nn.cu `SetLayout`);
+ * out = NULL: only the size */
+TZ_API int tz_debug_weight_set(tz_handle* h, uint8_t* out, size_t cap, size_t* out_size);
 /* parity hook: the exp of the device's softmax (policy.rs:10-19; glibc's expf algorithm restated) */
 TZ_API int tz_debug_expf(tz_handle* h, const float* in, int count, float* out);
 /* tuning hook: mean ms per tower-convolution launch over `count` positions (CUDA events, `reps` blocks) */

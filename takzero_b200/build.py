@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtakzero_b200.so")
-SOURCES = ["api.cu", "kernels.cu", "nn.cu", "model_file.cpp"]
+SOURCES = ["api.cu", "kernels.cu", "nn.cu", "comm.cu", "model_file.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--cudart", "static",
@@ -58,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose:
             print(out)
     cmd = [nvcc(), "-shared", "-o", LIB, *objs, "--cudart", "static",
-           "-gencode", "arch=compute_100a,code=sm_100a"]
+           "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     subprocess.check_call(cmd)
     build_hosts()
     return LIB

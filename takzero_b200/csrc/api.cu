@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/takzero_b200.h"
+#include "comm.cuh"
 #include "handle.cuh"
 #include "kernels.cuh"
 #include "nn.cuh"
@@ -155,6 +156,7 @@ extern "C" TZ_API int tz_create(const tz_config_t* cfg, tz_handle** out) {
     DM(d.leaf_state, Q);
     DM(d.actions, Q * d.M);
     DM(d.n_actions, Q);
+    DM(d.sq_ranges, Q * TZ_MAX_SQ);
     DM(d.logits, Q * d.M);
     DM(d.value, Q);
     DM(d.variance, Q);
@@ -187,6 +189,7 @@ extern "C" TZ_API int tz_create(const tz_config_t* cfg, tz_handle** out) {
     DM(h->tbl_f32c, G * d.M);
     DM(h->root_stats, G * 6);
     DM(h->ube, G);
+    DM(h->reduce_buf, 64);
 #undef DM
     if (e != cudaSuccess) {
         const int rc = fail(TZ_ENOMEM, "cudaMalloc: %s (n_games=%d arena_slots=%u)", cudaGetErrorString(e), d.G, cap);
@@ -238,6 +241,7 @@ extern "C" TZ_API void tz_destroy(tz_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     nn_free(h);
+    comm_destroy(h);
     for (void* p : h->allocs) cudaFree(p);
     if (h->pin_small) cudaFreeHost(h->pin_small);
     if (h->prof_counts) cudaFreeHost(h->prof_counts);
@@ -261,10 +265,10 @@ extern "C" TZ_API int tz_sync(tz_handle* h) {
 }
 
 static const char* status_text(uint32_t bits, char* buf, size_t len) {
-    static const char* names[] = {"arena_full", "depth", "no_child", "too_many_moves",
-                                  "bad_move",   "nan",   "set_empty", "replay_full"};
+    static const char* names[] = {"arena_full", "depth",       "no_child",      "too_many_moves",  "bad_move",
+                                  "nan",        "set_empty",   "replay_full",   "network_stall",   "weights_mismatch"};
     buf[0] = 0;
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < 10; i++)
         if (bits & (1u << i)) {
             strncat(buf, names[i], len - strlen(buf) - 1);
             strncat(buf, " ", len - strlen(buf) - 1);
@@ -515,6 +519,7 @@ extern "C" TZ_API int tz_set_agent(tz_handle* h, int kind, tz_agent_fn fn, void*
     h->agent_kind = kind;
     h->agent_fn = fn;
     h->agent_ctx = ctx;
+    nn_bind_search(h);  // k_expand finishes the network's heads itself when (and only when) the network is the agent
     return TZ_OK;
 }
 
@@ -569,7 +574,7 @@ static int lockstep(tz_handle* h, int phase, int halving_i, const float* dbetas)
         launch_expand(d, h->stream);
     }
     h->prof_active = false;
-    h->launches += 3;
+    h->launches += 2 + (h->agent_kind == TZ_AGENT_SYNTHETIC ? 1 : 0);  // the network counts its own launches
     return TZ_OK;
 }
 
@@ -825,9 +830,101 @@ extern "C" TZ_API int tz_set_weights(tz_handle* h, const tz_tensor_t* tensors, i
         shape_ptrs[i] = shapes[i].data();
         ndims[i] = tensors[i].ndim;
     }
-    CU(cudaStreamSynchronize(h->stream));
     const int rc = nn_set_weights(h, names.data(), data.data(), shape_ptrs.data(), ndims.data(), count);
     if (rc) return fail(rc, "tz_set_weights: %s", nn_last_error());
+    return TZ_OK;
+}
+
+// ---- multi-GPU: NCCL communicator, weight generations, counter sums (comm.cu, nn.cu) ----------------------
+
+extern "C" TZ_API int tz_comm_unique_id(void* out_id128) {
+    if (!out_id128) return fail(TZ_EINVAL, "null out");
+    const int rc = comm_unique_id(out_id128);
+    if (rc) return fail(rc, "tz_comm_unique_id: %s", comm_last_error());
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_comm_init(tz_handle* h, const void* id128, int nranks, int rank) {
+    CHECK_H(h);
+    if (nranks > 1 && !id128) return fail(TZ_EINVAL, "null id");
+    const int rc = comm_init(h, id128, nranks, rank);
+    if (rc) return fail(rc, "tz_comm_init: %s", comm_last_error());
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_comm_destroy(tz_handle* h) {
+    CHECK_H(h);
+    CU(cudaStreamSynchronize(h->stream));
+    comm_destroy(h);
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_broadcast_weights(tz_handle* h, const tz_tensor_t* tensors, int count, int res_blocks, int root) {
+    CHECK_H(h);
+    std::vector<const char*> names;
+    std::vector<const float*> data;
+    std::vector<std::vector<long long>> shapes;
+    std::vector<const long long*> shape_ptrs;
+    std::vector<int> ndims;
+    if (comm_rank(h) == root) {
+        if (!tensors || count <= 0) return fail(TZ_EINVAL, "the root rank passes the tensors");
+        names.resize(count);
+        data.resize(count);
+        shapes.resize(count);
+        shape_ptrs.resize(count);
+        ndims.resize(count);
+        for (int i = 0; i < count; i++) {
+            if (!tensors[i].name || !tensors[i].data || tensors[i].ndim < 0 || tensors[i].ndim > 4)
+                return fail(TZ_EINVAL, "bad tensor %d", i);
+            names[i] = tensors[i].name;
+            data[i] = tensors[i].data;
+            for (int k = 0; k < tensors[i].ndim; k++) shapes[i].push_back((long long)tensors[i].shape[k]);
+            shape_ptrs[i] = shapes[i].data();
+            ndims[i] = tensors[i].ndim;
+        }
+    } else {
+        count = 0;
+    }
+    const int rc = nn_broadcast_weights(h, names.data(), data.data(), shape_ptrs.data(), ndims.data(), count, res_blocks, root);
+    if (rc) return fail(rc, "tz_broadcast_weights: %s", nn_last_error());
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_weight_generation(tz_handle* h, uint64_t* out_generation, double* out_ms) {
+    CHECK_H(h);
+    double ms = 0.0;
+    unsigned long long gen = 0;
+    const int rc = nn_generation_ms(h, &ms, &gen);
+    if (rc) return fail(rc, "no weight generation yet");
+    if (out_generation) *out_generation = gen;
+    if (out_ms) *out_ms = ms;
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_allreduce_sum(tz_handle* h, uint64_t* values, int count) {
+    CHECK_H(h);
+    if (!values || count <= 0 || count > 64) return fail(TZ_EINVAL, "count must be 1..64");
+    CU(cudaMemcpyAsync(h->reduce_buf, values, (size_t)count * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+    const int rc = comm_allreduce_sum_u64(h, h->reduce_buf, count, h->stream);
+    if (rc) return fail(rc, "tz_allreduce_sum: %s", comm_last_error());
+    CU(cudaMemcpyAsync(values, h->reduce_buf, (size_t)count * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_debug_network_mode(tz_handle* h, int per_layer_launches, int chunk_min_tiles, int drop_progress) {
+    if (!h) return fail(TZ_EINVAL, "null handle");
+    h->dbg_per_layer = per_layer_launches != 0;
+    h->dbg_chunk_tiles = chunk_min_tiles;
+    h->dbg_drop_progress = drop_progress != 0;
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_debug_weight_set(tz_handle* h, uint8_t* out, size_t cap, size_t* out_size) {
+    CHECK_H(h);
+    if (!out_size) return fail(TZ_EINVAL, "null out_size");
+    const int rc = nn_debug_weight_set(h, out, cap, out_size);
+    if (rc) return fail(rc, "tz_debug_weight_set failed (weights set? cap >= size?)");
     return TZ_OK;
 }
 
@@ -846,7 +943,7 @@ extern "C" TZ_API int tz_evaluate(tz_handle* h, const tz_state_t* states, int co
     CU(cudaMemcpyAsync(d.leaf_state, states, c * sizeof(TzState), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(d.actions, actions, c * d.M * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(d.n_actions, n_actions, c * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    const int rc = nn_forward(h, d.leaf_state, nullptr, count, d.actions, d.n_actions, d.logits, d.value, d.variance);
+    const int rc = nn_forward_host(h, count);
     if (rc) return fail(rc, "network forward failed: %s", cudaGetErrorString(cudaGetLastError()));
     CU(cudaMemcpyAsync(logits, d.logits, c * d.M * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(values, d.value, c * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
@@ -887,7 +984,7 @@ extern "C" TZ_API int tz_debug_activations(tz_handle* h, int which, int count, f
     CHECK_H(h);
     if (!nn_ready(h)) return fail(TZ_ENOWEIGHTS, "no weights");
     if (which < 0 || which > 2 || count <= 0 || count > h->d.Q || !out) return fail(TZ_EINVAL, "bad argument");
-    const int n = h->d.n, ch = which == 2 ? 64 : 256;
+    const int n = h->d.n, ch = which == 2 ? 64 : 256;  // 2: the 16-bit input planes of the first convolution
     const size_t total = (size_t)count * n * n * ch;
     Scratch s;
     float* dout;

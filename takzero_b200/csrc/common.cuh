@@ -28,7 +28,8 @@ struct __align__(16) TzState {
     uint8_t pad0;
     uint16_t ply;
     uint16_t reversible_plies;
-    uint8_t pad1[14];
+    uint8_t pad1[14];  // device copies in the evaluation queue keep derived data here (encode.cuh): pad1[0] = white -
+                       // black top flats, bytes 372..383 = the position's scalar input planes as 16-bit pairs
 };
 static_assert(sizeof(TzState) == 384, "TzState must be 384 bytes");
 
@@ -73,6 +74,7 @@ enum {
     TZ_ERR_SET_EMPTY = 64,
     TZ_ERR_REPLAY_FULL = 128,
     TZ_ERR_NETWORK_STALL = 256,
+    TZ_ERR_WEIGHTS_MISMATCH = 512,
 };
 
 // Device-side view of one handle, passed by value to every kernel.
@@ -95,9 +97,18 @@ struct TzDev {
     TzState* leaf_state; // [G] leaf positions, by queue slot
     uint16_t* actions;   // [G][M] legal moves of the leaf, by queue slot
     int* n_actions;      // [G] by queue slot
+    uint32_t* sq_ranges; // [Q][36] by queue slot and square (row * N + col): index of the first legal move that starts
+                         // on the square | number of such moves << 16 (moves of one square are contiguous)
     float* logits;       // [G][M] legal-move logits, by queue slot
     float* value;        // [G] by queue slot
     float* variance;     // [G] by queue slot
+    // device network (nn.cu): when nn_head_feat is set, k_expand computes value / variance of queue slot q from the two
+    // head features per row the last tower convolution left there, instead of reading value[] / variance[]
+    int nn_f16;                      // 16-bit type of the active weight set (the queued scalar planes are stored in it)
+    const float* nn_head_feat;       // [Q * N*N][2]
+    const float* nn_head_misc;       // conv biases, linear weights / biases of the value and UBE heads
+    const uint32_t* nn_novelty_set;  // 2^32-bit set or null (empty)
+    const uint32_t* nn_novelty_idx;  // [Q] hash index of every queued position
     const float* ln_table;  // exploration_rate(n), n < TZ_LN_TABLE (host libm logf)
     // sequential halving
     uint16_t* set_child;  // [G][TZ_MAX_K] candidate set (root child index)

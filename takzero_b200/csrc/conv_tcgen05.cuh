@@ -51,6 +51,17 @@
 // the last tower layer's epilogue) use rows of all positions.  A chunk's first layer waits until the chunk two
 // before it has completely finished (chunk_done), because it overwrites that chunk's activation set.
 //
+// First and last layer talk to the search directly (BASELINE north star (3) / (4)):
+// * Layer::enc_states: the A producer warp of the input convolution builds its halo tile from the queued TzState
+//   records (game_repr, network/repr.rs:169-228: 64 16-bit channels per square, written straight into the canonical
+//   UMMA layout with st.shared, then fence.proxy.async + a plain mbarrier arrive) -- the input planes never exist in
+//   global memory.
+// * Layer::g_out: the epilogue of the policy convolution keeps only the logits of the legal moves
+//   (net6_simhash.rs:277-306 `gather`): thread = (position, square) looks up the moves that start on its square
+//   (TzDev::sq_ranges, contiguous in possible_moves order), stages its 32 channels of the current block in shared
+//   memory and stores logit[move_channel] to the queue's logit row.  The [positions][9036] f32 policy tensor
+//   (302 MB per pass of 8192 positions) is never written.
+//
 // TZ_DEBUG_TIMING is a compile-time tuning experiment (tools/build_variant.sh); the numbers it produced for
 // the earlier row-major one-CTA / pair kernels are in profiles/r1_conv_timing.txt.
 #pragma once
@@ -58,6 +69,8 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+
+#include "encode.cuh"
 
 namespace conv {
 
@@ -80,34 +93,40 @@ constexpr int N_OUT = 256;
 constexpr int THREADS = 256;
 constexpr int W_EPI0 = 0, W_APROD = 4, W_BPROD = 5, W_MMA = 6, W_ALLOC = 7;
 constexpr int MASK_BYTES = 36 * 9 * 16;        // [N*N][9 taps] 128-bit lane masks
+constexpr int GATHER_BYTES = 4 * 32 * 32 * 4;  // policy epilogue: 32 rows x 32 channels f32 per epilogue warp
 constexpr int SMEM_BYTES =
     A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + 4096 /*bias, one copy per epilogue warp*/ + 512 /*barriers*/ +
-    MASK_BYTES;
+    MASK_BYTES + GATHER_BYTES;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget of one CTA");
 constexpr int MAX_LAYERS = 48;                 // layers one launch can chain (net5: 40 tower convolutions)
 
 struct Layer {
-    const __nv_bfloat16* in;        // [cin/8][rows][8] activations
+    const __nv_bfloat16* in;        // [cin/8][rows][8] activations of the chunk's set; null for the encoding layer
+    const TzState* enc_states;      // input convolution: the queued positions (row = position * N*N + square), the A
+                                    // tile is encoded from them (pad1[0] holds white - black top flats)
     const __nv_bfloat16* w;         // [cin/64][9 taps][2 halves][8][128][8] pre-arranged weight blocks
     const float* bias;              // [256]
     const __nv_bfloat16* residual;  // [32][rows_set][8] or null
     __nv_bfloat16* out_act;         // [32][rows_set][8] or null
-    float* out_f32;                 // [64][f32_rows][4] (policy logits, global rows without guard) or null
     const float* head_w;            // [2][256] value / UBE 1x1 convolution weights, or null
-    float* head_out;                // [f32_rows][2]: the two head dot products of every (global) row
-    int cin;                        // channels of `in` (multiple of 64)
+    float* head_out;                // [positions * N*N][2]: the two head dot products of every (global) row
+    // policy convolution: legal-logit gather in the epilogue (all by position = evaluation-queue slot)
+    float* g_out;                   // [positions][g_stride] logits of the listed moves, or null
+    const uint16_t* g_actions;      // [positions][g_stride] moves
+    const uint32_t* g_ranges;       // [positions][36] per square: index of its first move | count << 16 (indices into
+                                    // g_perm when that is set, else into g_actions directly)
+    const uint16_t* g_perm;         // [positions][g_stride] move indices grouped by square, or null (already grouped)
+    int g_stride;
+    int cin;                        // input channels (multiple of 64)
     int relu;
-    int in_global;                  // 1: `in` holds all positions (input planes, rows_global per plane);
-                                    // 0: `in` is the chunk's activation set like residual / out_act
 };
 
 struct Params {
     Layer layers[MAX_LAYERS];       // run back to back; layer l reads what layer l-1 wrote
     int n_layers;
-    long long rows_global;          // rows per chunk plane of a buffer holding all positions (incl. guard + halo)
     long long rows_set;             // rows per chunk plane of one activation set
     long long set_stride;           // elements between activation set 0 (even chunks) and set 1 (odd chunks)
     int chunk_min_tiles;            // least pair tiles (256 rows) per chunk; huge: the whole launch is one chunk
-    long long f32_rows;
     const int* count_ptr;           // number of positions (device), or null: use count_max
     int count_max;
     int n;                          // board size
@@ -341,6 +360,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
     const uint32_t t_full = b_empty + 8 * B_STAGES, t_empty = t_full + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * A_STAGES + 3 * B_STAGES + 4);
     uint4* s_masks = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(bars) + 512);
+    float* s_gather = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_masks) + MASK_BYTES);
 
     const int count = p.count_ptr ? *p.count_ptr : p.count_max;
     const int nn = p.n * p.n;
@@ -386,30 +406,89 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
     const uint32_t a_sig = rank == 0 ? a_full : a_land, b_sig = rank == 0 ? b_full : b_land;
 
     if (warp == W_APROD) {
-        // ---- A producer (both CTAs): this CTA's 144-row halo tile, 8 chunk planes of 2304 B per stage
-        if (lane == 0) {
-            int stage = 0, phase = 0;
-            for (int item = pair; item < items; item += npairs) {
-                const Item it = sched.at(item);
-                const int layer = it.layer, pt = it.pt;
-                const Layer& L = p.layers[layer];
+        // ---- A producer (both CTAs): this CTA's 144-row halo tile, one 64-channel block per stage.  Every lane walks
+        // the item sequence (stage / phase stay warp-uniform); lane 0 issues the bulk copies of ordinary layers, all
+        // lanes build the tile of the encoding layer.
+        int stage = 0, phase = 0;
+        for (int item = pair; item < items; item += npairs) {
+            const Item it = sched.at(item);
+            const int layer = it.layer, pt = it.pt;
+            const Layer& L = p.layers[layer];
+            const int t = pt * 2 + (int)rank;
+            if (L.enc_states != nullptr) {
+                // ---- input convolution: encode rows [t*128 - HALO, t*128 + 128 + HALO) of the chunk from the queued
+                // positions (rows outside the chunk are never read unmasked: a tap only looks at squares of the same
+                // position, and positions do not straddle chunks)
+                if (lane == 0) {
+                    if (it.chunk >= 2 && p.n_layers > 1)  // overwrites nothing itself, but its epilogue does: see below
+                        wait_counter(p.chunk_done + it.chunk - 2, 8u * (unsigned)sched.chunk_tiles, p.status);
+                    mbar_wait(a_empty + 8 * stage, phase ^ 1);
+                }
+                __syncwarp();
+#ifdef TZ_DEBUG_TIMING
+                const long long enc_t0 = clock64();
+#endif
+                uint8_t* dst = a_smem + stage * A_STAGE_BYTES;
+                const int first = t * TILE_M - HALO;  // chunk-relative row of tile row 0 (rows of a launch fit 31 bits)
+                // a lane owns rows lane, lane + 32, ...: all loads first (they are independent), then the encoding
+                constexpr int RPL = (A_ROWS + 31) / 32;
+                uint64_t stack[RPL];
+                uint4 tail[RPL];     // bytes 368..383 of the state: pad1[0], then the three scalar words
+                uint32_t hts[RPL];   // height | top << 8 | to_move << 16, or ~0u for a row outside the chunk
+#pragma unroll
+                for (int k = 0; k < RPL; k++) {
+                    const int r = lane + 32 * k;
+                    const int rel = first + r;
+                    hts[k] = 0xffffffffu;
+                    stack[k] = 0;
+                    tail[k] = make_uint4(0u, 0u, 0u, 0u);
+                    if (r < A_ROWS && rel >= 0 && rel < it.rows) {
+                        const unsigned grow = (unsigned)(it.chunk * sched.chunk_rows + rel);
+                        const int q = (int)(grow / (unsigned)nn), sq = (int)(grow - (unsigned)q * (unsigned)nn);
+                        const uint8_t* st = reinterpret_cast<const uint8_t*>(L.enc_states + q);
+                        stack[k] = *reinterpret_cast<const uint64_t*>(st + 8 * sq);
+                        hts[k] = (uint32_t)st[288 + sq] | ((uint32_t)st[324 + sq] << 8) | ((uint32_t)st[360] << 16);
+                        tail[k] = *reinterpret_cast<const uint4*>(st + 368);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < RPL; k++) {
+                    const int r = lane + 32 * k;
+                    if (r >= A_ROWS) continue;
+                    uint8_t* row = dst + r * 16;
+                    if (hts[k] != 0xffffffffu) {
+                        const uint64_t ones = enc::square_indicator_bits(stack[k], (int)(hts[k] & 0xff), (int)((hts[k] >> 8) & 0xff),
+                                                                         (int)((hts[k] >> 16) & 0xff), p.n);
+                        enc::encode_square16_smem(row, A_KC_BYTES, ones, tail[k].y, tail[k].z, tail[k].w, p.n, p.f16);
+                    } else {
+#pragma unroll
+                        for (int kc = 0; kc < 8; kc++) *reinterpret_cast<uint4*>(row + kc * A_KC_BYTES) = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                }
+                // generic-proxy writes -> the tensor core's (async proxy) reads, then publish the stage
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_sig + 8 * stage);
+#ifdef TZ_DEBUG_TIMING
+                if (pair == 0 && rank == 0 && lane == 0 && item < 2 * npairs) printf("encode of one tile: %lld cycles\n", clock64() - enc_t0);
+#endif
+                if (++stage == A_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+                continue;
+            }
+            const int kblocks = L.cin >> 6;
+            if (lane == 0) {
                 // rows [t*128 - HALO, t*128 + 128 + HALO) of the previous layer's output: CTA tiles t-1, t, t+1, i.e.
                 // pair tiles {pt-1, pt} for rank 0 and {pt, pt+1} for rank 1; waited for per 64-channel block below
                 const unsigned need = 8u * (unsigned)layer;
                 const unsigned* prog = p.progress + ((size_t)it.chunk * sched.chunk_tiles) * 4;
                 const int lo = pt - 1 + (int)rank;
-                if (layer == 0 && it.chunk >= 2 && p.n_layers > 1) {
-                    // this chunk's first layer overwrites the activation set of chunk - 2: all of it must be done
-                    const unsigned all_warps = 8u * (unsigned)sched.chunk_tiles;
-                    wait_counter(p.chunk_done + it.chunk - 2, all_warps, p.status);
-                }
-                const int t = pt * 2 + (int)rank;
-                const size_t in_rows = L.in_global ? (size_t)p.rows_global : (size_t)p.rows_set;
-                const size_t in_first = L.in_global ? (size_t)it.chunk * sched.chunk_rows : 0;  // row of the chunk
-                const __nv_bfloat16* in_base = L.in_global ? L.in : L.in + (size_t)(it.chunk & 1) * p.set_stride;
+                const __nv_bfloat16* in_base = L.in + (size_t)(it.chunk & 1) * p.set_stride;
                 const uint8_t* src_tile =
-                    reinterpret_cast<const uint8_t*>(in_base) + (in_first + (size_t)(p.guard + t * TILE_M - HALO)) * 16;
-                const int kblocks = L.cin >> 6;
+                    reinterpret_cast<const uint8_t*>(in_base) + (size_t)(p.guard + t * TILE_M - HALO) * 16;
+                int st = stage, ph = phase;
                 for (int kb = 0; kb < kblocks; kb++) {
                     if (layer > 0 && (fine || kb == 0)) {
                         // fine: wait for this 64-channel block only; else for the whole tile (its last block)
@@ -418,29 +497,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                             if (q >= 0 && q < it.tiles) wait_counter(prog + q * 4 + blk, need, p.status);
                         fence_proxy_async();
                     }
-                    mbar_wait(a_empty + 8 * stage, phase ^ 1);
-#ifdef TZ_EXP_DOUBLE_A  // energy experiment: every activation block is fetched twice
-                    mbar_arrive_expect_tx(a_sig + 8 * stage, 2 * A_STAGE_BYTES);
-#else
-                    mbar_arrive_expect_tx(a_sig + 8 * stage, A_STAGE_BYTES);
-#endif
-                    const uint32_t dst = smem_u32(a_smem + stage * A_STAGE_BYTES);
+                    mbar_wait(a_empty + 8 * st, ph ^ 1);
+                    mbar_arrive_expect_tx(a_sig + 8 * st, A_STAGE_BYTES);
+                    const uint32_t dst = smem_u32(a_smem + st * A_STAGE_BYTES);
 #pragma unroll
                     for (int kc = 0; kc < 8; kc++)
-                        bulk_g2s(dst + kc * A_KC_BYTES, src_tile + (size_t)(kb * 8 + kc) * in_rows * 16, A_KC_BYTES,
-                                 a_sig + 8 * stage);
-#ifdef TZ_EXP_DOUBLE_A
-#pragma unroll
-                    for (int kc = 0; kc < 8; kc++)
-                        bulk_g2s(dst + kc * A_KC_BYTES, src_tile + (size_t)(kb * 8 + kc) * in_rows * 16, A_KC_BYTES,
-                                 a_sig + 8 * stage);
-#endif
-                    if (++stage == A_STAGES) {
-                        stage = 0;
-                        phase ^= 1;
+                        bulk_g2s(dst + kc * A_KC_BYTES, src_tile + (size_t)(kb * 8 + kc) * (size_t)p.rows_set * 16,
+                                 A_KC_BYTES, a_sig + 8 * st);
+                    if (++st == A_STAGES) {
+                        st = 0;
+                        ph ^= 1;
                     }
                 }
             }
+            for (int kb = 0; kb < kblocks; kb++)
+                if (++stage == A_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
         }
     } else if (warp == W_BPROD) {
         // ---- B producer (both CTAs): this CTA's half (128 of the 256 N rows) of every weight block
@@ -452,22 +526,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                 const int blocks = (L.cin >> 6) * 9;
                 for (int blk = 0; blk < blocks; blk++) {
                     mbar_wait(b_empty + 8 * stage, phase ^ 1);
-#if defined(TZ_EXP_NO_B) || defined(TZ_EXP_HALF_B)
-                    // energy experiments (INVALID results): only the first B_STAGES weight blocks are ever copied
-                    // (NO_B), or every other one (HALF_B)
-#ifdef TZ_EXP_HALF_B
-                    if (blk & 1) {
-#else
-                    if (item != pair || blk >= B_STAGES) {
-#endif
-                        mbar_arrive(b_sig + 8 * stage);
-                    } else
-#endif
-                    {
-                        mbar_arrive_expect_tx(b_sig + 8 * stage, B_STAGE_BYTES);
-                        bulk_g2s(smem_u32(b_smem + stage * B_STAGE_BYTES), src + (size_t)blk * 2 * B_STAGE_BYTES,
-                                 B_STAGE_BYTES, b_sig + 8 * stage);
-                    }
+                    mbar_arrive_expect_tx(b_sig + 8 * stage, B_STAGE_BYTES);
+                    bulk_g2s(smem_u32(b_smem + stage * B_STAGE_BYTES), src + (size_t)blk * 2 * B_STAGE_BYTES,
+                             B_STAGE_BYTES, b_sig + 8 * stage);
                     if (++stage == B_STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -522,8 +583,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                                    ((uint32_t)((2 * TILE_M) >> 4) << 24);
             int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0, it = 0;
 #ifdef TZ_DEBUG_TIMING
-            long long w_t = 0, w_a = 0, w_b = 0;
+            long long w_t = 0, w_a = 0, w_b = 0, w_a0 = 0;
             const long long mma_start = clock64();
+            long long gt_start;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_start));
 #endif
             for (int item = pair; item < items; item += npairs, it++) {
                 const Item wi = sched.at(item);
@@ -536,7 +599,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                 const uint4* masks0 = s_masks + ((size_t)(pt * 2) * TILE_M % nn) * 9;
                 const uint4* masks1 = s_masks + ((size_t)(pt * 2 + 1) * TILE_M % nn) * 9;
                 for (int kb = 0; kb < kblocks; kb++) {
-                    TWAIT(w_a, mbar_wait(a_full + 8 * a_stage, a_phase));
+#ifdef TZ_DEBUG_TIMING
+                    if (p.layers[wi.layer].enc_states != nullptr)
+                        TWAIT(w_a0, mbar_wait(a_full + 8 * a_stage, a_phase));
+                    else
+#endif
+                        TWAIT(w_a, mbar_wait(a_full + 8 * a_stage, a_phase));
                     const uint32_t a_base = smem_u32(a_smem + a_stage * A_STAGE_BYTES);
                     // tap order: the centre tap first (no mask, it initialises every lane), then the rest
                     for (int ti = 0; ti < 9; ti++) {
@@ -572,8 +640,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
             }
 #ifdef TZ_DEBUG_TIMING
             if ((pair == 0 || pair == 40) && lane == 0)
-                printf("pair %d mma: tiles %d total %lld wait_tmem %lld wait_a %lld wait_b %lld\n", pair, it,
-                       clock64() - mma_start, w_t, w_a, w_b);
+            {
+                long long gt_end;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_end));
+                printf("pair %d mma: tiles %d total %lld wait_tmem %lld wait_a %lld (encoded tiles %lld) wait_b %lld ns %lld\n",
+                       pair, it, clock64() - mma_start, w_t, w_a, w_a0, w_b, gt_end - gt_start);
+            }
 #endif
         }
     } else if (warp >= W_EPI0 && warp < W_EPI0 + 4) {
@@ -597,7 +669,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
             const size_t set_off = (size_t)(wi.chunk & 1) * p.set_stride;
             const __nv_bfloat16* residual = L.residual ? L.residual + set_off : nullptr;
             __nv_bfloat16* out_act = L.out_act ? L.out_act + set_off : nullptr;
-            float* out_f32 = L.out_f32;
             const float* head_w = L.head_w;
             const int relu = L.relu;
             const int acc = it & 1;
@@ -607,6 +678,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
             const size_t grow = (size_t)(p.guard + rel) * 8;  // element offset of the row inside a plane
             const size_t grel = (size_t)wi.chunk * sched.chunk_rows + (size_t)rel;  // row among all positions
             float head_v = 0.0f, head_u = 0.0f;
+            // policy layer: the legal moves that start on this thread's square (their logits are all it keeps)
+            float* g_row = nullptr;
+            const uint16_t* g_act = nullptr;
+            const uint16_t* g_perm = nullptr;
+            int g_first = 0, g_count = 0;
+            // channels of the square's first eight moves (8 bits each; g_valid says which slots hold one), decoded once
+            // per tile, and the 32-channel blocks that hold any of the square's moves
+            uint32_t g_ch0 = 0, g_ch1 = 0, g_valid = 0, g_blocks = 0;
+            if (L.g_out != nullptr && valid) {
+                const unsigned ug = (unsigned)grel;
+                const int q = (int)(ug / (unsigned)nn), sq = (int)(ug - (unsigned)q * (unsigned)nn);
+                const uint32_t range = L.g_ranges[(size_t)q * 36 + sq];
+                g_first = (int)(range & 0xffffu);
+                g_count = (int)(range >> 16);
+                g_row = L.g_out + (size_t)q * L.g_stride;
+                g_act = L.g_actions + (size_t)q * L.g_stride;
+                g_perm = L.g_perm ? L.g_perm + (size_t)q * L.g_stride : nullptr;
+                for (int m = 0; m < g_count; m++) {
+                    const int i = g_perm ? (int)g_perm[g_first + m] : g_first + m;
+                    const int ch = enc::move_channel(p.n, g_act[i]);
+                    if (ch < 0 || ch >= N_OUT) continue;  // cannot be a move of this board (host lists only)
+                    g_blocks |= 1u << (ch >> 5);
+                    if (m < 4) g_ch0 |= (uint32_t)ch << (8 * m);
+                    else if (m < 8) g_ch1 |= (uint32_t)ch << (8 * (m - 4));
+                    if (m < 8) g_valid |= 1u << m;
+                }
+            }
+            float* stg = s_gather + (wq * 32 + lane) * 32;  // this thread's 32 staged channels (XOR-swizzled by lane)
             mbar_wait(t_full + 8 * acc, (it >> 1) & 1);
             tc_fence_after();
             // Inside a fused launch the residual rows were written by another SM two layers ago.  One gpu-scope
@@ -649,11 +748,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                                 make_uint4(pack16(f[j * 8], f[j * 8 + 1], p.f16), pack16(f[j * 8 + 2], f[j * 8 + 3], p.f16),
                                            pack16(f[j * 8 + 4], f[j * 8 + 5], p.f16), pack16(f[j * 8 + 6], f[j * 8 + 7], p.f16));
                     }
-                    if (out_f32) {
+                    if ((g_blocks >> (c0 >> 5)) & 1u) {
+                        // own row only: the thread stages its 32 channels and picks the legal ones by dynamic index
 #pragma unroll
-                        for (int j = 0; j < 8; j++)
-                            *reinterpret_cast<float4*>(out_f32 + ((size_t)(c0 / 4 + j) * (size_t)p.f32_rows + grel) * 4) =
-                                make_float4(f[j * 4], f[j * 4 + 1], f[j * 4 + 2], f[j * 4 + 3]);
+                        for (int j = 0; j < 32; j++) stg[j ^ lane] = f[j];
+#pragma unroll
+                        for (int m = 0; m < 8; m++) {
+                            const int ch = (int)(((m < 4 ? g_ch0 : g_ch1) >> (8 * (m & 3))) & 0xffu);
+                            if (((g_valid >> m) & 1u) && (ch & ~31) == c0) {
+                                const int i = g_perm ? (int)g_perm[g_first + m] : g_first + m;
+                                g_row[i] = stg[(ch & 31) ^ lane];
+                            }
+                        }
+                        for (int m = 8; m < g_count; m++) {  // squares with more than eight moves: decode again
+                            const int i = g_perm ? (int)g_perm[g_first + m] : g_first + m;
+                            const int ch = enc::move_channel(p.n, g_act[i]);
+                            if (ch >= 0 && (ch & ~31) == c0) g_row[i] = stg[(ch & 31) ^ lane];
+                        }
                     }
                     if (head_w) {  // value / UBE 1x1 convolutions over the tower output (net6_simhash.rs:88-119)
 #pragma unroll

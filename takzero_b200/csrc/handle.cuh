@@ -6,6 +6,7 @@
 #include "common.cuh"
 
 struct NnState;  // nn.cu
+struct TzComm;   // comm.cu
 
 struct tz_handle {
     int device = 0;
@@ -18,6 +19,12 @@ struct tz_handle {
     void* agent_ctx = nullptr;
     NnState* nn = nullptr;
     int nn_f16 = 1;  // 16-bit type the next tz_set_weights converts to: 1 fp16 (default), 0 bf16
+    TzComm* comm = nullptr;  // NCCL communicator of this rank (tz_comm_init), null = single GPU
+    unsigned long long* reduce_buf = nullptr;  // device staging of tz_allreduce_sum
+    // tz_debug_network_mode (test / measurement hooks; the defaults are the product)
+    int dbg_per_layer = 0;     // one launch per convolution instead of the fused launch
+    int dbg_chunk_tiles = -1;  // minimum pair tiles per chunk (-1: default 150, 0: one chunk)
+    int dbg_drop_progress = 0; // CTA pair 0 withholds its tiles (watchdog test)
     // device staging of host-facing arguments / results
     float* betas = nullptr;
     float* gumbel = nullptr;

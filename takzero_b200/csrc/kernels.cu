@@ -12,6 +12,7 @@
 //   k_restart       batched.rs:185-203, env.rs:65-79
 //   k_targets       node/policy.rs:23-48, node/mod.rs:215-230
 //   k_select_actions node/mod.rs:132-207
+#include "encode.cuh"
 #include "kernels.cuh"
 #include "rules.cuh"
 #include "tree.cuh"
@@ -78,15 +79,28 @@ __device__ __forceinline__ int warp_forward(const TzDev& d, const GameTree& t, T
 
 // Forward::NeedsNetwork: legal moves + leaf position into evaluation-queue slot q
 __device__ __forceinline__ bool warp_enqueue(const TzDev& d, int g, int q, TzState* st, uint16_t* moves, int lane) {
-    const int cnt = warp_movegen(st, d.n, moves, lane);
+    const int cnt = warp_movegen(st, d.n, moves, lane, d.sq_ranges + (size_t)q * TZ_MAX_SQ);
     if (cnt < 0 || cnt > d.M) {
+        // reported, never truncated; the queue slot is already taken, so it is filled with a well-formed entry without
+        // moves (the agent and k_expand then have nothing to read out of bounds)
         flag_error(d, TZ_ERR_TOO_MANY_MOVES, lane);
+        if (lane == 0) {
+            d.nn_queue[q] = g;
+            d.n_actions[q] = 0;
+        }
+        for (int sq = lane; sq < TZ_MAX_SQ; sq += 32) d.sq_ranges[(size_t)q * TZ_MAX_SQ + sq] = 0;
+        warp_store_state(&d.leaf_state[q], st, lane);
         return false;
     }
+    // what the network's input encoding needs of the whole position rides along in the queued copy: the flat count
+    // difference and the six scalar planes (network/repr.rs:199-227)
+    const TzBoards b = warp_boards(st, d.nn, lane);
     if (lane == 0) {
         d.nn_queue[q] = g;
         d.n_actions[q] = cnt;
+        enc::store_position_scalars(st, __popcll(b.flat[0]) - __popcll(b.flat[1]), d.n, d.half_komi, d.nn_f16);
     }
+    __syncwarp();
     warp_store_state(&d.leaf_state[q], st, lane);
     uint16_t* out = d.actions + (size_t)q * d.M;
     for (int i = lane; i < cnt; i += 32) out[i] = moves[i];
@@ -200,7 +214,13 @@ __device__ __forceinline__ void warp_expand(const TzDev& d, int g, int q, const 
     const uint16_t* act = d.actions + (size_t)q * d.M;
     for (int i = lane; i < n; i += 32) p[i] = lg[i];
     __syncwarp();
-    float value = d.value[q], variance = d.variance[q];
+    float value, variance;
+    if (d.nn_head_feat != nullptr)  // device network: the heads' last step happens here (encode.cuh)
+        enc::warp_heads(d.nn_head_feat, d.nn_head_misc, d.nn_novelty_set, d.nn_novelty_idx, q, d.nn, lane, &value, &variance);
+    else {
+        value = d.value[q];
+        variance = d.variance[q];
+    }
     // NaN / infinite network outputs: the reference panics (net6_simhash.rs:304, NotNan).  Here the error bit is
     // raised and the outputs are replaced by finite ones (uniform priors, zero logits / value / variance), so that no
     // NaN ever enters a tree: comparisons against NaN would derail the argmax / ranking code that indexes the arena.
@@ -374,8 +394,11 @@ __global__ void __launch_bounds__(32 * WPB) k_gumbel_init(TzDev d, int k, const 
     const uint32_t first = t.first[0];
     float* keys = s_key[warp];
     bool bad = false;
+    // batched.rs:233-239 zips one draw with every child: a caller whose rows are shorter than a root's child list has
+    // not supplied them -- reported (never another game's noise), the children without a draw are ordered last
+    if (n > stride) flag_error(d, TZ_ERR_TOO_MANY_MOVES, lane);
     for (int i = lane; i < n; i += 32) {
-        const float key = fadd(t.logit[first + i], gumbel[(size_t)g * stride + i]);
+        const float key = i < stride ? fadd(t.logit[first + i], gumbel[(size_t)g * stride + i]) : -__int_as_float(0x7f800000);
         bad = bad || key != key;
         // a NaN key (NaN noise, or -inf logit + inf noise) would give several children the same rank and leave
         // slots of the candidate set unwritten: order it last instead (the error bit is raised below)

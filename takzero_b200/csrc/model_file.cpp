@@ -710,9 +710,10 @@ extern "C" TZ_API int tz_read_model_file(const char* path, tz_model_tensor_fn fn
 }
 
 // Net::load (network/mod.rs:20-27, net6_simhash.rs:164-181): VarStore::load of `path`, then the SimHash set from
-// the sidecar `bitvec.bin` in the same directory.  A missing sidecar is the empty set of a fresh network here (the
-// reference returns an error); networks without `simhash_matrix` (net5) skip the novelty part.
-extern "C" TZ_API int tz_load_model(tz_handle* h, const char* path) {
+// the sidecar `bitvec.bin` in the same directory.  A missing sidecar is an error, as in the reference (with an empty
+// set every local uncertainty would silently become 4.0); allow_missing_set = 1 takes it as the empty set of a freshly
+// initialised network instead.  Networks without `simhash_matrix` / `lcghash_init` (net5) skip the novelty part.
+extern "C" TZ_API int tz_load_model_ex(tz_handle* h, const char* path, int allow_missing_set) {
     if (!h || !path) return model_fail(TZ_EINVAL, "null argument");
     std::vector<NamedTensor> ts;
     try {
@@ -737,23 +738,31 @@ extern "C" TZ_API int tz_load_model(tz_handle* h, const char* path) {
         if (ts[i].shape.size() > 4) continue;
         args.push_back(tz_tensor_t{names[i].c_str(), ts[i].data.data(), ts[i].shape.data(), (int)ts[i].shape.size()});
     }
-    int rc = tz_set_weights(h, args.data(), (int)args.size());
-    if (rc != TZ_OK) return rc;
+    // the sidecar is read (or found missing) before the current model is touched: a failed load keeps the old one
+    std::vector<uint8_t> bits;
     if (simhash || lcghash) {
         std::string dir = path;
         const size_t slash = dir.find_last_of('/');
         dir = slash == std::string::npos ? std::string() : dir.substr(0, slash + 1);
-        std::vector<uint8_t> bits;
         FILE* f = std::fopen((dir + "bitvec.bin").c_str(), "rb");
         if (f) {
             bits.resize(size_t(1) << 29);
             const size_t got = std::fread(bits.data(), 1, bits.size(), f);
             std::fclose(f);
             if (got != bits.size()) return model_fail(TZ_EINVAL, dir + "bitvec.bin: expected 2^29 bytes");
+        } else if (!allow_missing_set) {
+            return model_fail(TZ_EINVAL, dir + "bitvec.bin is missing (the novelty set saved next to the model, "
+                              "net6_simhash.rs:164-181); tz_load_model_ex(.., 1) loads the model with an empty set");
         }
+    }
+    int rc = tz_set_weights(h, args.data(), (int)args.size());
+    if (rc != TZ_OK) return rc;
+    if (simhash || lcghash) {
         rc = lcghash ? tz_set_lcghash(h, lcghash->data.data(), bits.empty() ? nullptr : bits.data())
                      : tz_set_simhash(h, simhash->data.data(), bits.empty() ? nullptr : bits.data());
         if (rc != TZ_OK) return rc;
     }
     return TZ_OK;
 }
+
+extern "C" TZ_API int tz_load_model(tz_handle* h, const char* path) { return tz_load_model_ex(h, path, 0); }

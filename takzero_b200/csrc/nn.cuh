@@ -7,10 +7,17 @@ void nn_free(tz_handle* h);
 const char* nn_last_error();
 int nn_set_weights(tz_handle* h, const char* const* names, const float* const* data, const long long* const* shapes,
                    const int* ndims, int count);
-// policy/value/uncertainty of the queued leaf positions -> d.logits / d.value / d.variance
+int nn_broadcast_weights(tz_handle* h, const char* const* names, const float* const* data, const long long* const* shapes,
+                         const int* ndims, int count, int res_blocks, int root);
+int nn_generation_ms(tz_handle* h, double* ms, unsigned long long* generation);
+int nn_debug_weight_set(tz_handle* h, unsigned char* out, size_t cap, size_t* size);
+// k_expand finishes the heads itself when the agent is the device network: refresh the pointers it uses
+void nn_bind_search(tz_handle* h);
+// policy / value / uncertainty of the queued leaf positions: legal logits -> d.logits, head features for k_expand
 int nn_forward_queue(tz_handle* h);
-int nn_forward(tz_handle* h, const TzState* states, const int* count_ptr, int count_max, const uint16_t* actions,
-               const int* n_actions, float* logits, float* value, float* variance);
+// the same for `count` host-supplied positions already in d.leaf_state / d.actions / d.n_actions -> d.logits,
+// d.value, d.variance
+int nn_forward_host(tz_handle* h, int count);
 int nn_encode_planes(tz_handle* h, const TzState* states, int count, float* out_f32);
 void nn_set_layer_limit(tz_handle* h, int limit);
 int nn_debug_read(tz_handle* h, int which, int count, float* out_dev);

@@ -188,8 +188,10 @@ __device__ __forceinline__ void square_dirs(const TzState* s, int n, int row, in
 // Legal moves in fast-tak order (pinned by runs/*.txt): squares
 // file-major, placements flat/wall/cap, spreads carry-major x (+,-,<,>) x descending
 // lexicographic drops.  Writes u16 moves to `out` (shared memory) and returns the
-// count (or -1 when more than TZ_MAX_MOVES).  Warp-convergent.
-__device__ __forceinline__ int warp_movegen(const TzState* s, int n, uint16_t* out, int lane) {
+// count (or -1 when more than TZ_MAX_MOVES).  Warp-convergent.  `ranges` (optional, global memory, 36 entries indexed by
+// square = row * N + col) receives for every square the index of its first move | its move count << 16: the moves that
+// start on one square are contiguous, which is what the policy convolution's epilogue gathers by (conv_tcgen05.cuh).
+__device__ __forceinline__ int warp_movegen(const TzState* s, int n, uint16_t* out, int lane, uint32_t* ranges = nullptr) {
     const int nn = n * n;
     const int me = s->to_move;
     const bool opening = s->ply < 2;
@@ -237,6 +239,13 @@ __device__ __forceinline__ int warp_movegen(const TzState* s, int n, uint16_t* o
     const int total = total0 + __shfl_sync(FULL_MASK, inc1, 7);
     if (total > TZ_MAX_MOVES) return -1;
     int off[2] = {inc0 - cnt[0], total0 + inc1 - cnt[1]};
+    if (ranges != nullptr) {
+#pragma unroll
+        for (int slot = 0; slot < 2; slot++) {
+            const int k = lane + 32 * slot;
+            if (k < nn) ranges[(k % n) * n + k / n] = (uint32_t)off[slot] | ((uint32_t)cnt[slot] << 16);
+        }
+    }
     // pass 2: each lane writes its squares' moves
 #pragma unroll
     for (int slot = 0; slot < 2; slot++) {

@@ -39,6 +39,16 @@ def _declare():
     capi.declare("tz_debug_activations", [vp, i32, i32, vp], i32)
     capi.declare("tz_debug_time_tower", [vp, i32, i32, C.POINTER(C.c_double)], i32)
     capi.declare("tz_load_model", [vp, C.c_char_p], i32)
+    capi.declare("tz_load_model_ex", [vp, C.c_char_p, i32], i32)
+    capi.declare("tz_debug_network_mode", [vp, i32, i32, i32], i32)
+    capi.declare("tz_debug_weight_set", [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)], i32)
+    capi.declare("tz_debug_expf", [vp, vp, i32, vp], i32)
+    capi.declare("tz_comm_unique_id", [vp], i32)
+    capi.declare("tz_comm_init", [vp, vp, i32, i32], i32)
+    capi.declare("tz_comm_destroy", [vp], i32)
+    capi.declare("tz_broadcast_weights", [vp, C.POINTER(_Tensor), i32, i32, i32], i32)
+    capi.declare("tz_weight_generation", [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_double)], i32)
+    capi.declare("tz_allreduce_sum", [vp, vp, i32], i32)
     capi.declare("tz_read_model_file", [C.c_char_p, _MODEL_TENSOR_FN, vp], i32)
     _declared = True
 
@@ -47,11 +57,7 @@ DTYPE_BF16, DTYPE_F16 = 0, 1
 DTYPE_DEFAULT = DTYPE_F16  # the library's default: the mode that meets the >= 99 % chosen-move agreement bar
 
 
-def set_weights(mcts: capi.BatchedMCTS, tensors: Dict[str, np.ndarray], dtype: int = DTYPE_DEFAULT) -> None:
-    """`Net::load`: upload named f32 tensors (PyTorch layout, names in include/takzero_b200.h); `dtype` is the
-    16-bit type of weights and activations on the device (fp16 by default)."""
-    _declare()
-    capi._check(capi.lib().tz_set_network_dtype(mcts.handle, dtype))
+def _tensor_array(tensors: Dict[str, np.ndarray]):
     keep = []
     arr = (_Tensor * len(tensors))()
     for i, (name, t) in enumerate(tensors.items()):
@@ -59,16 +65,86 @@ def set_weights(mcts: capi.BatchedMCTS, tensors: Dict[str, np.ndarray], dtype: i
         shape = (C.c_int64 * a.ndim)(*a.shape)
         keep += [a, shape]
         arr[i] = _Tensor(name.encode(), a.ctypes.data_as(C.POINTER(C.c_float)), shape, a.ndim)
+    return arr, keep
+
+
+def set_weights(mcts: capi.BatchedMCTS, tensors: Dict[str, np.ndarray], dtype: int = DTYPE_DEFAULT) -> None:
+    """`Net::load`: upload named f32 tensors (PyTorch layout, names in include/takzero_b200.h); `dtype` is the
+    16-bit type of weights and activations on the device (fp16 by default).  The tensors are staged by the library
+    before the call returns; BatchNorm folding and the weight arrangement run on the GPU beside the search."""
+    _declare()
+    capi._check(capi.lib().tz_set_network_dtype(mcts.handle, dtype))
+    arr, _keep = _tensor_array(tensors)
     capi._check(capi.lib().tz_set_weights(mcts.handle, arr, len(tensors)))
 
 
-def load_model(mcts: capi.BatchedMCTS, path: str, dtype: int = DTYPE_DEFAULT) -> None:
-    """`Net::load(path, device)` (network/mod.rs:20-27, net6_simhash.rs:164-181): read the reference's
-    `model_latest.ot` (tch VarStore archive; also a `torch.save` state dict or a TZW1 file) inside the library,
-    upload it, and take the SimHash matrix / `bitvec.bin` sidecar when the file has them."""
+def broadcast_weights(mcts: capi.BatchedMCTS, tensors: Dict[str, np.ndarray] | None, root: int = 0,
+                      res_blocks: int = 0, dtype: int = DTYPE_DEFAULT) -> None:
+    """One weight generation on every rank of the handle's communicator (`tz_broadcast_weights`, collective): the
+    root passes the tensors, the others None; also valid without a communicator (= set_weights)."""
     _declare()
     capi._check(capi.lib().tz_set_network_dtype(mcts.handle, dtype))
-    capi._check(capi.lib().tz_load_model(mcts.handle, str(path).encode()))
+    if tensors is None:
+        capi._check(capi.lib().tz_broadcast_weights(mcts.handle, None, 0, res_blocks, root))
+    else:
+        arr, _keep = _tensor_array(tensors)
+        capi._check(capi.lib().tz_broadcast_weights(mcts.handle, arr, len(tensors), res_blocks, root))
+
+
+def weight_generation(mcts: capi.BatchedMCTS):
+    """(generations so far, device milliseconds of the last one: upload + fold + broadcast)."""
+    _declare()
+    gen, ms = C.c_uint64(), C.c_double()
+    capi._check(capi.lib().tz_weight_generation(mcts.handle, C.byref(gen), C.byref(ms)))
+    return gen.value, ms.value
+
+
+def comm_unique_id() -> bytes:
+    _declare()
+    buf = C.create_string_buffer(128)
+    capi._check(capi.lib().tz_comm_unique_id(buf))
+    return buf.raw
+
+
+def comm_init(mcts: capi.BatchedMCTS, unique_id: bytes | None, nranks: int, rank: int) -> None:
+    _declare()
+    capi._check(capi.lib().tz_comm_init(mcts.handle, unique_id, nranks, rank))
+
+
+def allreduce_sum(mcts: capi.BatchedMCTS, values) -> list:
+    """Whole-job totals of per-rank counters over the handle's communicator (ncclAllReduce)."""
+    _declare()
+    a = np.ascontiguousarray(values, dtype=np.uint64)
+    capi._check(capi.lib().tz_allreduce_sum(mcts.handle, capi._ptr(a), len(a)))
+    return [int(x) for x in a]
+
+
+def debug_network_mode(mcts: capi.BatchedMCTS, per_layer_launches: bool = False, chunk_min_tiles: int = -1,
+                       drop_progress: bool = False) -> None:
+    """Test / measurement hook (`tz_debug_network_mode`): launch structure for the NEXT set_weights, watchdog test."""
+    _declare()
+    capi._check(capi.lib().tz_debug_network_mode(mcts.handle, int(per_layer_launches), chunk_min_tiles,
+                                                 int(drop_progress)))
+
+
+def weight_set(mcts: capi.BatchedMCTS) -> np.ndarray:
+    """The active weight set as bytes (parity hook for the on-device folding / arrangement)."""
+    _declare()
+    size = C.c_size_t()
+    capi._check(capi.lib().tz_debug_weight_set(mcts.handle, None, 0, C.byref(size)))
+    out = np.zeros(size.value, dtype=np.uint8)
+    capi._check(capi.lib().tz_debug_weight_set(mcts.handle, capi._ptr(out), out.size, C.byref(size)))
+    return out
+
+
+def load_model(mcts: capi.BatchedMCTS, path: str, dtype: int = DTYPE_DEFAULT, allow_missing_set: bool = False) -> None:
+    """`Net::load(path, device)` (network/mod.rs:20-27, net6_simhash.rs:164-181): read the reference's
+    `model_latest.ot` (tch VarStore archive; also a `torch.save` state dict or a TZW1 file) inside the library,
+    upload it, and take the SimHash matrix / `bitvec.bin` sidecar when the file has them (a missing sidecar is an
+    error like in the reference unless `allow_missing_set`)."""
+    _declare()
+    capi._check(capi.lib().tz_set_network_dtype(mcts.handle, dtype))
+    capi._check(capi.lib().tz_load_model_ex(mcts.handle, str(path).encode(), int(allow_missing_set)))
 
 
 def read_model_file(path: str, stored_names: bool = False) -> Dict[str, np.ndarray]:

@@ -47,6 +47,30 @@ def test_encode_golden_vector():
     m.close()
 
 
+@pytest.mark.parametrize("n,half_komi", [(4, 4), (5, 4), (6, 4)])
+@pytest.mark.parametrize("dtype", [network.DTYPE_F16, network.DTYPE_BF16])
+def test_first_convolution_input_planes_are_game_repr_in_16_bits(n, half_komi, dtype):
+    """The network never stores its input planes: the first convolution's A producer encodes them from the queued
+    positions (conv_tcgen05.cuh).  The hook runs the same device function: every value must be game_repr's
+    (repr.rs:169-228) rounded to the network's 16-bit type, channels beyond C zero."""
+    count = 96
+    games = sample_positions(n, half_komi, count, 7 * n)
+    actions = [O.possible_moves(g) for g in games]
+    m = capi.BatchedMCTS(n, half_komi, count, arena_slots=4096)
+    network.set_weights(m, net_ref.Net(n, seed=1, blocks=1).tensors(), dtype)
+    network.evaluate(m, games_to_states(games), actions)
+    got = network.debug_activations(m, 2, count)  # [count, N*N, 64]
+    want = np.stack([O.game_repr(g) for g in games]).reshape(count, -1, n * n).transpose(0, 2, 1)  # [count, N*N, C]
+    C_ = want.shape[2]
+    if dtype == network.DTYPE_F16:
+        want16 = want.astype(np.float16).astype(np.float32)
+    else:
+        want16 = torch.from_numpy(np.ascontiguousarray(want)).to(torch.bfloat16).to(torch.float32).numpy()
+    assert np.array_equal(got[:, :, :C_].view(np.uint32), want16.view(np.uint32))
+    assert (got[:, :, C_:] == 0).all()
+    m.close()
+
+
 def check_network(n, half_komi, count, blocks, seed, randomize_bn, dtype=network.DTYPE_BF16, tol=TOL):
     ref = net_ref.Net(n, seed=seed, blocks=blocks, randomize_bn=randomize_bn)
     games = sample_positions(n, half_komi, count, seed)
@@ -198,7 +222,7 @@ def test_simhash_indices_and_uncertainty():
 
 
 @pytest.mark.parametrize("n,hk,count", [(4, 4, 701), (6, 4, 333), (5, 4, 97)])
-def test_chunked_fused_launch_equals_one_chunk_and_per_layer_launches(n, hk, count, monkeypatch):
+def test_chunked_fused_launch_equals_one_chunk_and_per_layer_launches(n, hk, count):
     """The network body runs as one persistent launch whose positions are cut into chunks that walk through all
     layers on small L2-resident activation sets (conv_tcgen05.cuh).  Chunk and tile placement must not change a
     single bit: many small chunks (fewer tiles than CTA pairs, partial last tile), one chunk, and one launch per
@@ -208,13 +232,10 @@ def test_chunked_fused_launch_equals_one_chunk_and_per_layer_launches(n, hk, cou
     actions = [O.possible_moves(g) for g in games]
     states = games_to_states(games)
     outs = {}
-    for name, env in (("chunks", {"TZ_NN_CHUNK_TILES": "3"}), ("one", {"TZ_NN_CHUNK_TILES": "0"}),
-                      ("layers", {"TZ_TOWER": "layers"})):
-        for k in ("TZ_NN_CHUNK_TILES", "TZ_TOWER"):
-            monkeypatch.delenv(k, raising=False)
-        for k, v in env.items():
-            monkeypatch.setenv(k, v)
+    for name, mode in (("chunks", {"chunk_min_tiles": 3}), ("one", {"chunk_min_tiles": 0}),
+                       ("layers", {"per_layer_launches": True})):
         m = capi.BatchedMCTS(n, hk, count, arena_slots=4096)
+        network.debug_network_mode(m, **mode)
         network.set_weights(m, ref.tensors())  # the mode is read when the weights are set
         outs[name] = network.evaluate(m, states, actions)
         for _ in range(4 if name == "chunks" else 0):  # the cross-CTA hand-offs are timing dependent: repeat
@@ -232,7 +253,7 @@ def test_chunked_fused_launch_equals_one_chunk_and_per_layer_launches(n, hk, cou
     assert float(np.abs(outs["chunks"][1] - want_values).max()) <= TOL
 
 
-def test_watchdog_turns_a_stalled_dependency_into_a_status_bit(monkeypatch):
+def test_watchdog_turns_a_stalled_dependency_into_a_status_bit():
     """The fused launch waits on other CTA pairs' progress counters.  With the test hook that makes pair 0 withhold
     its tiles, the dependent pairs must not spin forever: the watchdog raises TZ_STATUS_NETWORK_STALL (256), the
     launch ends, and the handle reports the error instead of hanging the GPU."""
@@ -246,7 +267,7 @@ def test_watchdog_turns_a_stalled_dependency_into_a_status_bit(monkeypatch):
     network.set_weights(m, ref.tensors())
     good = network.evaluate(m, games_to_states(games), actions)
     assert m.status() == 0
-    monkeypatch.setenv("TZ_EXP_DROP_PROGRESS", "1")
+    network.debug_network_mode(m, drop_progress=True)
     t0 = time.perf_counter()
     try:
         network.evaluate(m, games_to_states(games), actions)
@@ -255,7 +276,6 @@ def test_watchdog_turns_a_stalled_dependency_into_a_status_bit(monkeypatch):
     assert time.perf_counter() - t0 < 60.0
     assert m.status() & 256
     m.close()
-    monkeypatch.delenv("TZ_EXP_DROP_PROGRESS")
     m = capi.BatchedMCTS(n, hk, count, arena_slots=4096)  # a fresh handle works as before
     network.set_weights(m, ref.tensors())
     again = network.evaluate(m, games_to_states(games), actions)
@@ -293,15 +313,19 @@ def test_load_model_from_tch_archive_with_bitvec_sidecar(tmp_path):
     for x, y in zip(want[0], got[0]):
         assert np.array_equal(x, y)
     assert np.array_equal(want[1], got[1]) and np.array_equal(want[2], got[2])
-    # without the sidecar: the empty set of a fresh network, every local uncertainty is 4.0
+    # without the sidecar: an error like Net::load's (net6_simhash.rs:164-181) that leaves the loaded model in place,
+    # unless the caller asks for the empty set of a fresh network (every local uncertainty is then 4.0)
     (tmp_path / "bitvec.bin").unlink()
-    network.load_model(b, str(tmp_path / "model_latest.ot"))
+    with pytest.raises(capi.TakzeroError, match="bitvec.bin is missing"):
+        network.load_model(b, str(tmp_path / "model_latest.ot"))
+    assert np.array_equal(network.evaluate(b, states, actions)[2], want[2])
+    network.load_model(b, str(tmp_path / "model_latest.ot"), allow_missing_set=True)
     assert (network.evaluate(b, states, actions)[2] == 4.0).all()
     # a file that lacks a tensor is refused with its name, and the previous model stays usable
     tensors.pop("policy.conv2d.bias")
     weights.save_ot(str(tmp_path / "broken.ot"), tensors)
     with pytest.raises(capi.TakzeroError, match="policy.conv2d.bias"):
-        network.load_model(b, str(tmp_path / "broken.ot"))
+        network.load_model(b, str(tmp_path / "broken.ot"), allow_missing_set=True)
     again = network.evaluate(b, states, actions)
     assert all(np.array_equal(x, y) for x, y in zip(want[0], again[0])) and np.array_equal(want[1], again[1])
     for h in (a, b):

@@ -380,9 +380,10 @@ def test_device_expf_is_the_restated_glibc_expf():
     8th f32 bit pattern of the softmax range [-104, 0] plus a sweep of the positive range.  Bit-exact."""
     import ctypes as C
 
+    from takzero_b200 import network
+
+    network._declare()
     L = capi.lib()
-    L.tz_debug_expf.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
-    L.tz_debug_expf.restype = C.c_int
     m = capi.BatchedMCTS(4, 4, 4, arena_slots=4096)
     lo, hi = int(np.float32(-1e-30).view(np.uint32)), int(np.float32(-104.0).view(np.uint32))
     neg = np.arange(lo, hi, 41, dtype=np.uint32).view(np.float32)
