@@ -102,6 +102,14 @@ pub struct tz_selfplay_t {
 }
 #[repr(C)]
 #[derive(Clone, Copy)]
+pub struct tz_reanalyze_t {
+    pub sampled_actions: c_int,
+    pub search_budget: u32,
+    pub target_beta: f32,
+    pub seed: u64,
+}
+#[repr(C)]
+#[derive(Clone, Copy)]
 pub struct tz_profile_t {
     pub ms: [f64; 8],
     pub launches: [u64; 8],
@@ -149,6 +157,9 @@ extern "C" {
     pub fn tz_set_root_priors(h: *mut tz_handle, stride: c_int, prob: *const f32, logit: *const f32) -> c_int;
     pub fn tz_selfplay_move(h: *mut tz_handle, params: *const tz_selfplay_t) -> c_int;
     pub fn tz_launch_count(h: *mut tz_handle, out: *mut u64) -> c_int;
+    pub fn tz_stage_positions(h: *mut tz_handle, states: *const tz_state_t, count: usize) -> c_int;
+    pub fn tz_reanalyze_batch(h: *mut tz_handle, pool_indices: *const u32, params: *const tz_reanalyze_t) -> c_int;
+    pub fn tz_reanalyze_read(h: *mut tz_handle, stride: c_int, out_policy: *mut f32, out_ube: *mut f32, out_value: *mut f32, out_n: *mut c_int, out_moves: *mut tz_move_t) -> c_int;
     pub fn tz_profile_begin(h: *mut tz_handle, sample_every: c_int) -> c_int;
     pub fn tz_profile_end(h: *mut tz_handle, out: *mut tz_profile_t) -> c_int;
     pub fn tz_timer_start(h: *mut tz_handle) -> c_int;

@@ -219,6 +219,24 @@ typedef struct tz_selfplay_t {
 TZ_API int tz_selfplay_move(tz_handle* h, const tz_selfplay_t* params);
 TZ_API int tz_launch_count(tz_handle* h, uint64_t* out);             /* kernels launched so far */
 
+/* The loop body of `reanalyze` (reanalyze/src/main.rs:147-235) without per-batch host buffers.  tz_stage_positions
+ * uploads the positions of the replay buffer once (position_buffer, main.rs:60-75); tz_reanalyze_batch makes the
+ * staged positions pool_indices[g] the fresh roots of the games (`*node = Node::default(); *env = replay_env`, NULL =
+ * keep the current positions / roots, e.g. after tz_set_positions), searches them (ZERO_BETA, library-drawn Gumbel
+ * noise) and leaves the targets on the device: improved policy at most_visited_count() visitations, UBE target, and
+ * the value target (root evaluation when known, else the negated evaluation of the selected child, main.rs:184-195).
+ * Asynchronous like tz_selfplay_move; tz_reanalyze_read copies the targets of the last batch out. */
+typedef struct tz_reanalyze_t {
+    int sampled_actions;    /* SAMPLED_ACTIONS */
+    uint32_t search_budget; /* SEARCH_BUDGET */
+    float target_beta;      /* UBE_TARGET_BETA */
+    uint64_t seed;
+} tz_reanalyze_t;
+TZ_API int tz_stage_positions(tz_handle* h, const tz_state_t* states, size_t count);
+TZ_API int tz_reanalyze_batch(tz_handle* h, const uint32_t* pool_indices, const tz_reanalyze_t* params);
+TZ_API int tz_reanalyze_read(tz_handle* h, int stride, float* out_policy, float* out_ube, float* out_value, int* out_n,
+                      tz_move_t* out_moves);
+
 /* Sampled per-kernel device timing: every `sample_every`-th lock-step simulation is bracketed with
  * CUDA events on the library's stream.  Categories: 0 select(+movegen,+known backup), 1 encode,
  * 2 input conv, 3 tower convs, 4 policy conv, 5 heads+gather, 6 expand(+softmax,+backup), 7 synthetic agent. */

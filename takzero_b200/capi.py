@@ -87,6 +87,13 @@ class SelfplayParams(C.Structure):
                 ("seed", C.c_uint64)]
 
 
+class ReanalyzeParams(C.Structure):
+    """tz_reanalyze_t: SAMPLED_ACTIONS, SEARCH_BUDGET, UBE_TARGET_BETA of reanalyze/src/main.rs as runtime fields."""
+
+    _fields_ = [("sampled_actions", C.c_int), ("search_budget", C.c_uint32), ("target_beta", C.c_float),
+                ("seed", C.c_uint64)]
+
+
 class Profile(C.Structure):
     _fields_ = [("ms", C.c_double * 8), ("launches", C.c_uint64 * 8), ("locksteps", C.c_uint64),
                 ("positions", C.c_uint64)]
@@ -160,6 +167,9 @@ def lib():
         "tz_tree_principal_variation": ([vp, vp, i32], i32),
         "tz_selfplay_move": ([vp, P(SelfplayParams)], i32),
         "tz_launch_count": ([vp, P(u64)], i32),
+        "tz_stage_positions": ([vp, vp, C.c_size_t], i32),
+        "tz_reanalyze_batch": ([vp, vp, P(ReanalyzeParams)], i32),
+        "tz_reanalyze_read": ([vp, i32, vp, vp, vp, vp, vp], i32),
         "tz_profile_begin": ([vp, i32], i32),
         "tz_profile_end": ([vp, P(Profile)], i32),
         "tz_timer_start": ([vp], i32),
@@ -434,6 +444,29 @@ class BatchedMCTS:
     def selfplay_move(self, params: SelfplayParams) -> None:
         """One whole self-play move on the device, asynchronous (see tz_selfplay_move)."""
         _check(lib().tz_selfplay_move(self._h, C.byref(params)))
+
+    # ---- reanalyze (reanalyze/src/main.rs:147-235) ---------------------------------------------------------
+    def stage_positions(self, states: np.ndarray) -> None:
+        """Upload the replay buffer's positions once; batches then pick their roots by index."""
+        states = _arr(states, STATE_DTYPE)
+        _check(lib().tz_stage_positions(self._h, _ptr(states), len(states)))
+
+    def reanalyze_batch(self, pool_indices, params: ReanalyzeParams) -> None:
+        """One batch on the device, asynchronous: fresh roots from the staged positions (None: the current ones),
+        search, targets."""
+        idx = None if pool_indices is None else _arr(pool_indices, np.uint32, (self.G,))
+        _check(lib().tz_reanalyze_batch(self._h, _ptr(idx), C.byref(params)))
+
+    def reanalyze_read(self, out=None) -> dict:
+        """Targets of the last batch: improved policy, moves, child counts, UBE and value targets."""
+        if out is None:
+            out = {"policy": np.zeros((self.G, self.move_stride), np.float32),
+                   "moves": np.zeros((self.G, self.move_stride), np.uint16),
+                   "ube": np.zeros(self.G, np.float32), "value": np.zeros(self.G, np.float32),
+                   "n": np.zeros(self.G, np.int32)}
+        _check(lib().tz_reanalyze_read(self._h, self.move_stride, _ptr(out["policy"]), _ptr(out["ube"]),
+                                       _ptr(out["value"]), _ptr(out["n"]), _ptr(out["moves"])))
+        return out
 
     def launch_count(self) -> int:
         out = C.c_uint64()

@@ -189,6 +189,8 @@ extern "C" TZ_API int tz_create(const tz_config_t* cfg, tz_handle** out) {
     DM(h->tbl_f32c, G * d.M);
     DM(h->root_stats, G * 6);
     DM(h->ube, G);
+    DM(h->value_target, G);
+    DM(h->pool_idx, G);
     DM(h->reduce_buf, 64);
 #undef DM
     if (e != cudaSuccess) {
@@ -243,6 +245,7 @@ extern "C" TZ_API void tz_destroy(tz_handle* h) {
     nn_free(h);
     comm_destroy(h);
     for (void* p : h->allocs) cudaFree(p);
+    if (h->pool) cudaFree(h->pool);
     if (h->pin_small) cudaFreeHost(h->pin_small);
     if (h->prof_counts) cudaFreeHost(h->prof_counts);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
@@ -904,11 +907,14 @@ extern "C" TZ_API int tz_weight_generation(tz_handle* h, uint64_t* out_generatio
 extern "C" TZ_API int tz_allreduce_sum(tz_handle* h, uint64_t* values, int count) {
     CHECK_H(h);
     if (!values || count <= 0 || count > 64) return fail(TZ_EINVAL, "count must be 1..64");
-    CU(cudaMemcpyAsync(h->reduce_buf, values, (size_t)count * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
-    const int rc = comm_allreduce_sum_u64(h, h->reduce_buf, count, h->stream);
-    if (rc) return fail(rc, "tz_allreduce_sum: %s", comm_last_error());
-    CU(cudaMemcpyAsync(values, h->reduce_buf, (size_t)count * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    // all collectives of a handle go out on one stream, in the order of the calls (the same on every rank)
+    cudaStream_t st = nn_collective_stream(h);
     CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpyAsync(h->reduce_buf, values, (size_t)count * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    const int rc = comm_allreduce_sum_u64(h, h->reduce_buf, count, st);
+    if (rc) return fail(rc, "tz_allreduce_sum: %s", comm_last_error());
+    CU(cudaMemcpyAsync(values, h->reduce_buf, (size_t)count * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return TZ_OK;
 }
 
@@ -1033,6 +1039,77 @@ extern "C" TZ_API int tz_selfplay_move(tz_handle* h, const tz_selfplay_t* sp) {
     h->launches += 6;
     CU(cudaGetLastError());
     return TZ_OK;
+}
+
+// ---- reanalyze (reanalyze/src/main.rs:147-235) without per-batch host buffers ----------------------------------------
+
+extern "C" TZ_API int tz_stage_positions(tz_handle* h, const tz_state_t* states, size_t count) {
+    CHECK_H(h);
+    if (!states || count == 0) return fail(TZ_EINVAL, "no positions");
+    for (size_t lo = 0; lo < count; lo += 1 << 20) {
+        const int part = (int)(count - lo < (size_t)(1 << 20) ? count - lo : (size_t)(1 << 20));
+        const int bad = first_invalid_state(states + lo, part, h->d.n);
+        if (bad >= 0) return fail(TZ_EINVAL, "state %zu is not a possible position of this board", lo + (size_t)bad);
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    if (count > h->pool_cap) {
+        if (h->pool) cudaFree(h->pool);
+        h->pool = nullptr;
+        h->pool_cap = 0;
+        if (cudaMalloc((void**)&h->pool, count * sizeof(TzState)) != cudaSuccess)
+            return fail(TZ_ENOMEM, "cudaMalloc of %zu staged positions failed", count);
+        h->pool_cap = count;
+    }
+    CU(cudaMemcpyAsync(h->pool, states, count * sizeof(TzState), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->pool_count = count;
+    return TZ_OK;
+}
+
+// one reanalyze batch: fresh roots from staged positions, search, targets -- everything stays on the device
+extern "C" TZ_API int tz_reanalyze_batch(tz_handle* h, const uint32_t* pool_indices, const tz_reanalyze_t* rp) {
+    CHECK_H(h);
+    if (!rp) return fail(TZ_EINVAL, "null parameters");
+    if (rp->sampled_actions <= 0 || rp->sampled_actions > TZ_MAX_K)
+        return fail(TZ_EINVAL, "At least one action must be sampled (and at most %d)", TZ_MAX_K);
+    const uint32_t steps = ilog2_u32((uint32_t)rp->sampled_actions);
+    if (steps == 0 || rp->search_budget % (steps * (uint32_t)rp->sampled_actions) != 0)
+        return fail(TZ_EINVAL, "The search budget should be a multiple of k*log2(k) for clean visits");
+    const TzDev& d = h->d;
+    if (pool_indices) {
+        if (h->pool_count == 0) return fail(TZ_EINVAL, "tz_stage_positions first");
+        for (int g = 0; g < d.G; g++)
+            if (pool_indices[g] >= h->pool_count) return fail(TZ_EINVAL, "pool index %u of game %d out of range", pool_indices[g], g);
+        CU(cudaMemcpyAsync(h->pool_idx, pool_indices, (size_t)d.G * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+        launch_gather_positions(d, h->pool, h->pool_idx, h->stream);  // *node = Node::default(); *env = replay_env
+        h->launches += 1;
+    }
+    launch_gumbel_noise(d, h->gumbel, d.M, rp->seed, h->move_counter, h->stream);
+    h->gumbel_stride = d.M;
+    const int rc = tz_search_device(h, nullptr, rp->sampled_actions, rp->search_budget, h->gumbel, d.M);  // ZERO_BETA
+    if (rc) return rc;
+    launch_targets(d, -1.0f, rp->target_beta, d.M, h->tbl_f32a, h->ube, h->tbl_n, h->tbl_moves, h->stream);
+    launch_reanalyze_values(d, h->moves, h->value_target, h->stream);
+    h->launches += 3;
+    CU(cudaGetLastError());
+    return TZ_OK;
+}
+
+// the targets of the last tz_reanalyze_batch: improved policy with most_visited_count() visitations, UBE target,
+// value target, per root the child count and moves
+extern "C" TZ_API int tz_reanalyze_read(tz_handle* h, int stride, float* out_policy, float* out_ube, float* out_value,
+                                        int* out_n, tz_move_t* out_moves) {
+    CHECK_H(h);
+    const TzDev& d = h->d;
+    if (stride != d.M || !out_policy || !out_ube || !out_value || !out_n || !out_moves)
+        return fail(TZ_EINVAL, "stride must equal move_stride (%d) and all outputs must be given", d.M);
+    const size_t cells = (size_t)d.G * stride;
+    CU(cudaMemcpyAsync(out_policy, h->tbl_f32a, cells * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(out_moves, h->tbl_moves, cells * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(out_ube, h->ube, (size_t)d.G * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(out_value, h->value_target, (size_t)d.G * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(out_n, h->tbl_n, (size_t)d.G * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    return finish(h);
 }
 
 extern "C" TZ_API int tz_launch_count(tz_handle* h, uint64_t* out) {

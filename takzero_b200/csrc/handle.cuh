@@ -44,6 +44,10 @@ struct tz_handle {
     float *tbl_f32a = nullptr, *tbl_f32b = nullptr, *tbl_f32c = nullptr;
     uint32_t* root_stats = nullptr;
     float* ube = nullptr;
+    float* value_target = nullptr;    // [G] reanalyze value targets
+    TzState* pool = nullptr;          // device-resident positions of tz_stage_positions (the replay buffer of `reanalyze`)
+    size_t pool_count = 0, pool_cap = 0;
+    uint32_t* pool_idx = nullptr;     // [G]
     // pinned host staging
     unsigned char* pin_small = nullptr;
     TzState* pin_states = nullptr;

@@ -722,6 +722,16 @@ __global__ void __launch_bounds__(32 * WPB) k_set_positions(TzDev d, const TzSta
     warp_fresh_game(d, g, &s_state[warp], lane);
 }
 
+// positions picked out of a device-resident pool (the replay buffer of `reanalyze`): game g <- pool[indices[g]], fresh root
+__global__ void __launch_bounds__(32 * WPB) k_gather_positions(TzDev d, const TzState* pool, const uint32_t* indices) {
+    __shared__ TzState s_state[WPB];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * WPB + warp;
+    if (g >= d.G) return;
+    warp_load_state(&s_state[warp], &pool[indices[g]], lane);
+    warp_fresh_game(d, g, &s_state[warp], lane);
+}
+
 __global__ void k_reset_roots(TzDev d, const uint8_t* mask) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= d.G || (mask && !mask[g])) return;
@@ -881,6 +891,35 @@ __global__ void __launch_bounds__(32 * WPB) k_targets(TzDev d, float visitations
         }
         out_ube[g] = ube;
     }
+}
+
+// value target of `reanalyze` (reanalyze/src/main.rs:184-195): the root's evaluation when it is known, else the negated
+// evaluation of the child the search selected; as f32 (eval.rs:95-105)
+__global__ void __launch_bounds__(32 * WPB) k_reanalyze_values(TzDev d, const uint16_t* selected, float* out_value) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * WPB + warp;
+    if (g >= d.G) return;
+    const GameTree t = game_tree(d.arena, g);
+    const uint32_t meta = t.meta[0];
+    const Ev root_ev = ev_make(tz_meta_tag(meta), t.eval[0]);
+    if (ev_known(root_ev)) {
+        if (lane == 0) out_value[g] = ev_to_f32(root_ev);
+        return;
+    }
+    const int n = (int)tz_meta_nchild(meta);
+    const uint32_t first = t.first[0];
+    const uint16_t mv = selected[g];
+    int found = 0x7fffffff;
+    for (int i = lane; i < n; i += 32)
+        if (tz_meta_move(t.meta[first + i]) == mv && i < found) found = i;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(FULL_MASK, found, o));
+    if (found == 0x7fffffff) {  // "all non-terminal nodes should have at least one child"
+        flag_error(d, TZ_ERR_NO_CHILD, lane);
+        if (lane == 0) out_value[g] = 0.0f;
+        return;
+    }
+    if (lane == 0) out_value[g] = ev_to_f32(ev_negate(node_eval(t, first + (uint32_t)found)));
 }
 
 // select_best_action (node/mod.rs:132-163) of node `slot`; returns the child index, -1 without children
@@ -1133,6 +1172,12 @@ void launch_random_steps(const TzDev& d, const uint8_t* mask, int steps, unsigne
 }
 void launch_set_positions(const TzDev& d, const TzState* states, const uint8_t* mask, cudaStream_t st) {
     k_set_positions<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, states, mask);
+}
+void launch_gather_positions(const TzDev& d, const TzState* pool, const uint32_t* indices, cudaStream_t st) {
+    k_gather_positions<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, pool, indices);
+}
+void launch_reanalyze_values(const TzDev& d, const uint16_t* selected, float* out_value, cudaStream_t st) {
+    k_reanalyze_values<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, selected, out_value);
 }
 void launch_reset_roots(const TzDev& d, const uint8_t* mask, cudaStream_t st) {
     k_reset_roots<<<(d.G + 127) / 128, 128, 0, st>>>(d, mask);

@@ -38,3 +38,5 @@ void launch_set_root_priors(const TzDev& d, int stride, const float* prob, const
 void launch_random_steps(const TzDev& d, const uint8_t* mask, int steps, unsigned long long seed, cudaStream_t st);
 
 void launch_debug_expf(const float* in, int count, float* out, cudaStream_t st);
+void launch_gather_positions(const TzDev& d, const TzState* pool, const uint32_t* indices, cudaStream_t st);
+void launch_reanalyze_values(const TzDev& d, const uint16_t* selected, float* out_value, cudaStream_t st);

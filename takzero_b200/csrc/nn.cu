@@ -859,6 +859,8 @@ static void bind_search(tz_handle* h) {
     h->d.nn_novelty_idx = on ? s->simhash_idx : nullptr;
 }
 void nn_bind_search(tz_handle* h) { bind_search(h); }
+// every collective of a handle is issued on one stream: the weight stream once a network exists
+cudaStream_t nn_collective_stream(tz_handle* h) { return h->nn && h->nn->wstream ? h->nn->wstream : h->stream; }
 
 // test hook (no GPU needed): the kernel's own work-item schedule for `count` positions, and the bounds the host
 // sizes the activation sets and progress counters with.  out[0..4] = items, chunks, chunk_tiles, chunk_rows of the

@@ -13,6 +13,7 @@ int nn_generation_ms(tz_handle* h, double* ms, unsigned long long* generation);
 int nn_debug_weight_set(tz_handle* h, unsigned char* out, size_t cap, size_t* size);
 // k_expand finishes the heads itself when the agent is the device network: refresh the pointers it uses
 void nn_bind_search(tz_handle* h);
+cudaStream_t nn_collective_stream(tz_handle* h);
 // policy / value / uncertainty of the queued leaf positions: legal logits -> d.logits, head features for k_expand
 int nn_forward_queue(tz_handle* h);
 // the same for `count` host-supplied positions already in d.leaf_state / d.actions / d.n_actions -> d.logits,

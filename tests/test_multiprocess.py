@@ -1,5 +1,6 @@
-"""CPU, world_size 2 over gloo: the host-side multi-GPU logic (sharding, weight broadcast, counter
-reduction, max-over-ranks timing).  No GPU and no compute calls."""
+"""CPU, world_size 2 over gloo: the host-side multi-GPU logic (sharding of games and replay-buffer positions, the
+hand-over of the communicator's unique id, counter reduction, max-over-ranks timing).  No GPU and no compute calls; the
+weight broadcast and the set swap themselves run in the library (tests/test_gpu_weights.py, test_gpu_multirank.py)."""
 import os
 import socket
 
@@ -26,14 +27,13 @@ def _worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         base, n = tzd.shard(rank, world, 64)
-        # every rank initialises differently; after the broadcast all hold rank 0's weights
-        mine = weights.random_init(4, seed=100 + rank, blocks=1)
-        got = tzd.broadcast_weights(mine, src=0)
-        want = weights.random_init(4, seed=100, blocks=1)
-        same = all(np.array_equal(got[k], want[k]) for k in want) and list(got) == list(want)
+        lo, hi = tzd.shard_range(1_000_001, rank, world)
+        # the NCCL unique id of the library's communicator travels from rank 0 like this (128 bytes)
+        uid = bytes(range(128)) if rank == 0 else None
+        got = tzd.exchange_bytes(uid, 128, src=0)
         totals = tzd.sum_counters([10.0 * (rank + 1), float(n)])
         slowest = tzd.max_over_ranks([5.0 + rank])
-        out[rank] = (base, n, same, totals, slowest)
+        out[rank] = (base, n, got == bytes(range(128)), totals, slowest, lo, hi)
     finally:
         dist.destroy_process_group()
 
@@ -44,18 +44,20 @@ def test_two_rank_host_logic():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert out[0][:2] == (0, 64) and out[1][:2] == (64, 64)  # contiguous, disjoint game ranges
+    assert (out[0][5], out[0][6], out[1][5], out[1][6]) == (0, 500_001, 500_001, 1_000_001)
     for r in range(world):
-        assert out[r][2], "weights differ from rank 0 after the broadcast"
+        assert out[r][2], "the unique id differs from rank 0's after the exchange"
         assert out[r][3] == [30.0, 128.0]
         assert out[r][4] == [6.0]
 
 
-def test_pack_unpack_round_trip():
-    t = weights.random_init(4, seed=1, blocks=1)
-    names, flat = tzd.pack(t)
-    back = tzd.unpack(names, {k: v.shape for k, v in t.items()}, flat)
-    assert all(np.array_equal(back[k], t[k]) for k in t)
-    assert flat.dtype == np.float32
+def test_shard_range_covers_everything_once():
+    for total, world in ((1_000_000, 8), (10, 3), (7, 8), (0, 2)):
+        spans = [tzd.shard_range(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
 
 
 def test_flops_per_position_matches_baseline_md():
