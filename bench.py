@@ -454,7 +454,11 @@ def run_selfplay(args, wl, emit):
                 "every_move": {"value": value, "generations": every["generations"]},
                 "one_per_region": {"value": sparse_value, "generations": sparse["generations"]},
                 "none": {"value": never_value, "generations": 0},
+                # duration of the last generation on the side stream (upload + fold + broadcast; for N > 1 it includes
+                # waiting for a gap between the search's network launches on every rank, because the NCCL kernel needs
+                # SMs the persistent network kernel holds) and what a generation per move costs the timed loop
                 "generation_ms_max_over_ranks": gen_ms,
+                "cost_ms_per_move": (every["ms"] - never["ms"]) / args.steps,
                 "what": "tz_broadcast_weights: f32 tensors H2D on rank 0, BatchNorm fold + arrangement on the GPU, "
                         "ncclBroadcast of the 16-bit set, swap between moves; on a side stream beside the search",
             },

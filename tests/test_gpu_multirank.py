@@ -53,7 +53,8 @@ def _worker(rank, world, port, out):
             want = network.evaluate(local, states, actions)
             local.close()
             got = network.evaluate(m, states, actions)
-            same = bool(np.array_equal(got_set[8:], want_set[8:]))  # bytes 16..23 hold the generation counter
+            # bytes 16..23 of the header hold the generation counter (2 here, 1 on the fresh local handle)
+            same = bool(np.array_equal(got_set[:16], want_set[:16]) and np.array_equal(got_set[24:], want_set[24:]))
             same = same and all(np.array_equal(a, b) for a, b in zip(got[0], want[0])) and np.array_equal(got[1], want[1])
             results.append(same)
         # a search move between the generations still works, and the counters add up over the ranks
