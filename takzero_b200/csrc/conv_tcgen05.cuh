@@ -62,6 +62,15 @@
 //   memory and stores logit[move_channel] to the queue's logit row.  The [positions][9036] f32 policy tensor
 //   (302 MB per pass of 8192 positions) is never written.
 //
+// Local chain (small batches of 4x4 boards): when N*N divides the 128 rows of a CTA, no position straddles two CTAs, so
+// a tile needs nothing from its neighbours; when moreover a layer has no more tiles than there are CTA pairs, pair p
+// keeps tile p for ALL layers and the activations never leave the SM: the epilogue writes the 16-bit outputs of a
+// layer straight into the A stages of the next one (the canonical UMMA layout, st.shared + fence.proxy.async + mbarrier
+// arrive) 64 channels at a time, so the next layer's first MMAs start ~2 us after the last MMA of this one instead of
+// after a round trip through L2 with gpu-scope release / acquire flags (measured chain: 6.5 us per layer, which bounded
+// 1024 games of 4x4 at 16.5 us per layer against 10 us of MMAs).  Only the residual stream x still goes through
+// global memory, written and read back by the same thread.
+//
 // TZ_DEBUG_TIMING is a compile-time tuning experiment (tools/build_variant.sh); the numbers it produced for
 // the earlier row-major one-CTA / pair kernels are in profiles/r1_conv_timing.txt.
 #pragma once
@@ -119,6 +128,8 @@ struct Layer {
     int g_stride;
     int cin;                        // input channels (multiple of 64)
     int relu;
+    int out_is_residual;            // the output is read again as a residual two layers on (else, in the local chain,
+                                    // it only ever lives in shared memory)
 };
 
 struct Params {
@@ -139,6 +150,7 @@ struct Params {
     unsigned* chunk_done;           // [chunks]: epilogue-warp arrivals of the last layer (8 per tile)
     unsigned* status;               // the handle's sticky error word (watchdog of the dependency waits)
     int debug_drop_progress;        // test hook: CTA pair 0 never publishes its tiles (exercises the watchdog)
+    int allow_local;                // 0: never use the local chain (debug read-backs of the activation buffers)
 };
 
 // work item -> (chunk, layer, pair tile); every role of the kernel walks the same sequence
@@ -181,6 +193,23 @@ struct Schedule {
     }
 };
 
+#ifdef TZ_DEBUG_CHAIN
+// chain-latency experiment: globaltimer stamps of one CTA pair's roles around two mid-network layers, kept in global
+// memory and printed by the pair when the launch ends (printing at the events themselves distorts them)
+__device__ long long g_chain[64];
+__device__ __forceinline__ long long gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define CHAIN(cond, layer, kind, k)                                        \
+    do {                                                                   \
+        if (cond) g_chain[((layer) - 10) * 32 + (kind) * 4 + (k)] = gtime(); \
+    } while (0)
+#else
+#define CHAIN(cond, layer, kind, k)
+#endif
+
 #ifdef TZ_DEBUG_TIMING
 #define TWAIT(acc, stmt)                 \
     do {                                 \
@@ -212,6 +241,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t n) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -321,6 +353,9 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     // ptxas emit MEMBAR.ALL.GPU + CGAERRBAR per arrive, which serialises the whole pipeline
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_cluster_n(uint32_t cluster_addr, uint32_t n) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(n) : "memory");
+}
 // waits on barriers that the other CTA arrives on use the plain try_wait too (an acquire.cluster wait costs a
 // CCTL.IVALL = L1 invalidate per wait); the protected data is read by the tensor core, not by this thread
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
@@ -372,10 +407,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
     // epilogues then publish every 64 output channels separately so that the next layer's first MMAs overlap the
     // rest of the epilogue.  With more tiles that only costs (four device-wide fences per tile instead of one).
     const bool fine = sched.chunk_tiles < 2 * npairs;
+    // Local chain (see the header): pair p owns tile p of every layer, activations stay in shared memory.
+    const bool local = p.allow_local && p.n_layers > 1 && (TILE_M % nn) == 0 && sched.chunk_tiles <= npairs &&
+                       items == sched.chunk_tiles * p.n_layers;
+    const int item0 = local ? (pair < sched.chunk_tiles ? pair : items) : pair;
+    const int istep = local ? sched.chunk_tiles : npairs;
+    // arrivals that complete an A stage: one per CTA (its producer), or in the local chain one per epilogue warp
+    const uint32_t a_arrivals = local ? 4u : 1u;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < A_STAGES; i++) {
-            mbar_init(a_full + 8 * i, 2);
+            mbar_init(a_full + 8 * i, 2 * a_arrivals);
             mbar_init(a_land + 8 * i, 1);
             mbar_init(a_empty + 8 * i, 1);
         }
@@ -410,7 +452,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
         // the item sequence (stage / phase stay warp-uniform); lane 0 issues the bulk copies of ordinary layers, all
         // lanes build the tile of the encoding layer.
         int stage = 0, phase = 0;
-        for (int item = pair; item < items; item += npairs) {
+        for (int item = item0; item < items; item += istep) {
             const Item it = sched.at(item);
             const int layer = it.layer, pt = it.pt;
             const Layer& L = p.layers[layer];
@@ -468,7 +510,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                 // generic-proxy writes -> the tensor core's (async proxy) reads, then publish the stage
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(a_sig + 8 * stage);
+                if (lane == 0) {
+                    if (rank == 0) mbar_arrive_n(a_sig + 8 * stage, a_arrivals);
+                    else mbar_arrive(a_sig + 8 * stage);  // a_land; the relay forwards a_arrivals
+                }
 #ifdef TZ_DEBUG_TIMING
                 if (pair == 0 && rank == 0 && lane == 0 && item < 2 * npairs) printf("encode of one tile: %lld cycles\n", clock64() - enc_t0);
 #endif
@@ -479,6 +524,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                 continue;
             }
             const int kblocks = L.cin >> 6;
+            if (local) continue;  // the previous layer's epilogue fills the stages of this item
             if (lane == 0) {
                 // rows [t*128 - HALO, t*128 + 128 + HALO) of the previous layer's output: CTA tiles t-1, t, t+1, i.e.
                 // pair tiles {pt-1, pt} for rank 0 and {pt, pt+1} for rank 1; waited for per 64-channel block below
@@ -496,6 +542,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                         for (int q = lo; q <= lo + 1; q++)
                             if (q >= 0 && q < it.tiles) wait_counter(prog + q * 4 + blk, need, p.status);
                         fence_proxy_async();
+                        CHAIN(pair == 10 && rank == 0 && (layer == 10 || layer == 11), layer, 0, kb);
                     }
                     mbar_wait(a_empty + 8 * st, ph ^ 1);
                     mbar_arrive_expect_tx(a_sig + 8 * st, A_STAGE_BYTES);
@@ -520,7 +567,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
         // ---- B producer (both CTAs): this CTA's half (128 of the 256 N rows) of every weight block
         if (lane == 0) {
             int stage = 0, phase = 0;
-            for (int item = pair; item < items; item += npairs) {
+            for (int item = item0; item < items; item += istep) {
                 const Layer& L = p.layers[sched.at(item).layer];
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(L.w) + (size_t)rank * B_STAGE_BYTES;
                 const int blocks = (L.cin >> 6) * 9;
@@ -541,7 +588,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
         if (rank != 0 && lane == 0) {
             int stage = 0, phase = 0;
             const uint32_t b_full_leader = map_to_rank(b_full, 0);
-            for (int item = pair; item < items; item += npairs) {
+            for (int item = item0; item < items; item += istep) {
                 const int blocks = (p.layers[sched.at(item).layer].cin >> 6) * 9;
                 for (int blk = 0; blk < blocks; blk++) {
                     mbar_wait(b_land + 8 * stage, phase);
@@ -559,11 +606,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
             if (lane == 0) {
                 int stage = 0, phase = 0;
                 const uint32_t a_full_leader = map_to_rank(a_full, 0);
-                for (int item = pair; item < items; item += npairs) {
-                    const int kblocks = p.layers[sched.at(item).layer].cin >> 6;
+                for (int item = item0; item < items; item += istep) {
+                    const Layer& RL = p.layers[sched.at(item).layer];
+                    if (local && RL.enc_states == nullptr) break;  // only the encoded first layer lands here
+                    const int kblocks = RL.cin >> 6;
                     for (int kb = 0; kb < kblocks; kb++) {
                         mbar_wait(a_land + 8 * stage, phase);
-                        mbar_arrive_cluster(a_full_leader + 8 * stage);
+                        mbar_arrive_cluster_n(a_full_leader + 8 * stage, a_arrivals);
                         if (++stage == A_STAGES) {
                             stage = 0;
                             phase ^= 1;
@@ -588,7 +637,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
             long long gt_start;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_start));
 #endif
-            for (int item = pair; item < items; item += npairs, it++) {
+            for (int item = item0; item < items; item += istep, it++) {
                 const Item wi = sched.at(item);
                 const int pt = wi.pt;
                 const int kblocks = p.layers[wi.layer].cin >> 6;
@@ -611,6 +660,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                         const int tap = ti == 0 ? 4 : (ti <= 4 ? ti - 1 : ti);
                         TWAIT(w_b, mbar_wait(b_full + 8 * b_stage, b_phase));
                         tc_fence_after();
+                        CHAIN(pair == 10 && lane == 0 && ti == 0 && (wi.layer == 10 || wi.layer == 11), wi.layer, 1, kb);
                         const int off = (tap / 3 - 1) * p.n + (tap % 3 - 1);
                         const uint4 m0 = masks0[tap], m1 = masks1[tap];
                         const uint32_t a_tap = a_base + (HALO + off) * 16;
@@ -625,6 +675,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                             tc_commit_pair(b_empty + 8 * b_stage);
                             if (ti == 8) tc_commit_pair(a_empty + 8 * a_stage);
                             if (ti == 8 && kb == kblocks - 1) tc_commit_pair(t_full + 8 * acc);
+                            CHAIN(pair == 10 && ti == 8 && kb == kblocks - 1 && (wi.layer == 10 || wi.layer == 11), wi.layer, 3, 1);
                         }
                         __syncwarp();
                         if (++b_stage == B_STAGES) {
@@ -654,8 +705,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
         const uint32_t t_empty_leader = map_to_rank(t_empty, 0);
         const size_t plane = (size_t)p.rows_set * 8;  // elements per chunk plane of an activation set
         float* bias_w = s_bias + wq * N_OUT;          // this warp's copy of the current layer's bias
-        int it = 0, bias_layer = -1;
-        for (int item = pair; item < items; item += npairs, it++) {
+        const uint32_t a_full_leader = map_to_rank(a_full, 0);
+        int it = 0, bias_layer = -1, a_consumed = 0;
+        for (int item = item0; item < items; item += istep, it++) {
             const Item wi = sched.at(item);
             const int layer = wi.layer, pt = wi.pt;
             const Layer& L = p.layers[layer];
@@ -668,7 +720,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
             }
             const size_t set_off = (size_t)(wi.chunk & 1) * p.set_stride;
             const __nv_bfloat16* residual = L.residual ? L.residual + set_off : nullptr;
-            __nv_bfloat16* out_act = L.out_act ? L.out_act + set_off : nullptr;
+            // local chain: the output becomes the next item's A tile in shared memory (stage of its k-block kb =
+            // (a_next + kb) mod A_STAGES); global memory only keeps what a later layer reads as its residual
+            a_consumed += L.cin >> 6;
+            const int a_next = a_consumed % A_STAGES;
+            const bool to_smem = local && L.out_act != nullptr && layer + 1 < p.n_layers;
+            __nv_bfloat16* out_act = L.out_act && (!local || L.out_is_residual) ? L.out_act + set_off : nullptr;
             const float* head_w = L.head_w;
             const int relu = L.relu;
             const int acc = it & 1;
@@ -708,17 +765,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
             float* stg = s_gather + (wq * 32 + lane) * 32;  // this thread's 32 staged channels (XOR-swizzled by lane)
             mbar_wait(t_full + 8 * acc, (it >> 1) & 1);
             tc_fence_after();
+            CHAIN(pair == 10 && rank == 0 && wq == 0 && lane == 0 && (layer == 10 || layer == 11), layer, 3, 0);
             // Inside a fused launch the residual rows were written by another SM two layers ago.  One gpu-scope
             // acquire per tile (on the counter that writer released) makes the plain loads below see them: it costs
             // an L1 invalidate per warp and tile, whereas L2-only (ld.cg) loads made the epilogue 1.8x slower
             // than the MMAs of a tile.
             unsigned* prog_tile = p.progress + ((size_t)wi.chunk * sched.chunk_tiles + pt) * 4;
-            if (residual != nullptr && layer >= 2) (void)ld_acquire_gpu(prog_tile + 3);
+            if (residual != nullptr && layer >= 2 && !local) (void)ld_acquire_gpu(prog_tile + 3);
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * N_OUT;
+            // the residual rows of the next 32 channels are fetched while the current ones are processed: their L2
+            // latency (the rows were written by another SM) would otherwise sit between every two blocks, which is
+            // what bounds a layer when there is only one tile per CTA pair (small batches)
+            uint4 rnext[4];
+            if (residual && valid) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) rnext[j] = *reinterpret_cast<const uint4*>(residual + (size_t)j * plane + grow);
+            }
 #pragma unroll 1
             for (int c0 = 0; c0 < N_OUT; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
+                uint4 rcur[4];
+                if (residual && valid) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) rcur[j] = rnext[j];
+                    if (c0 + 32 < N_OUT) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            rnext[j] = *reinterpret_cast<const uint4*>(residual + (size_t)((c0 + 32) / 8 + j) * plane + grow);
+                    }
+                }
                 tmem_ld_wait();
                 if (valid) {
                     float f[32];
@@ -727,7 +803,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                     if (residual) {
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
-                            const uint4 r = *reinterpret_cast<const uint4*>(residual + (size_t)(c0 / 8 + j) * plane + grow);
+                            const uint4 r = rcur[j];
                             const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
                             for (int e = 0; e < 4; e++) {
@@ -745,6 +821,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
 #pragma unroll
                         for (int j = 0; j < 4; j++)
                             *reinterpret_cast<uint4*>(out_act + (size_t)(c0 / 8 + j) * plane + grow) =
+                                make_uint4(pack16(f[j * 8], f[j * 8 + 1], p.f16), pack16(f[j * 8 + 2], f[j * 8 + 3], p.f16),
+                                           pack16(f[j * 8 + 4], f[j * 8 + 5], p.f16), pack16(f[j * 8 + 6], f[j * 8 + 7], p.f16));
+                    }
+                    if (to_smem) {
+                        uint8_t* row = a_smem + ((a_next + (c0 >> 6)) % A_STAGES) * A_STAGE_BYTES +
+                                       ((c0 & 63) >> 3) * A_KC_BYTES + (HALO + wq * 32 + lane) * 16;
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            *reinterpret_cast<uint4*>(row + j * A_KC_BYTES) =
                                 make_uint4(pack16(f[j * 8], f[j * 8 + 1], p.f16), pack16(f[j * 8 + 2], f[j * 8 + 3], p.f16),
                                            pack16(f[j * 8 + 4], f[j * 8 + 5], p.f16), pack16(f[j * 8 + 6], f[j * 8 + 7], p.f16));
                     }
@@ -774,10 +859,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                         }
                     }
                 }
-                if (p.n_layers > 1 && (fine ? (c0 & 32) != 0 : c0 == N_OUT - 32) && !(p.debug_drop_progress && pair == 0)) {
+                if (to_smem && (c0 & 32) != 0) {
+                    // 64 more channels = one k-block of the next layer are in place: generic-proxy writes -> the tensor
+                    // core's reads, then this warp's arrival on the stage (8 epilogue warps of the pair complete it)
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        const uint32_t bar = 8u * (uint32_t)((a_next + (c0 >> 6)) % A_STAGES);
+                        if (rank == 0) mbar_arrive(a_full + bar);
+                        else mbar_arrive_cluster(a_full_leader + bar);
+                    }
+                }
+                if (!local && p.n_layers > 1 && (fine ? (c0 & 32) != 0 : c0 == N_OUT - 32) && !(p.debug_drop_progress && pair == 0)) {
                     // 64 more output channels (fine) or the whole tile of this warp's rows are visible device-wide
                     __threadfence();
                     __syncwarp();
+                    CHAIN(pair == 10 && rank == 0 && wq == 0 && lane == 0 && (layer == 10 || layer == 11), layer, 2, c0 >> 6);
                     if (fine) {
                         if (lane == 0) red_release_gpu_add(prog_tile + (c0 >> 6), 1u);
                     } else if (lane < 4) {
@@ -790,13 +887,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive_cluster(t_empty_leader + 8 * acc);
-                if (p.n_layers > 1 && layer == p.n_layers - 1) red_release_gpu_add(p.chunk_done + wi.chunk, 1u);
+                if (!local && p.n_layers > 1 && layer == p.n_layers - 1) red_release_gpu_add(p.chunk_done + wi.chunk, 1u);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();  // nobody leaves (or frees TMEM) while the pair's MMAs may still touch its memory
+#ifdef TZ_DEBUG_CHAIN
+    if (pair == 10 && rank == 0 && threadIdx.x == 0 && p.n_layers > 12) {
+        const long long t0 = g_chain[4];  // layer 10: MMAs of kb 0 start
+        for (int l = 0; l < 2; l++) {
+            const long long* c = g_chain + l * 32;
+            printf("L%d dep_ready %lld %lld %lld %lld | mma_start %lld %lld %lld %lld | issue_end %lld t_full %lld | publish %lld %lld %lld %lld\n",
+                   10 + l, c[0] - t0, c[1] - t0, c[2] - t0, c[3] - t0, c[4] - t0, c[5] - t0, c[6] - t0, c[7] - t0, c[13] - t0,
+                   c[12] - t0, c[8] - t0, c[9] - t0, c[10] - t0, c[11] - t0);
+        }
+    }
+#endif
     if (warp == W_ALLOC) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");

@@ -591,7 +591,10 @@ static int ensure_state(tz_handle* h, int blocks) {
         s->max_chunks = cb.chunks;
         s->rows_set = conv::HALO + (size_t)s->chunk_tiles * (2 * conv::TILE_M) + 2 * conv::HALO;
     }
-    if (!dalloc((void**)&s->act_x, 2 * s->rows_set * FILTERS * 2) || !dalloc((void**)&s->act_t, 2 * s->rows_set * FILTERS * 2) ||
+    // both activation buffers are one allocation
+    const size_t act_bytes = 2 * s->rows_set * FILTERS * 2;
+    if (dalloc((void**)&s->act_x, 2 * act_bytes)) s->act_t = s->act_x + act_bytes / 2;
+    if (!s->act_x ||
         !dalloc((void**)&s->head_feat, (size_t)s->max_positions * nn * 2 * sizeof(float)) ||
         !dalloc((void**)&s->perm, (size_t)s->max_positions * h->d.M * sizeof(uint16_t)) ||
         !dalloc((void**)&s->wset[0], s->lay.total) || !dalloc((void**)&s->wset[1], s->lay.total)) {
@@ -974,9 +977,12 @@ static int launch_network(tz_handle* h, const Boundary& io, const int* count_ptr
     std::vector<conv::Layer> all;
     all.push_back(conv_layer(s, set, 0, nullptr, nullptr, s->act_x, 1));
     all.back().enc_states = io.states;
-    for (int l = 0; l < 2 * s->blocks; l++)
+    all.back().out_is_residual = 1;
+    for (int l = 0; l < 2 * s->blocks; l++) {
         all.push_back((l & 1) ? conv_layer(s, set, 1 + l, s->act_t, s->act_x, s->act_x, 1)
                               : conv_layer(s, set, 1 + l, s->act_x, nullptr, s->act_t, 1));
+        all.back().out_is_residual = l & 1;  // x (the block stream) is the next block's residual, t is not
+    }
     all.back().head_w = reinterpret_cast<const float*>(s->wset[set] + s->lay.head_w);
     all.back().head_out = s->head_feat;
     all.push_back(conv_layer(s, set, 1 + 2 * s->blocks, s->act_x, nullptr, nullptr, 0));
@@ -992,6 +998,7 @@ static int launch_network(tz_handle* h, const Boundary& io, const int* count_ptr
         conv::Params p;
         for (size_t i = 0; i < chunk; i++) p.layers[i] = all[first + i];
         p.n_layers = (int)chunk;
+        p.allow_local = upto < 0;  // the debug read-backs look at the activation buffers in global memory
         if (launch_layers(h, p, set, count_ptr, count_max, s->rows_set, s->chunk_min_tiles) != cudaSuccess) return -1;
         first += chunk;
         launches++;
@@ -1125,6 +1132,7 @@ int nn_time_tower(tz_handle* h, int count, int reps, double* ms_per_conv) {
         conv::Params p;
         p.layers[0] = L;
         p.n_layers = 1;
+        p.allow_local = 0;
         return launch_layers(h, p, set, nullptr, count, rows, 1 << 28);
     };
     conv::Layer first = conv_layer(s, set, 0, nullptr, nullptr, x, 1);

@@ -253,13 +253,43 @@ def test_chunked_fused_launch_equals_one_chunk_and_per_layer_launches(n, hk, cou
     assert float(np.abs(outs["chunks"][1] - want_values).max()) <= TOL
 
 
+@pytest.mark.parametrize("count", [1, 8, 9, 130, 1024, 1184, 1185])
+def test_local_chain_of_4x4_small_batches_is_bit_identical(count):
+    """4x4: 16 squares divide the 128 rows of a CTA, so with at most one tile per CTA pair (<= 1184 positions) the fused
+    launch keeps every tile's activations in shared memory from layer to layer (conv_tcgen05.cuh "local chain").  Same
+    bits as one launch per layer through global memory, for a single position, exactly one CTA, a ragged last tile, the
+    BASELINE configs[1] size, the largest local size and the first size that is not local any more."""
+    n, hk = 4, 4
+    ref = net_ref.Net(n, seed=8, blocks=3, randomize_bn=True)
+    games = sample_positions(n, hk, min(count, 256), 99)
+    games = [games[i % len(games)] for i in range(count)]
+    actions = [O.possible_moves(g) for g in games]
+    states = games_to_states(games)
+    outs = []
+    for per_layer in (False, True):
+        m = capi.BatchedMCTS(n, hk, count, arena_slots=4096)
+        network.debug_network_mode(m, per_layer_launches=per_layer)
+        network.set_weights(m, ref.tensors())
+        outs.append(network.evaluate(m, states, actions))
+        if not per_layer:
+            again = network.evaluate(m, states, actions)
+            assert all(np.array_equal(a, b) for a, b in zip(outs[0][0], again[0])) and np.array_equal(outs[0][1], again[1])
+        assert m.status() == 0
+        m.close()
+    assert all(np.array_equal(a, b) for a, b in zip(outs[0][0], outs[1][0]))
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
+    want_logits, want_values, _ = ref.policy_value_uncertainty(games[:64], actions[:64])
+    assert max(float(np.abs(a - b).max()) for a, b in zip(outs[0][0][:64], want_logits)) <= TOL
+    assert float(np.abs(outs[0][1][:64] - want_values).max()) <= TOL
+
+
 def test_watchdog_turns_a_stalled_dependency_into_a_status_bit():
     """The fused launch waits on other CTA pairs' progress counters.  With the test hook that makes pair 0 withhold
     its tiles, the dependent pairs must not spin forever: the watchdog raises TZ_STATUS_NETWORK_STALL (256), the
     launch ends, and the handle reports the error instead of hanging the GPU."""
     import time
 
-    n, hk, count = 4, 4, 256
+    n, hk, count = 5, 4, 160  # 5x5: positions straddle tiles, so the pairs do depend on each other (no local chain)
     ref = net_ref.Net(n, seed=2, blocks=2)
     games = sample_positions(n, hk, count, 5)
     actions = [O.possible_moves(g) for g in games]
