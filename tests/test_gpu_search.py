@@ -402,3 +402,28 @@ def test_device_expf_is_the_restated_glibc_expf():
     ok = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
     assert ok.all(), f"{(~ok).sum()} mismatches, first at {xs[~ok][0]!r}"
     m.close()
+
+
+def test_gumbel_rows_shorter_than_a_root_are_reported():
+    """batched.rs:233-239 zips one Gumbel draw with every root child.  A caller whose noise rows are shorter than a
+    root's child list has not supplied them: reported as TZ_STATUS_TOO_MANY_MOVES (never the next game's noise), the
+    children without a draw rank last, and the search still ends with a complete candidate set."""
+    n, hk, G = 4, 4, 8
+    m = capi.BatchedMCTS(n, hk, G, arena_slots=1 << 14)
+    m.new_openings(seed=2)
+    m.simulate(None)
+    n_children = int(m.root_stats()["n_children"].min())
+    assert n_children > 12
+    gumbel = np.random.default_rng(0).gumbel(size=(G, 12)).astype(np.float32)
+    with pytest.raises(capi.TakzeroError, match="too_many_moves"):
+        m.gumbel_sequential_halving(None, 8, 24, gumbel)
+    assert m.status() == 8
+    m.close()
+    # with rows as long as the longest child list the same call is fine
+    m = capi.BatchedMCTS(n, hk, G, arena_slots=1 << 14)
+    m.new_openings(seed=2)
+    m.simulate(None)
+    width = int(m.root_stats()["n_children"].max())
+    m.gumbel_sequential_halving(None, 8, 24, np.random.default_rng(0).gumbel(size=(G, width)).astype(np.float32))
+    assert m.status() == 0
+    m.close()
