@@ -8,6 +8,7 @@ Workloads (BASELINE.json `configs`):
   6x6_selfplay (default)  configs[2] / configs[3]: 6x6 Tak, half komi 4, 8192 concurrent games per GPU, k = 16 sampled
                           actions, 256 simulations/move, random-init 16x256 ResNet (torch seed 123)
   4x4_1024                configs[1]: 4x4 Tak, 1024 concurrent games, k = 16, 128 simulations/move, 16x256 ResNet
+  5x5_selfplay            (not a BASELINE config; the third board size of the north star) 5x5, 8192 games, 20x256 ResNet
   reanalyze_1m            configs[4]: 6x6 `reanalyze` fresh-target search over a synthetic replay buffer of 1 M positions
                           (all plies of random playouts), positions sharded over the GPUs by contiguous index range,
                           batches of 8192 fresh roots per GPU, k = 16, 256 simulations
@@ -51,6 +52,8 @@ WORKLOADS = {
                          metric="self-play MCTS simulations/sec, 6x6 Tak"),
     "4x4_1024": dict(kind="selfplay", n=4, games=1024, k=16, budget=128,
                      metric="self-play MCTS simulations/sec, 4x4 Tak"),
+    "5x5_selfplay": dict(kind="selfplay", n=5, games=8192, k=16, budget=256,
+                         metric="self-play MCTS simulations/sec, 5x5 Tak"),
     "reanalyze_1m": dict(kind="reanalyze", n=6, games=8192, k=16, budget=256, buffer=1_000_000,
                          metric="reanalyze MCTS simulations/sec, 6x6 Tak"),
 }
@@ -130,7 +133,7 @@ def workload_config(wl: dict, name: str, n_gpus: int) -> dict:
     }
     if wl["kind"] == "selfplay":
         cfg["description"] = (f"{n}x{n} Tak (half komi {HALF_KOMI}) self-play, {wl['games']} concurrent games per GPU, "
-                              f"Gumbel sequential halving k={wl['k']}, {wl['budget']} sims/move, 16x256 ResNet, "
+                              f"Gumbel sequential halving k={wl['k']}, {wl['budget']} sims/move, {20 if n == 5 else 16}x256 ResNet, "
                               f"model reload (weight generation) before every move")
         cfg["sharding"] = f"games sharded over {n_gpus} GPU(s) by contiguous global id, no data-path collective"
     else:

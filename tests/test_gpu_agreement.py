@@ -93,6 +93,19 @@ def test_bf16_mode_agreement_is_measured_and_reported(headline):
     assert agree >= 0.95
 
 
+@pytest.mark.parametrize("n,hk,G,k,budget,key", [(4, 4, 1024, 16, 128, "4x4_16blocks_k16_128sims_fp16"),
+                                                 (5, 4, 512, 16, 128, "5x5_20blocks_k16_128sims_fp16")])
+def test_default_dtype_agreement_on_the_other_board_sizes(n, hk, G, k, budget, key):
+    """BASELINE configs[1] (4x4, full 16-block network, k = 16, 128 simulations, 1024 positions) and the 5x5 network
+    (net5: 20 blocks): the same whole-search comparison for the default dtype."""
+    ref = net_ref.Net(n, seed=123)
+    agree, same_visits = run_agreement(n, hk, G, k, budget, network.DTYPE_DEFAULT, ref, playout_positions(n, hk, G, 7 + n),
+                                       seed=11)
+    print(f"{n}x{n}: chosen-move agreement {agree:.4f} on {G} positions, identical root visit vectors {same_visits:.4f}")
+    record(key, {"agreement": agree, "identical_root_visits": same_visits, "positions": G})
+    assert agree >= 0.99
+
+
 def test_default_dtype_agreement_small_network_4x4():
     """The round-1 configuration (4x4, 4 blocks, k = 8, 48 simulations, 384 positions), for continuity."""
     n, hk, G = 4, 4, 384
