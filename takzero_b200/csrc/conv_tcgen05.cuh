@@ -134,6 +134,8 @@ struct Layer {
 
 struct Params {
     Layer layers[MAX_LAYERS];       // run back to back; layer l reads what layer l-1 wrote
+    const __nv_bfloat16* dead_after[MAX_LAYERS];  // buffer of the chunk's activation set that nobody reads any more
+                                    // once layer l's MMAs are done (or null): its lines are discarded from L2
     int n_layers;
     long long rows_set;             // rows per chunk plane of one activation set
     long long set_stride;           // elements between activation set 0 (even chunks) and set 1 (odd chunks)
@@ -280,6 +282,10 @@ __device__ __forceinline__ void wait_counter(const unsigned* counter, unsigned n
     }
 }
 // generic-proxy writes (observed through the acquire above) -> async-proxy reads of this thread's bulk copies
+// the 128-byte line at `p` is dead: drop it from L2 without writing it back
+__device__ __forceinline__ void discard_l2_line(const void* p) {
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -765,6 +771,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
             float* stg = s_gather + (wq * 32 + lane) * 32;  // this thread's 32 staged channels (XOR-swizzled by lane)
             mbar_wait(t_full + 8 * acc, (it >> 1) & 1);
             tc_fence_after();
+#ifndef TZ_NO_DISCARD
+            if (p.dead_after[layer] != nullptr && !local && p.n_layers > 1) {
+                // All MMAs of the tile are done, so its A rows have been read for the last time -- by this tile.  Rows
+                // within HALO of the CTA tile's ends are also read by the neighbours; the 112 in between are dead: tell
+                // the L2 not to write them back (a chunk's activation set is dirty from end to end when the chunk has
+                // finished, and the next chunk's traffic would evict it to DRAM line by line).  One line = 8 rows of
+                // one chunk plane; 14 lines x 32 planes per CTA tile, spread over the 128 epilogue threads.
+                const uint8_t* base = reinterpret_cast<const uint8_t*>(p.dead_after[layer] + set_off) +
+                                      (size_t)(p.guard + t * TILE_M + HALO) * 16;
+                for (int i = wq * 32 + lane; i < 14 * 32; i += 128) {
+                    const int plane_i = i / 14, line_i = i - plane_i * 14;
+                    if (t * TILE_M + HALO + 8 * line_i < wi.rows)
+                        discard_l2_line(base + (size_t)plane_i * (size_t)p.rows_set * 16 + (size_t)line_i * 128);
+                }
+            }
+#endif
             CHAIN(pair == 10 && rank == 0 && wq == 0 && lane == 0 && (layer == 10 || layer == 11), layer, 3, 0);
             // Inside a fused launch the residual rows were written by another SM two layers ago.  One gpu-scope
             // acquire per tile (on the counter that writer released) makes the plain loads below see them: it costs

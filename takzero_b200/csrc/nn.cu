@@ -996,7 +996,15 @@ static int launch_network(tz_handle* h, const Boundary& io, const int* count_ptr
     for (size_t first = 0; first < all.size();) {
         const size_t chunk = s->fused ? all.size() - first : 1;
         conv::Params p;
-        for (size_t i = 0; i < chunk; i++) p.layers[i] = all[first + i];
+        for (size_t i = 0; i < chunk; i++) {
+            p.layers[i] = all[first + i];
+            p.dead_after[i] = nullptr;
+        }
+        if (chunk == all.size() && upto < 0) {
+            // the chunk's last reads of its activation set: t by the last tower convolution, x by the policy convolution
+            p.dead_after[chunk - 2] = s->act_t;
+            p.dead_after[chunk - 1] = s->act_x;
+        }
         p.n_layers = (int)chunk;
         p.allow_local = upto < 0;  // the debug read-backs look at the activation buffers in global memory
         if (launch_layers(h, p, set, count_ptr, count_max, s->rows_set, s->chunk_min_tiles) != cudaSuccess) return -1;
@@ -1131,6 +1139,7 @@ int nn_time_tower(tz_handle* h, int count, int reps, double* ms_per_conv) {
     auto one = [&](const conv::Layer& L) {
         conv::Params p;
         p.layers[0] = L;
+        p.dead_after[0] = nullptr;
         p.n_layers = 1;
         p.allow_local = 0;
         return launch_layers(h, p, set, nullptr, count, rows, 1 << 28);
