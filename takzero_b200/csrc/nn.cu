@@ -1001,8 +1001,9 @@ static int launch_network(tz_handle* h, const Boundary& io, const int* count_ptr
             p.dead_after[i] = nullptr;
         }
         if (chunk == all.size() && upto < 0) {
-            // the chunk's last reads of its activation set: t by the last tower convolution, x by the policy convolution
-            p.dead_after[chunk - 2] = s->act_t;
+            // last reads: the block middle t by the second convolution of every block (the next block overwrites it), the
+            // stream x by the policy convolution
+            for (size_t i = 2; i + 1 < chunk; i += 2) p.dead_after[i] = s->act_t;
             p.dead_after[chunk - 1] = s->act_x;
         }
         p.n_layers = (int)chunk;
