@@ -397,12 +397,14 @@ def run_selfplay(args, wl, emit):
         sym = capi.pinned_array((G,), np.int32)
         adj = capi.pinned_array((G,), np.int32)
         plies = m.positions()["ply"].astype(np.int64)
+        target_out = (capi.pinned_array((G, M), np.float32), capi.pinned_array((G,), np.float32),
+                      capi.pinned_array((G,), np.int32))
 
         def host_move(i):
             nonlocal plies
             run.generation()  # Net::load: rank 0's f32 tensors go host -> device every move
             moves = m.gumbel_sequential_halving(betas, k, budget, gumbel_pool[i % pool])
-            pol, ube, cnt = m.targets(vis, TARGET_BETA)
+            pol, ube, cnt = m.targets(vis, TARGET_BETA, out=target_out)
             randoms[:] = rng.integers(0, 1 << 62, size=G, dtype=np.uint64)
             sel = m.select_actions_in_selfplay(WEIGHTED_RANDOM_PLIES, SAMPLE_THRESHOLD, ALLOWED_DROP, randoms)
             play = np.where(plies < WEIGHTED_RANDOM_PLIES, sel, moves).astype(np.uint16)

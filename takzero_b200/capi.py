@@ -387,12 +387,18 @@ class BatchedMCTS:
         _check(lib().tz_root_stats(self._h, _ptr(out)))
         return out
 
-    def targets(self, visitations: float, beta: float, stride: Optional[int] = None, with_moves: bool = False):
+    def targets(self, visitations: float, beta: float, stride: Optional[int] = None, with_moves: bool = False, out=None):
+        """`out` = (policy, ube, n[, moves]) arrays to fill (e.g. pinned memory from pinned_array: the copies are then
+        asynchronous DMA instead of staged through pageable memory)."""
         stride = stride or self.move_stride
-        pol = np.zeros((self.G, stride), dtype=np.float32)
-        ube = np.zeros(self.G, dtype=np.float32)
-        n = np.zeros(self.G, dtype=np.int32)
-        mv = np.zeros((self.G, stride), dtype=np.uint16) if with_moves else None
+        if out is not None:
+            pol, ube, n = out[0], out[1], out[2]
+            mv = out[3] if with_moves else None
+        else:
+            pol = np.zeros((self.G, stride), dtype=np.float32)
+            ube = np.zeros(self.G, dtype=np.float32)
+            n = np.zeros(self.G, dtype=np.int32)
+            mv = np.zeros((self.G, stride), dtype=np.uint16) if with_moves else None
         _check(lib().tz_targets(self._h, visitations, beta, stride, _ptr(pol), _ptr(ube), _ptr(n), _ptr(mv)))
         return (pol, ube, n, mv) if with_moves else (pol, ube, n)
 

@@ -427,3 +427,60 @@ def test_gumbel_rows_shorter_than_a_root_are_reported():
     m.gumbel_sequential_halving(None, 8, 24, np.random.default_rng(0).gumbel(size=(G, width)).astype(np.float32))
     assert m.status() == 0
     m.close()
+
+
+def test_reanalyze_batch_on_the_device_equals_the_host_loop():
+    """reanalyze/src/main.rs:147-235 on the device (tz_stage_positions / tz_reanalyze_batch / tz_reanalyze_read): fresh
+    roots picked out of a staged pool, search, then per root the improved policy at most_visited_count() visitations,
+    the UBE target and the value target (root evaluation when known, else the negated evaluation of the selected
+    child as f32).  Must equal, bit for bit, the same steps through the host-buffer calls with the value rule applied by
+    the oracle's Eval functions."""
+    n, hk, G, k, budget = 4, 4, 48, 8, 48
+    rng = np.random.default_rng(21)
+    d = O.playout_positions(n, hk, 5, 1, 4000)
+    live = np.flatnonzero(d["terminal"] == 0)
+    # late positions, so that some roots get solved and the "known root" branch of the value rule is exercised
+    late = live[np.argsort(-d["states"].view(capi.STATE_DTYPE).reshape(-1)["ply"][live])[:300]]
+    pool = d["states"].view(capi.STATE_DTYPE).reshape(-1)[late].copy()
+    idx = rng.choice(len(pool), size=G, replace=False).astype(np.uint32)
+    params = capi.ReanalyzeParams(k, budget, 0.25, 77)
+
+    a = capi.BatchedMCTS(n, hk, G, arena_slots=1 << 14)
+    a.stage_positions(pool)
+    a.reanalyze_batch(idx, params)
+    got = a.reanalyze_read()
+    assert a.status() == 0
+
+    b = capi.BatchedMCTS(n, hk, G, arena_slots=1 << 14)
+    b.set_positions(pool[idx])
+    selected = b.gumbel_sequential_halving(None, k, budget, None, seed=77)
+    pol, ube, cnt, moves = b.targets(-1.0, 0.25, with_moves=True)
+    roots, ch = b.root_stats(), b.root_children()
+    L = O.lib()
+    want_value = np.zeros(G, dtype=np.float32)
+    solved = 0
+    for g in range(G):
+        if roots["eval_tag"][g] != capi.E_VALUE:
+            e = O.make_eval(int(roots["eval_tag"][g]), int(roots["eval_bits"][g]))
+            solved += 1
+        else:
+            i = int(np.flatnonzero(ch["moves"][g, : ch["n"][g]] == selected[g])[0])
+            tag, bits = int(ch["eval_tag"][g, i]), int(ch["eval_bits"][g, i])
+            child = O.make_eval(tag, bits if tag else float(np.uint32(bits).view(np.float32)))
+            e = L.tk_eval_negate(child)
+        want_value[g] = L.tk_eval_to_f32(e)
+    assert solved > 0 and solved < G
+    assert np.array_equal(got["n"], cnt)
+    assert np.array_equal(got["moves"], moves)
+    assert np.array_equal(got["policy"].view(np.uint32), pol.view(np.uint32))
+    assert np.array_equal(got["ube"].view(np.uint32), ube.view(np.uint32))
+    assert np.array_equal(got["value"].view(np.uint32), want_value.view(np.uint32))
+    # a second batch on the same handle (other roots) and the error for an index outside the pool
+    a.reanalyze_batch(rng.choice(len(pool), size=G, replace=False).astype(np.uint32), params)
+    assert a.reanalyze_read()["n"].min() > 0 and a.status() == 0
+    bad = idx.copy()
+    bad[3] = len(pool)
+    with pytest.raises(capi.TakzeroError, match="out of range"):
+        a.reanalyze_batch(bad, params)
+    for h in (a, b):
+        h.close()
