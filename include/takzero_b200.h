@@ -267,7 +267,10 @@ TZ_API int tz_tree_principal_variation(tz_handle* h, tz_move_t* out_moves, int c
  *   policy.conv2d.{weight [O,256,3,3], bias [O]}; {value,ube}.conv2d.{weight [1,256,1,1], bias [1]};
  *   {value,ube}.linear.{weight [1,N*N], bias [1]}.
  * The number of residual blocks is taken from the names (16 for net4/net6, 20 for net5).  BatchNorm is
- * folded (eval mode, eps 1e-5) and the convolutions are converted to the 16-bit network type here. */
+ * folded (eval mode, eps 1e-5) and the convolutions are converted to the 16-bit network type here.
+ * A 5x5 model's RND estimator (net5.rs:120-146,193-211) rides along when its tensors are present:
+ *   {rnd_learning,rnd_target}.{input_linear [1024,C*N*N], hidden_linear [1024,1024], final_linear [512,1024]}.{weight,bias},
+ *   min [1], max [1]; the local uncertainty is then normalized_rnd instead of the hash-set lookup. */
 TZ_API int tz_set_weights(tz_handle* h, const tz_tensor_t* tensors, int count);
 
 /* ---- multi-GPU (one process per GPU; games shard by contiguous global id, tz_config_t::game_base) ------------

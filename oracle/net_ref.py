@@ -80,8 +80,21 @@ class Policy(nn.Module):  # net6_simhash.rs:74-86
         return self.conv2d(x)
 
 
+class Rnd(nn.Module):  # net5.rs:120-146 `rnd`
+    def __init__(self, size: int):
+        super().__init__()
+        self.input_linear = nn.Linear(size, 1024)
+        self.hidden_linear = nn.Linear(1024, 1024)
+        self.final_linear = nn.Linear(1024, 512)
+
+    def forward(self, x):
+        x = x.reshape(x.shape[0], -1)
+        x = x / x.square().sum(dim=1, keepdim=True)
+        return self.final_linear(torch.relu(self.hidden_linear(torch.relu(self.input_linear(x)))))
+
+
 class Net(nn.Module):
-    def __init__(self, n: int, seed: int = 123, blocks: int | None = None, randomize_bn: bool = False):
+    def __init__(self, n: int, seed: int = 123, blocks: int | None = None, randomize_bn: bool = False, rnd: bool = False):
         super().__init__()
         torch.manual_seed(seed)
         L = O.lib()
@@ -95,6 +108,12 @@ class Net(nn.Module):
         # root.randn_standard("simhash_matrix", [input_size, HASH_BITS]) (net6_simhash.rs:136-139)
         self.simhash_matrix = torch.randn(self.cin * n * n, 32, generator=torch.Generator().manual_seed(seed + 7))
         self.simhash_set: set = set()  # indices whose bit is set (the reference keeps a 2^32-bit BitBox)
+        self.has_rnd = rnd
+        if rnd:  # net5.rs:163-170: the 5x5 network's local uncertainty is RND, not a hash set
+            self.rnd_learning = Rnd(self.cin * n * n)
+            self.rnd_target = Rnd(self.cin * n * n)
+            self.min = nn.Parameter(torch.zeros(1))
+            self.max = nn.Parameter(torch.ones(1))
         if randomize_bn:  # exercise the BN folding with non-trivial statistics
             g = torch.Generator().manual_seed(seed + 1)
             for m in self.modules():
@@ -116,6 +135,12 @@ class Net(nn.Module):
         xs = xs.clone()
         xs[:, self.cin - 2] = 0.0
         return xs.reshape(xs.shape[0], -1) @ self.simhash_matrix
+
+    @torch.no_grad()
+    def normalized_rnd(self, xs):
+        """net5.rs:193-211: sum((learning - target)^2), normalized with min / max, times MAXIMUM_VARIANCE."""
+        rnd = (self.rnd_learning(xs) - self.rnd_target(xs)).square().sum(dim=1)
+        return torch.clamp((rnd - self.min) / (self.max - self.min), 0.0, 1.0) * MAXIMUM_VARIANCE
 
     def get_indices(self, xs) -> np.ndarray:
         dots = self.simhash_dots(xs).numpy()
@@ -174,7 +199,10 @@ class Net(nn.Module):
         for i, acts in enumerate(actions):
             idx = torch.tensor([O.move_index(n, a) for a in acts], dtype=torch.long)
             out_logits.append(policy[i, idx].numpy().astype(np.float32))
-        local = torch.tensor([0.0 if int(i) in self.simhash_set else MAXIMUM_VARIANCE for i in self.get_indices(xs)])
+        if self.has_rnd:
+            local = self.normalized_rnd(xs)
+        else:
+            local = torch.tensor([0.0 if int(i) in self.simhash_set else MAXIMUM_VARIANCE for i in self.get_indices(xs)])
         unc = torch.clamp(torch.maximum(torch.exp(ube.view(-1)), local), 0.0, MAXIMUM_VARIANCE)
         return out_logits, values.view(-1).numpy().astype(np.float32), unc.numpy().astype(np.float32)
 

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtakzero_b200.so")
-SOURCES = ["api.cu", "kernels.cu", "nn.cu", "comm.cu", "model_file.cpp"]
+SOURCES = ["api.cu", "kernels.cu", "nn.cu", "rnd.cu", "comm.cu", "model_file.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--cudart", "static",

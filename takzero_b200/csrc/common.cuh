@@ -109,6 +109,7 @@ struct TzDev {
     const float* nn_head_misc;       // conv biases, linear weights / biases of the value and UBE heads
     const uint32_t* nn_novelty_set;  // 2^32-bit set or null (empty)
     const uint32_t* nn_novelty_idx;  // [Q] hash index of every queued position
+    const float* nn_rnd_unc;         // [Q] normalized RND uncertainty of every queued position (net5), or null
     const float* ln_table;  // exploration_rate(n), n < TZ_LN_TABLE (host libm logf)
     // sequential halving
     uint16_t* set_child;  // [G][TZ_MAX_K] candidate set (root child index)

@@ -124,11 +124,11 @@ __device__ __forceinline__ void encode_square16_smem(uint8_t* row, int plane_byt
 // Value head (conv1x1 + ReLU + Linear + tanh) and uncertainty = clamp(max(exp(ube), local), 0, 4) of queue slot q
 // from the two per-row features the epilogue of the last tower convolution wrote (the 1x1 convolutions), with
 // local = 0 when the position's novelty-hash bit is in the set, else MAXIMUM_VARIANCE = 4.0
-// (net6_simhash.rs:243-256).  Warp-convergent; every lane returns the same values.
+// (net6_simhash.rs:243-256), or the RND estimate of the 5x5 network.  Warp-convergent; every lane returns the same values.
 // head_misc: [2] conv biases, [2][36] linear weights, [2] linear biases.
 __device__ __forceinline__ void warp_heads(const float* head_feat, const float* head_misc, const uint32_t* novelty_set,
-                                           const uint32_t* novelty_idx, int q, int nn, int lane, float* value,
-                                           float* variance) {
+                                           const uint32_t* novelty_idx, const float* rnd_unc, int q, int nn, int lane,
+                                           float* value, float* variance) {
     const float bv = head_misc[0], bu = head_misc[1];
     const float* lin_v = head_misc + 2;
     const float* lin_u = head_misc + 2 + 36;
@@ -146,7 +146,9 @@ __device__ __forceinline__ void warp_heads(const float* head_feat, const float* 
     *value = tanhf(acc_v + head_misc[2 + 72]);
     const float ube = acc_u + head_misc[2 + 73];
     float local = 4.0f;
-    if (novelty_set) {
+    if (rnd_unc) {  // net5: normalized_rnd of the position (net5.rs:271-277), rnd.cu
+        local = rnd_unc[q];
+    } else if (novelty_set) {
         const uint32_t idx = novelty_idx[q];
         if ((novelty_set[idx >> 5] >> (idx & 31)) & 1u) local = 0.0f;
     }

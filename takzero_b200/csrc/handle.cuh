@@ -7,6 +7,7 @@
 
 struct NnState;  // nn.cu
 struct TzComm;   // comm.cu
+struct RndState; // rnd.cu
 
 struct tz_handle {
     int device = 0;
@@ -19,6 +20,7 @@ struct tz_handle {
     void* agent_ctx = nullptr;
     NnState* nn = nullptr;
     int nn_f16 = 1;  // 16-bit type the next tz_set_weights converts to: 1 fp16 (default), 0 bf16
+    RndState* rnd = nullptr;  // RND local-uncertainty estimator (net5), null = the model has none
     TzComm* comm = nullptr;  // NCCL communicator of this rank (tz_comm_init), null = single GPU
     unsigned long long* reduce_buf = nullptr;  // device staging of tz_allreduce_sum
     // tz_debug_network_mode (test / measurement hooks; the defaults are the product)

@@ -216,7 +216,8 @@ __device__ __forceinline__ void warp_expand(const TzDev& d, int g, int q, const 
     __syncwarp();
     float value, variance;
     if (d.nn_head_feat != nullptr)  // device network: the heads' last step happens here (encode.cuh)
-        enc::warp_heads(d.nn_head_feat, d.nn_head_misc, d.nn_novelty_set, d.nn_novelty_idx, q, d.nn, lane, &value, &variance);
+        enc::warp_heads(d.nn_head_feat, d.nn_head_misc, d.nn_novelty_set, d.nn_novelty_idx, d.nn_rnd_unc, q, d.nn, lane, &value,
+                        &variance);
     else {
         value = d.value[q];
         variance = d.variance[q];

@@ -21,6 +21,8 @@
 #include "conv_tcgen05.cuh"
 #include "encode.cuh"
 #include "nn.cuh"
+#include "planes.cuh"
+#include "rnd.cuh"
 #include "rules.cuh"
 
 #define WPB TZ_WARPS_PER_BLOCK
@@ -111,6 +113,8 @@ void nn_free(tz_handle* h) {
     h->d.nn_head_misc = nullptr;
     h->d.nn_novelty_set = nullptr;
     h->d.nn_novelty_idx = nullptr;
+    h->d.nn_rnd_unc = nullptr;
+    rnd_free(h);
 }
 
 // ---- input planes (network/repr.rs:169-228), parity hook -------------------------------------------
@@ -191,45 +195,6 @@ __global__ void k_encode16(const TzState* states, int count, int n, int f16, flo
 
 // One warp per position, lane = hash bit: dot of the f32 planes (side-to-move plane zeroed) with column
 // `lane` of the [C*N*N][32] matrix; bit set when the dot is >= 0; index = sum of 2^bit.
-// f32 input planes of one position into shared memory (x[plane * nn + square], `game_repr` order); the warp's
-// lanes own the squares.  zero_colour leaves the "black to move" plane at 0 (SimHash, net6_simhash.rs:209-222).
-__device__ __forceinline__ void warp_fill_planes(float* x, const TzState* st, int n, int half_komi, int lane,
-                                                 bool zero_colour) {
-    const int nn = n * n, ss = 2 * n + 3, C = 2 * (ss + 2) + 2;
-    for (int i = lane; i < C * nn; i += 32) x[i] = 0.0f;
-    __syncwarp();
-    const int me = st->to_move, other = me ^ 1;
-    const TzBoards b = warp_boards(st, nn, lane);
-    const int s0 = n == 3 ? 10 : n == 4 ? 15 : n == 5 ? 21 : 30;
-    const int c0 = n >= 5 ? 1 : 0;
-    const float r0 = __fdiv_rn((float)st->stones[me], (float)s0);
-    const float r1 = c0 ? __fdiv_rn((float)st->caps[me], (float)c0) : 0.0f;
-    const float r2 = __fdiv_rn((float)st->stones[other], (float)s0);
-    const float r3 = c0 ? __fdiv_rn((float)st->caps[other], (float)c0) : 0.0f;
-    const float fcd = __fsub_rn((float)(__popcll(b.flat[0]) - __popcll(b.flat[1])), __fdiv_rn((float)half_komi, 2.0f));
-    const float fcd_sq = __fdiv_rn(fcd, (float)nn);
-    for (int sq = lane; sq < nn; sq += 32) {
-        const int h = st->height[sq];
-        if (h > 0) {
-            const uint64_t stack = st->stack[sq];
-            const int top_col = (int)((stack >> (h - 1)) & 1ull);
-            x[(st->top[sq] + (top_col != me ? ss : 0)) * nn + sq] = 1.0f;
-            for (int i = 0; i < ss - 3 && h - 2 - i >= 0; i++) {
-                const int col = (int)((stack >> (h - 2 - i)) & 1ull);
-                x[(3 + i + (col != me ? ss : 0)) * nn + sq] = 1.0f;
-            }
-        }
-        const int base = 2 * ss;
-        x[(base + 0) * nn + sq] = r0;
-        x[(base + 1) * nn + sq] = r1;
-        x[(base + 2) * nn + sq] = r2;
-        x[(base + 3) * nn + sq] = r3;
-        if (!zero_colour && me == 1) x[(base + 4) * nn + sq] = 1.0f;
-        x[(base + 5) * nn + sq] = fcd_sq;
-    }
-    __syncwarp();
-}
-
 __global__ void __launch_bounds__(32 * WPB) k_simhash(const TzState* states, const int* count_ptr, int count_max, int n,
                                                        int half_komi, const float* matrix, uint32_t* out_idx) {
     __shared__ TzState s_state[WPB];
@@ -346,12 +311,12 @@ __global__ void __launch_bounds__(32 * WPB) k_prepare_eval(TzState* states, int 
 // arrays (tz_evaluate); the search does the same inside k_expand.
 __global__ void __launch_bounds__(32 * WPB) k_heads(const float* head_feat, const float* head_misc, int count, int n,
                                                      const uint32_t* novelty_set, const uint32_t* novelty_idx,
-                                                     float* out_value, float* out_variance) {
+                                                     const float* rnd_unc, float* out_value, float* out_variance) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * WPB + warp;
     if (q >= count) return;
     float value, variance;
-    enc::warp_heads(head_feat, head_misc, novelty_set, novelty_idx, q, n * n, lane, &value, &variance);
+    enc::warp_heads(head_feat, head_misc, novelty_set, novelty_idx, rnd_unc, q, n * n, lane, &value, &variance);
     if (lane == 0) {
         out_value[q] = value;
         out_variance[q] = variance;
@@ -789,6 +754,8 @@ int nn_set_weights(tz_handle* h, const char* const* names, const float* const* d
     if ((rc = stage_raw(h, ts)) != TZ_OK) return rc;
     const int target = h->nn->active < 0 ? 0 : h->nn->active ^ 1;
     if ((rc = upload_and_fold(h, target)) != TZ_OK) return rc;
+    // the RND estimator of a 5x5 model (rnd_learning.* / rnd_target.* / min / max) rides along with the tensors
+    if ((rc = rnd_set_weights(h, names, data, shapes, ndims, count)) != TZ_OK) NN_FAIL(rc, "%s", rnd_last_error());
     return publish(h, target);
 }
 
@@ -860,6 +827,7 @@ static void bind_search(tz_handle* h) {
     h->d.nn_head_misc = on ? reinterpret_cast<const float*>(s->wset[s->active] + s->lay.head_misc) : nullptr;
     h->d.nn_novelty_set = on ? s->simhash_set : nullptr;
     h->d.nn_novelty_idx = on ? s->simhash_idx : nullptr;
+    h->d.nn_rnd_unc = on ? rnd_uncertainty(h) : nullptr;
 }
 void nn_bind_search(tz_handle* h) { bind_search(h); }
 // every collective of a handle is issued on one stream: the weight stream once a network exists
@@ -1047,6 +1015,7 @@ int nn_forward_queue(tz_handle* h) {
         h->launches += launched;
     }
     launch_novelty(h, d.leaf_state, d.nn_count, d.Q);
+    if (rnd_forward(h, d.leaf_state, d.Q) != TZ_OK) return TZ_ECUDA;
     return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
 }
 
@@ -1075,8 +1044,9 @@ int nn_forward_host(tz_handle* h, int count) {
     h->launches += 1 + launched;
     if (limit >= 0) return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
     launch_novelty(h, d.leaf_state, nullptr, count);
+    if (rnd_forward(h, d.leaf_state, count) != TZ_OK) return TZ_ECUDA;
     k_heads<<<wblocks, 32 * WPB, 0, h->stream>>>(s->head_feat, reinterpret_cast<const float*>(s->wset[s->active] + s->lay.head_misc),
-                                                 count, d.n, s->simhash_set, s->simhash_idx, d.value, d.variance);
+                                                 count, d.n, s->simhash_set, s->simhash_idx, rnd_uncertainty(h), d.value, d.variance);
     h->launches += 1;
     return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
 }

@@ -429,3 +429,48 @@ def test_model_reload_replaces_weights_and_keeps_buffers():
     m.gumbel_sequential_halving(None, 8, 48, None, seed=1)
     assert m.status() == 0
     m.close()
+
+
+def test_rnd_local_uncertainty_of_the_5x5_network(tmp_path):
+    """net5.rs:120-146,193-211,271-277: the 5x5 network's local uncertainty is random network distillation -- two MLPs
+    (800 -> 1024 -> 1024 -> 512) on the planes divided by the sum of their squares, sum of squared differences,
+    normalized with `min` / `max`, times 4, combined as clamp(max(exp(ube), rnd), 0, 4).  Device (TF32 tensor-op GEMMs)
+    against the f32 restatement; the normalization is set so that the estimates spread over (0, 4)."""
+    from takzero_b200 import weights
+
+    n, hk, count = 5, 4, 96
+    ref = net_ref.Net(n, seed=31, blocks=2, rnd=True)
+    games = sample_positions(n, hk, count, 31)
+    actions = [O.possible_moves(g) for g in games]
+    states = games_to_states(games)
+    xs = torch.from_numpy(np.stack([O.game_repr(g).reshape(ref.cin, n, n) for g in games]))
+    with torch.no_grad():
+        raw = (ref.rnd_learning(xs) - ref.rnd_target(xs)).square().sum(dim=1)
+        # make exp(ube) small so that the RND term decides, and spread it over the range
+        ref.ube.linear.bias.fill_(-6.0)
+        ref.min.fill_(float(raw.min()) - 0.1 * float(raw.max() - raw.min()))
+        ref.max.fill_(float(raw.max()) + 0.1 * float(raw.max() - raw.min()))
+    _, _, want = ref.policy_value_uncertainty(games, actions)
+    assert want.min() > 0.05 and want.max() < 3.95 and want.std() > 0.3
+    m = capi.BatchedMCTS(n, hk, count, arena_slots=1 << 13)
+    network.set_weights(m, ref.tensors())
+    logits, values, got = network.evaluate(m, states, actions)
+    print("RND uncertainty: max abs err", float(np.abs(got - want).max()), "range", float(want.min()), float(want.max()))
+    assert np.abs(got - want).max() <= 2e-2
+    # the search uses it: with beta > 0 the device-network search runs and the root's children carry these std devs
+    m.set_agent(capi.AGENT_NETWORK)
+    m.set_positions(states)
+    m.gumbel_sequential_halving(np.full(count, 0.25, np.float32), 8, 24, None, seed=2)
+    assert m.status() == 0
+    std = m.root_children()["std_dev"]
+    assert np.isfinite(std).all() and std.max() <= 2.0 + 1e-6 and std.max() > 0.2
+    # through the model file (tch names) as well
+    weights.save_ot(str(tmp_path / "model_latest.ot"), ref.tensors())
+    b = capi.BatchedMCTS(n, hk, count, arena_slots=4096)
+    network.load_model(b, str(tmp_path / "model_latest.ot"))
+    assert np.array_equal(network.evaluate(b, states, actions)[2], got)
+    # a model without the estimator switches it off again: 4.0 everywhere
+    network.set_weights(b, net_ref.Net(n, seed=31, blocks=2).tensors())
+    assert (network.evaluate(b, states, actions)[2] == 4.0).all()
+    for h in (m, b):
+        h.close()
