@@ -249,7 +249,13 @@ class Run:
         tzd.init_comm(self.m, self.rank, self.world, self.cuda_dev if self.world > 1 else None)
         self.net_dtype = network.DTYPE_BF16 if os.environ.get("TZ_BENCH_DTYPE", "f16") == "bf16" else network.DTYPE_F16
         # the model of every generation: rank 0 owns the tensors (the others pass none)
-        self.tensors = weights.random_init(n, seed=123) if self.rank == 0 else None
+        self.tensors = None
+        if self.rank == 0:  # in pinned memory: the library then uploads them from where they are (no staging copy)
+            self.tensors = {}
+            for name, t in weights.random_init(n, seed=123).items():
+                buf = capi.pinned_array(t.shape, "float32")
+                buf[...] = t
+                self.tensors[name] = buf
         self.raw_weight_bytes = sum(4 * v.size for v in self.tensors.values()) if self.tensors else 0
         t_w = time.perf_counter()
         self.generation()

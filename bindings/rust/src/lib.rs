@@ -83,6 +83,28 @@ impl BatchedMcts {
         check(unsafe { sys::tz_load_model(self.h, c.as_ptr()) })?;
         check(unsafe { sys::tz_set_agent(self.h, sys::TZ_AGENT_NETWORK as i32, None, ptr::null_mut()) }).map(|_| ())
     }
+    /// One process per GPU (csrc/comm.cu): rank 0 calls [`BatchedMcts::comm_unique_id`] and hands the 128 bytes to the
+    /// others (a file in the run directory will do), then every rank calls `comm_init`.
+    pub fn comm_unique_id() -> Result<[u8; 128], String> {
+        let mut id = [0u8; 128];
+        check(unsafe { sys::tz_comm_unique_id(id.as_mut_ptr() as *mut _) })?;
+        Ok(id)
+    }
+    pub fn comm_init(&mut self, id: &[u8; 128], nranks: i32, rank: i32) -> Result<(), String> {
+        check(unsafe { sys::tz_comm_init(self.h, id.as_ptr() as *const _, nranks, rank) }).map(|_| ())
+    }
+    /// The `Net::load` before every move (selfplay/src/main.rs:107) as ONE collective over all ranks: the root passes
+    /// the model's tensors (e.g. read with `tz_read_model_file`), the others `None`; every rank swaps weight sets
+    /// between two moves.  Without a communicator this is `Net::load` on one GPU.
+    pub fn broadcast_weights(&mut self, tensors: Option<&[sys::tz_tensor_t]>, res_blocks: i32, root: i32) -> Result<(), String> {
+        let (p, n) = match tensors { Some(t) => (t.as_ptr(), t.len() as i32), None => (ptr::null(), 0) };
+        check(unsafe { sys::tz_broadcast_weights(self.h, p, n, res_blocks, root) }).map(|_| ())
+    }
+    /// Whole-job totals of per-rank counters (what `learn` adds up through `buffer_lengths.txt`).
+    pub fn allreduce_sum(&mut self, values: &mut [u64]) -> Result<(), String> {
+        check(unsafe { sys::tz_allreduce_sum(self.h, values.as_mut_ptr(), values.len() as i32) }).map(|_| ())
+    }
+
     /// `Env::new_opening` for every game, drawn by the library from `seed`.
     pub fn new_openings(&mut self, seed: u64) -> Result<(), String> {
         check(unsafe { sys::tz_new_openings(self.h, ptr::null(), ptr::null(), ptr::null(), seed) }).map(|_| ())

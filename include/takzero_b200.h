@@ -289,7 +289,10 @@ TZ_API int tz_comm_destroy(tz_handle* h);
  * image on its GPU, ncclBroadcast sends that image (39 MB for the 6x6 network) into the inactive one of every rank's two
  * weight sets, and every rank swaps sets for the launches it enqueues from then on -- i.e. between two moves.  All of
  * it runs on a side stream beside the search.  The other ranks pass tensors = NULL and the number of residual blocks
- * (0 = the board's default: 20 for 5x5, else 16); every rank must use the same tz_set_network_dtype. */
+ * (0 = the board's default: 20 for 5x5, else 16); every rank must use the same tz_set_network_dtype.  Tensor data in
+ * pinned memory (tz_host_alloc) is uploaded from where it is, asynchronously: leave it unchanged until
+ * tz_weight_generation has returned; data in pageable memory is copied into the library's own staging buffer before
+ * the call returns (the same holds for tz_set_weights). */
 TZ_API int tz_broadcast_weights(tz_handle* h, const tz_tensor_t* tensors, int count, int res_blocks, int root);
 /* number of generations so far and the device time of the last one (upload + fold + broadcast); waits for it */
 TZ_API int tz_weight_generation(tz_handle* h, uint64_t* out_generation, double* out_ms);

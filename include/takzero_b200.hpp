@@ -465,6 +465,54 @@ class BatchedMCTS {
     }
     // Net::load(path, device) (network/mod.rs:20-27, net6_simhash.rs:164-181) incl. the `bitvec.bin` sidecar
     void load_model(const std::string& path) { check(tz_load_model(h_, path.c_str())); }
+    // ---- several GPUs, one process each (csrc/comm.cu): NCCL communicator, weight generations, counter sums ----------
+    static std::vector<uint8_t> comm_unique_id() {  // by one rank; the 128 bytes reach the others by the host's own means
+        std::vector<uint8_t> id(128);
+        check(tz_comm_unique_id(id.data()));
+        return id;
+    }
+    void comm_init(const std::vector<uint8_t>& id, int nranks, int rank) {
+        check(tz_comm_init(h_, nranks > 1 ? id.data() : nullptr, nranks, rank));
+    }
+    // The per-move `Net::load` of selfplay/src/main.rs:107 as ONE collective: the root passes the model, the others
+    // nullptr (and the number of residual blocks, 0 = the board's default); all ranks swap weight sets between moves.
+    void broadcast_weights(const Weights* w, int root = 0, int res_blocks = 0) {
+        if (!w) {
+            check(tz_broadcast_weights(h_, nullptr, 0, res_blocks, root));
+            return;
+        }
+        std::vector<tz_tensor_t> t(w->names.size());
+        for (size_t i = 0; i < t.size(); i++)
+            t[i] = tz_tensor_t{w->names[i].c_str(), w->data[i].data(), w->shapes[i].data(), (int)w->shapes[i].size()};
+        check(tz_broadcast_weights(h_, t.data(), (int)t.size(), res_blocks, root));
+    }
+    std::vector<uint64_t> allreduce_sum(std::vector<uint64_t> values) {
+        check(tz_allreduce_sum(h_, values.data(), (int)values.size()));
+        return values;
+    }
+    // ---- reanalyze on the device (reanalyze/src/main.rs:147-235) -------------------------------------------------------
+    void stage_positions(const std::vector<tz_state_t>& buffer) { check(tz_stage_positions(h_, buffer.data(), buffer.size())); }
+    void reanalyze_batch(const std::vector<uint32_t>* pool_indices, int sampled_actions, uint32_t budget, float ube_beta,
+                         uint64_t seed) {
+        const tz_reanalyze_t p{sampled_actions, budget, ube_beta, seed};
+        check(tz_reanalyze_batch(h_, pool_indices ? pool_indices->data() : nullptr, &p));
+    }
+    struct ReanalyzeTargets {
+        std::vector<float> policy, ube, value;
+        std::vector<int> n;
+        std::vector<Move> moves;
+    };
+    ReanalyzeTargets reanalyze_read() {
+        ReanalyzeTargets t;
+        const size_t cells = (size_t)games_ * stride_;
+        t.policy.resize(cells);
+        t.moves.resize(cells);
+        t.ube.resize(games_);
+        t.value.resize(games_);
+        t.n.resize(games_);
+        check(tz_reanalyze_read(h_, stride_, t.policy.data(), t.ube.data(), t.value.data(), t.n.data(), t.moves.data()));
+        return t;
+    }
     void set_agent(int kind, tz_agent_fn fn = nullptr, void* ctx = nullptr) { check(tz_set_agent(h_, kind, fn, ctx)); }
     void new_openings(uint64_t seed) { check(tz_new_openings(h_, nullptr, nullptr, nullptr, seed)); }
     void set_positions(const std::vector<tz_state_t>& envs) { check(tz_set_positions(h_, envs.data(), nullptr)); }

@@ -64,7 +64,13 @@ struct NnState {
     int active = -1;
     unsigned long long generation = 0;
     float* raw_dev = nullptr;  // raw f32 tensors of the generation being folded
-    float* raw_pin = nullptr;  // pinned host staging of the same
+    float* raw_pin = nullptr;  // pinned host staging of the same (tensors that come from pageable memory)
+    float* head_pin = nullptr; // pinned staging of the small head tensors (always assembled on the host)
+    struct DirectCopy {
+        size_t off, count;
+        const float* src;
+    };
+    std::vector<DirectCopy> direct;  // this generation's tensors that already sit in pinned memory: copied from there
     cudaStream_t wstream = nullptr;  // uploads, folds and broadcasts run beside the search stream
     cudaEvent_t ev_ready = nullptr;  // wstream: the new set is complete
     cudaEvent_t ev_swap = nullptr;   // search stream: everything enqueued before the last swap (the readers of the
@@ -104,6 +110,7 @@ void nn_free(tz_handle* h) {
     if (s->wstream) cudaStreamSynchronize(s->wstream);
     for (void* p : s->allocs) cudaFree(p);
     if (s->raw_pin) cudaFreeHost(s->raw_pin);
+    if (s->head_pin) cudaFreeHost(s->head_pin);
     for (cudaEvent_t e : {s->ev_ready, s->ev_swap, s->ev_h2d, s->ev_gen[0], s->ev_gen[1]})
         if (e) cudaEventDestroy(e);
     if (s->wstream) cudaStreamDestroy(s->wstream);
@@ -620,20 +627,49 @@ static int ensure_state(tz_handle* h, int blocks) {
     return TZ_OK;
 }
 
-// raw f32 tensors -> pinned staging, in the order RawLayout gives (plain copies, no arithmetic)
+// Raw f32 tensors -> what the upload reads, in the order RawLayout gives (plain copies, no arithmetic).  Tensors the
+// caller keeps in pinned memory (tz_host_alloc) are not copied on the host at all: the upload DMAs them from where they
+// are (the caller leaves them alone until the generation is complete, tz_weight_generation); tensors in pageable memory
+// go through the library's pinned staging buffer.
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+
 static int stage_raw(tz_handle* h, const std::vector<HostTensor>& ts) {
     NnState* s = h->nn;
     const int nn = s->n * s->n;
-    if (!s->raw_pin && cudaHostAlloc((void**)&s->raw_pin, s->raw.total * sizeof(float), cudaHostAllocDefault) != cudaSuccess)
-        NN_FAIL(TZ_ENOMEM, "cudaHostAlloc of the %zu MB weight staging failed", s->raw.total * 4 >> 20);
+    if (!s->head_pin && cudaHostAlloc((void**)&s->head_pin, (2 * FILTERS + 76) * sizeof(float), cudaHostAllocDefault) != cudaSuccess)
+        NN_FAIL(TZ_ENOMEM, "cudaHostAlloc failed");
     if (!s->raw_dev) {
         if (cudaMalloc((void**)&s->raw_dev, s->raw.total * sizeof(float)) != cudaSuccess)
             NN_FAIL(TZ_ENOMEM, "cudaMalloc of the raw weight staging failed");
         s->allocs.push_back(s->raw_dev);
     }
-    if (s->h2d_recorded) cudaEventSynchronize(s->ev_h2d);  // the previous generation's upload has read raw_pin
+    if (s->h2d_recorded) cudaEventSynchronize(s->ev_h2d);  // the previous generation's upload has read its sources
+    s->direct.clear();
+    bool staging_failed = false;
     auto put = [&](size_t off, const std::string& name, size_t count) {
-        memcpy(s->raw_pin + off, find(ts, name)->data, count * sizeof(float));
+        const float* src = find(ts, name)->data;
+        if (is_pinned(src)) {
+            s->direct.push_back({off, count, src});
+            return;
+        }
+        if (!s->raw_pin && cudaHostAlloc((void**)&s->raw_pin, s->raw.total * sizeof(float), cudaHostAllocDefault) != cudaSuccess) {
+            staging_failed = true;
+            return;
+        }
+        memcpy(s->raw_pin + off, src, count * sizeof(float));
+        // adjacent staged pieces merge into one copy
+        if (!s->direct.empty() && s->direct.back().src == s->raw_pin + s->direct.back().off &&
+            s->direct.back().off + s->direct.back().count == off)
+            s->direct.back().count += count;
+        else
+            s->direct.push_back({off, count, s->raw_pin + off});
     };
     for (int l = 0; l < s->lay.layers; l++) {
         const bool first = l == 0, last = l == s->lay.layers - 1;
@@ -650,8 +686,7 @@ static int stage_raw(tz_handle* h, const std::vector<HostTensor>& ts) {
         }
         put(s->raw.w[l], conv_name + ".weight", (size_t)s->raw.cout[l] * s->raw.cin[l] * 9);
         if (last) {
-            memset(s->raw_pin + s->raw.aux[l], 0, FILTERS * sizeof(float));
-            put(s->raw.aux[l], conv_name + ".bias", (size_t)s->raw.cout[l]);
+            put(s->raw.aux[l], conv_name + ".bias", (size_t)s->raw.cout[l]);  // k_fold_bias reads cout of the 256 slots
         } else {
             put(s->raw.aux[l], bn_name + ".weight", FILTERS);
             put(s->raw.aux[l] + FILTERS, bn_name + ".bias", FILTERS);
@@ -659,10 +694,12 @@ static int stage_raw(tz_handle* h, const std::vector<HostTensor>& ts) {
             put(s->raw.aux[l] + 3 * FILTERS, bn_name + ".running_var", FILTERS);
         }
     }
-    float* hd = s->raw_pin + s->raw.heads;
+    if (staging_failed) NN_FAIL(TZ_ENOMEM, "cudaHostAlloc of the %zu MB weight staging failed", s->raw.total * 4 >> 20);
+    float* hd = s->head_pin;
     memset(hd, 0, (2 * FILTERS + 76) * sizeof(float));
-    put(s->raw.heads, "value.conv2d.weight", FILTERS);
-    put(s->raw.heads + FILTERS, "ube.conv2d.weight", FILTERS);
+    memcpy(hd, find(ts, "value.conv2d.weight")->data, FILTERS * sizeof(float));
+    memcpy(hd + FILTERS, find(ts, "ube.conv2d.weight")->data, FILTERS * sizeof(float));
+    s->direct.push_back({s->raw.heads, (size_t)(2 * FILTERS + 76), hd});
     float* misc = hd + 2 * FILTERS;  // [2] conv biases, [2][36] linear weights, [2] linear biases
     misc[0] = find(ts, "value.conv2d.bias")->data[0];
     misc[1] = find(ts, "ube.conv2d.bias")->data[0];
@@ -678,8 +715,9 @@ static int upload_and_fold(tz_handle* h, int target) {
     NnState* s = h->nn;
     if (s->swap_recorded && cudaStreamWaitEvent(s->wstream, s->ev_swap, 0) != cudaSuccess) NN_FAIL(TZ_ECUDA, "cudaStreamWaitEvent");
     cudaEventRecord(s->ev_gen[0], s->wstream);
-    if (cudaMemcpyAsync(s->raw_dev, s->raw_pin, s->raw.total * sizeof(float), cudaMemcpyHostToDevice, s->wstream) != cudaSuccess)
-        NN_FAIL(TZ_ECUDA, "weight upload failed");
+    for (const NnState::DirectCopy& c : s->direct)
+        if (cudaMemcpyAsync(s->raw_dev + c.off, c.src, c.count * sizeof(float), cudaMemcpyHostToDevice, s->wstream) != cudaSuccess)
+            NN_FAIL(TZ_ECUDA, "weight upload failed");
     cudaEventRecord(s->ev_h2d, s->wstream);
     s->h2d_recorded = true;
     FoldParams fp;
