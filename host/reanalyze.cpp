@@ -123,7 +123,6 @@ int main(int argc, char** argv) {
         std::vector<tz_state_t> position_buffer, exploration_buffer;
         std::streamoff replays_seek = 0, exploration_replays_seek = 0;
         const int stride = mcts.move_stride();
-        const std::vector<float> zero_beta(games, 0.0f);
         for (int b = 0; b < batches;) {
             for (;;) {  // main.rs:78-91
                 const BufferLengths lengths = read_buffer_lengths(directory);
@@ -163,34 +162,18 @@ int main(int argc, char** argv) {
             for (size_t idx : sample_distinct(seed, (uint64_t)b, 0, games - from_exploration, position_buffer.size()))
                 batch.push_back(position_buffer[idx]);
             mcts.set_positions(batch);  // *node = Node::default(); *env = replay_env
-            const std::vector<Move> selected = mcts.gumbel_sequential_halving(zero_beta, sampled_actions, budget, seed + b);
-            const std::vector<tz_root_t> roots = mcts.root_stats();
-            const BatchedMCTS::Children ch = mcts.root_children();
-            const BatchedMCTS::RootTargets rt = mcts.targets(-1.0f, ube_beta);
+            // search and targets on the device (tz_reanalyze_batch): improved policy at most_visited_count() visitations,
+            // UBE target, and the value rule of main.rs:184-195 (root evaluation if known, else the negated evaluation
+            // of the selected child) -- only the targets themselves come back
+            mcts.reanalyze_batch(nullptr, sampled_actions, budget, ube_beta, seed + (uint64_t)b);
+            const BatchedMCTS::ReanalyzeTargets rt = mcts.reanalyze_read();
             std::string contents;
             for (int g = 0; g < games; g++) {
-                Eval value;
-                if (roots[g].eval_tag != 0) {
-                    value.tag = roots[g].eval_tag;
-                    value.ply = roots[g].eval_bits;
-                } else {
-                    int found = -1;
-                    for (int i = 0; i < ch.n[g]; i++)
-                        if (ch.moves[(size_t)g * stride + i] == selected[g]) {
-                            found = i;
-                            break;
-                        }
-                    if (found < 0) throw std::runtime_error("all non-terminal nodes should have at least one child");
-                    Eval child;
-                    child.tag = ch.eval_tag[(size_t)g * stride + found];
-                    child.ply = ch.eval_bits[(size_t)g * stride + found];
-                    value = child.negate();
-                }
                 Target t;
                 t.env = batch[g];
                 for (int i = 0; i < rt.n[g]; i++)
                     t.policy.emplace_back(rt.moves[(size_t)g * stride + i], rt.policy[(size_t)g * stride + i]);
-                t.value = value.to_f32();
+                t.value = rt.value[g];
                 t.ube = rt.ube[g];
                 contents += t.to_string(board);
             }
