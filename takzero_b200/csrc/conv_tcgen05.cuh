@@ -749,9 +749,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
             // channels of the square's first eight moves (8 bits each; g_valid says which slots hold one), decoded once
             // per tile, and the 32-channel blocks that hold any of the square's moves
             uint32_t g_ch0 = 0, g_ch1 = 0, g_valid = 0, g_blocks = 0;
+            int g_q = 0;
             if (L.g_out != nullptr && valid) {
                 const unsigned ug = (unsigned)grel;
                 const int q = (int)(ug / (unsigned)nn), sq = (int)(ug - (unsigned)q * (unsigned)nn);
+                g_q = q;
                 const uint32_t range = L.g_ranges[(size_t)q * 36 + sq];
                 g_first = (int)(range & 0xffffu);
                 g_count = (int)(range >> 16);
@@ -867,11 +869,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                                 g_row[i] = stg[(ch & 31) ^ lane];
                             }
                         }
-                        for (int m = 8; m < g_count; m++) {  // squares with more than eight moves: decode again
-                            const int i = g_perm ? (int)g_perm[g_first + m] : g_first + m;
-                            const int ch = enc::move_channel(p.n, g_act[i]);
-                            if (ch >= 0 && (ch & ~31) == c0) g_row[i] = stg[(ch & 31) ^ lane];
-                        }
                     }
                     if (head_w) {  // value / UBE 1x1 convolutions over the tower output (net6_simhash.rs:88-119)
 #pragma unroll
@@ -879,6 +876,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                             head_v = fmaf(f[j], __ldg(head_w + c0 + j), head_v);
                             head_u = fmaf(f[j], __ldg(head_w + N_OUT + c0 + j), head_u);
                         }
+                    }
+                }
+                if (L.g_out != nullptr) {
+                    // Squares with more than eight moves (tall stacks late in a game: up to several dozen spreads from
+                    // one square) would make their one thread the slowest of the tile: the whole warp takes such a
+                    // row's remaining moves, 32 at a time, from the owner's staged channels.
+                    uint32_t heavy = __ballot_sync(0xffffffffu, valid && g_count > 8 && ((g_blocks >> (c0 >> 5)) & 1u));
+                    if (heavy) {
+                        __syncwarp();  // the owners' staged channels are visible to the other lanes
+                        while (heavy) {
+                            const int src = __ffs(heavy) - 1;
+                            heavy &= heavy - 1;
+                            const int hq = __shfl_sync(0xffffffffu, g_q, src);
+                            const int hfirst = __shfl_sync(0xffffffffu, g_first, src);
+                            const int hcount = __shfl_sync(0xffffffffu, g_count, src);
+                            float* hrow = L.g_out + (size_t)hq * L.g_stride;
+                            const uint16_t* hact = L.g_actions + (size_t)hq * L.g_stride;
+                            const uint16_t* hperm = L.g_perm ? L.g_perm + (size_t)hq * L.g_stride : nullptr;
+                            const float* hstg = s_gather + (wq * 32 + src) * 32;
+                            for (int m = 8 + lane; m < hcount; m += 32) {
+                                const int i = hperm ? (int)hperm[hfirst + m] : hfirst + m;
+                                const int ch = enc::move_channel(p.n, hact[i]);
+                                if (ch >= 0 && (ch & ~31) == c0) hrow[i] = hstg[(ch & 31) ^ src];
+                            }
+                        }
+                        __syncwarp();  // before the owners stage the next block over these channels
                     }
                 }
                 if (to_smem && (c0 & 32) != 0) {
