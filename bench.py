@@ -360,21 +360,27 @@ def run_selfplay(args, wl, emit):
     run = Run(args, wl)
     m, capi = run.m, run.capi
     G, k, budget, M = wl["games"], wl["k"], wl["budget"], run.m.move_stride
-    m.new_openings(seed=1000)
     vis = target_visitations(k, budget)
     params = capi.SelfplayParams(k, budget, 0.0, WEIGHTED_RANDOM_PLIES, SAMPLE_THRESHOLD, ALLOWED_DROP, vis,
                                  TARGET_BETA, 20261018)
 
     # ---- resident path: warm-up, then EXACTLY --steps timed moves, a weight generation before every move ----------
-    for _ in range(args.warmup):
-        run.generation()
-        m.selfplay_move(params)
+    def fresh_games():
+        """Every timed loop searches the same plies: games from their openings + the warm-up moves."""
+        m.new_openings(seed=1000)
+        for _ in range(args.warmup):
+            run.generation()
+            m.selfplay_move(params)
+
+    fresh_games()
     clocks = ClockSampler(run.local_rank)
     clocks.start()
     every = timed_selfplay(run, params, args.steps, 1, profile=True)
     clock_info = clocks.stop()
     # the same with ONE generation in the region (the amortised cadence: a new model every >= --steps moves) and none
+    fresh_games()
     sparse = timed_selfplay(run, params, args.steps, args.steps, profile=False)
+    fresh_games()
     never = timed_selfplay(run, params, args.steps, 0, profile=False)
     positions = G * args.steps
 
@@ -402,6 +408,7 @@ def run_selfplay(args, wl, emit):
         randoms = capi.pinned_array((G,), np.uint64)
         sym = capi.pinned_array((G,), np.int32)
         adj = capi.pinned_array((G,), np.int32)
+        m.new_openings(seed=1000)  # the same plies as the resident loops
         plies = m.positions()["ply"].astype(np.int64)
         target_out = (capi.pinned_array((G, M), np.float32), capi.pinned_array((G,), np.float32),
                       capi.pinned_array((G,), np.int32))
@@ -423,7 +430,7 @@ def run_selfplay(args, wl, emit):
 
         h2d = 4 * G + 4 * G * M + 8 * G + 2 * G + 8 * G + run.raw_weight_bytes
         d2h = 2 * G + 4 * G * M + 4 * G + 4 * G + 2 * G + 4 * G + 5 * 4
-        e2e_warm = max(1, min(args.warmup, 2))
+        e2e_warm = max(1, args.warmup)
         for i in range(e2e_warm):
             host_move(i)
         run.barrier()
