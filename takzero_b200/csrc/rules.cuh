@@ -150,10 +150,20 @@ __device__ __forceinline__ uint16_t tz_mk_move(int row, int col, int kind, int p
 
 // number of legal drop sequences for `c` carried pieces, `reach` free squares and an
 // optional capstone flattening of a wall on square reach+1
+// (compositions of c into at most `reach` parts = sum_{j < min(reach, c)} C(c-1, j): partial sums of the binomial
+// rows, one byte per limit, looked up instead of added up -- this is the hottest arithmetic of k_select)
 __device__ __forceinline__ int spread_count(int c, int reach, bool smash) {
-    int cnt = 0;
     const int lim = reach < c ? reach : c;
-    for (int p = 1; p <= lim; p++) cnt += tz_binom(c - 1, p - 1);
+    unsigned long long sums;  // byte (lim - 1) = sum_{j < lim} C(c - 1, j)
+    switch (c) {
+        case 1: sums = 0x01ull; break;
+        case 2: sums = 0x0201ull; break;
+        case 3: sums = 0x040301ull; break;
+        case 4: sums = 0x08070401ull; break;
+        case 5: sums = 0x100f0b0501ull; break;
+        default: sums = 0x201f1a100601ull; break;
+    }
+    int cnt = lim > 0 ? (int)((sums >> (8 * (lim - 1))) & 0xffull) : 0;
     if (smash && reach + 1 <= c) cnt += reach == 0 ? (c == 1) : tz_binom(c - 2, reach - 1);
     return cnt;
 }
@@ -197,6 +207,7 @@ __device__ __forceinline__ int warp_movegen(const TzState* s, int n, uint16_t* o
     const bool opening = s->ply < 2;
     const bool can_stone = s->stones[me] > 0, can_cap = s->caps[me] > 0;
     int cnt[2] = {0, 0};
+    uint32_t dirs[2] = {0, 0};  // per direction: free run (3 bits) | wall behind it << 3, kept for pass 2
     // pass 1: per-square counts, squares indexed in generation order k = col*n + row
 #pragma unroll
     for (int slot = 0; slot < 2; slot++) {
@@ -209,6 +220,8 @@ __device__ __forceinline__ int warp_movegen(const TzState* s, int n, uint16_t* o
         } else if (!opening && (int)((s->stack[sq] >> (h - 1)) & 1ull) == me) {
             SquareDirs d;
             square_dirs(s, n, row, col, d);
+#pragma unroll
+            for (int k2 = 0; k2 < 4; k2++) dirs[slot] |= (uint32_t)(d.free_run[k2] | (d.wall_next[k2] ? 8 : 0)) << (4 * k2);
             const bool is_cap = s->top[sq] == TZ_CAP;
             const int maxc = h < n ? h : n;
             int c_total = 0;
@@ -265,18 +278,21 @@ __device__ __forceinline__ int warp_movegen(const TzState* s, int n, uint16_t* o
                 if (can_cap) out[o++] = tz_mk_move(row, col, TZ_CAP, 0);
             }
         } else {
-            SquareDirs d;
-            square_dirs(s, n, row, col, d);
             const bool is_cap = s->top[sq] == TZ_CAP;
             const int maxc = h < n ? h : n;
             for (int c = 1; c <= maxc; c++)
                 for (int k2 = 0; k2 < 4; k2++) {
-                    const int reach = d.free_run[k2] < c ? d.free_run[k2] : c;
-                    const bool smash = is_cap && d.wall_next[k2] && d.free_run[k2] < c;
+                    const int run = (int)((dirs[slot] >> (4 * k2)) & 7u);
+                    const bool wall = (dirs[slot] >> (4 * k2 + 3)) & 1u;
+                    const int reach = run < c ? run : c;
+                    const bool smash = is_cap && wall && run < c;
                     if (reach == 0 && !smash) continue;
+                    const bool all = reach >= c;  // every drop sequence fits: no per-pattern test
                     for (int rev = 1 << (c - 1); rev < (1 << c); rev++) {
-                        const int parts = __popc(rev);
-                        if (!(parts <= reach || (smash && parts == reach + 1 && (rev & 1)))) continue;
+                        if (!all) {
+                            const int parts = __popc(rev);
+                            if (!(parts <= reach || (smash && parts == reach + 1 && (rev & 1)))) continue;
+                        }
                         // pattern byte: bit (8-c+i) = bit (c-1-i) of rev
                         const int pat = (int)(__brev((unsigned)rev) >> (32 - c)) << (8 - c);
                         out[o++] = tz_mk_move(row, col, k2, pat);
