@@ -105,8 +105,19 @@ extern "C" TZ_API int tz_create(const tz_config_t* cfg, tz_handle** out) {
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(TZ_ECUDA, "no CUDA device: takzero_b200 has no CPU fallback");
     if (cfg->device < 0 || cfg->device >= ndev) return fail(TZ_EINVAL, "bad device ordinal %d", cfg->device);
+    if (cfg->move_stride > TZ_MAX_MOVES) return fail(TZ_EINVAL, "move_stride > %d", TZ_MAX_MOVES);
     CU(cudaSetDevice(cfg->device));
     tz_handle* h = new tz_handle();
+    // from here on a failure releases what was made so far
+#define CUH(call)                                                                        \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) {                                                         \
+            const int rc_ = fail(TZ_ECUDA, "%s: %s", #call, cudaGetErrorString(e_));      \
+            tz_destroy(h);                                                               \
+            return rc_;                                                                  \
+        }                                                                                \
+    } while (0)
     h->device = cfg->device;
     h->agent_kind = TZ_AGENT_SYNTHETIC;
     TzDev& d = h->d;
@@ -118,14 +129,13 @@ extern "C" TZ_API int tz_create(const tz_config_t* cfg, tz_handle** out) {
     d.G = cfg->n_games;
     d.Q = cfg->tree_batch > cfg->n_games ? cfg->tree_batch : cfg->n_games;
     d.M = cfg->move_stride > 0 ? cfg->move_stride : default_stride(d.n);
-    if (d.M > TZ_MAX_MOVES) return fail(TZ_EINVAL, "move_stride > %d", TZ_MAX_MOVES);
     d.game_base = cfg->game_base;
     const size_t G = (size_t)d.G, Q = (size_t)d.Q;
 
     uint32_t cap = cfg->arena_slots;
     if (cap == 0) {
         size_t free_b = 0, total_b = 0;
-        CU(cudaMemGetInfo(&free_b, &total_b));
+        CUH(cudaMemGetInfo(&free_b, &total_b));
         size_t c = (size_t)((double)free_b * 0.5 / ((double)G * 2.0 * 28.0));
         if (c > 262144) c = 262144;
         if (c < 4096) c = 4096;
@@ -199,7 +209,7 @@ extern "C" TZ_API int tz_create(const tz_config_t* cfg, tz_handle** out) {
         return rc;
     }
     d.ln_table = ln_table;
-    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     // exploration_rate(n) = ln((1 + n + 500) / 500) + 4 (policy.rs:140-145), evaluated with the
     // host libm like Rust's f32::ln, in the reference's operation order
     {
@@ -211,16 +221,16 @@ extern "C" TZ_API int tz_create(const tz_config_t* cfg, tz_handle** out) {
             volatile float l = logf(x);
             tab[i] = l + 4.0f;
         }
-        CU(cudaMemcpy(ln_table, tab.data(), sizeof(float) * TZ_LN_TABLE, cudaMemcpyHostToDevice));
+        CUH(cudaMemcpy(ln_table, tab.data(), sizeof(float) * TZ_LN_TABLE, cudaMemcpyHostToDevice));
     }
-    CU(cudaMemsetAsync(d.arena.half, 0, G, h->stream));
-    CU(cudaMemsetAsync(d.counters, 0, G * 4 * sizeof(unsigned long long), h->stream));
-    CU(cudaMemsetAsync(d.status, 0, sizeof(uint32_t), h->stream));
-    CU(cudaMemsetAsync(d.nn_count, 0, sizeof(int), h->stream));
-    CU(cudaMemsetAsync(d.set_len, 0, G * sizeof(int), h->stream));
-    CU(cudaMemsetAsync(h->fin_len, 0, G * sizeof(int), h->stream));
+    CUH(cudaMemsetAsync(d.arena.half, 0, G, h->stream));
+    CUH(cudaMemsetAsync(d.counters, 0, G * 4 * sizeof(unsigned long long), h->stream));
+    CUH(cudaMemsetAsync(d.status, 0, sizeof(uint32_t), h->stream));
+    CUH(cudaMemsetAsync(d.nn_count, 0, sizeof(int), h->stream));
+    CUH(cudaMemsetAsync(d.set_len, 0, G * sizeof(int), h->stream));
+    CUH(cudaMemsetAsync(h->fin_len, 0, G * sizeof(int), h->stream));
     // host staging for the callback agent and small read-backs
-    CU(cudaHostAlloc((void**)&h->pin_small, 4096, cudaHostAllocDefault));
+    CUH(cudaHostAlloc((void**)&h->pin_small, 4096, cudaHostAllocDefault));
     // every game starts from a fresh default position with an empty root
     std::vector<TzState> init(G);
     memset(init.data(), 0, G * sizeof(TzState));
@@ -230,10 +240,11 @@ extern "C" TZ_API int tz_create(const tz_config_t* cfg, tz_handle** out) {
         init[g].stones[0] = init[g].stones[1] = (uint8_t)stones;
         init[g].caps[0] = init[g].caps[1] = (uint8_t)caps;
     }
-    CU(cudaMemcpyAsync(h->fin_start, init.data(), G * sizeof(TzState), cudaMemcpyHostToDevice, h->stream));
+    CUH(cudaMemcpyAsync(h->fin_start, init.data(), G * sizeof(TzState), cudaMemcpyHostToDevice, h->stream));
     launch_set_positions(d, h->fin_start, nullptr, h->stream);
-    CU(cudaStreamSynchronize(h->stream));
-    CU(cudaGetLastError());
+    CUH(cudaStreamSynchronize(h->stream));
+    CUH(cudaGetLastError());
+#undef CUH
     *out = h;
     return TZ_OK;
 }
@@ -506,14 +517,13 @@ extern "C" TZ_API int tz_set_agent(tz_handle* h, int kind, tz_agent_fn fn, void*
     if (kind == TZ_AGENT_HOST) {
         if (!fn) return fail(TZ_EINVAL, "TZ_AGENT_HOST needs a callback");
         const size_t G = (size_t)h->d.Q, M = (size_t)h->d.M;
-        if (!h->pin_states) {
-            CU(cudaHostAlloc((void**)&h->pin_states, G * sizeof(TzState), cudaHostAllocDefault));
-            CU(cudaHostAlloc((void**)&h->pin_actions, G * M * sizeof(uint16_t), cudaHostAllocDefault));
-            CU(cudaHostAlloc((void**)&h->pin_nact, G * sizeof(int), cudaHostAllocDefault));
-            CU(cudaHostAlloc((void**)&h->pin_logits, G * M * sizeof(float), cudaHostAllocDefault));
-            CU(cudaHostAlloc((void**)&h->pin_value, G * sizeof(float), cudaHostAllocDefault));
-            CU(cudaHostAlloc((void**)&h->pin_variance, G * sizeof(float), cudaHostAllocDefault));
-        }
+        // each buffer on its own: a call that failed half way is completed by the next one
+        if (!h->pin_states) CU(cudaHostAlloc((void**)&h->pin_states, G * sizeof(TzState), cudaHostAllocDefault));
+        if (!h->pin_actions) CU(cudaHostAlloc((void**)&h->pin_actions, G * M * sizeof(uint16_t), cudaHostAllocDefault));
+        if (!h->pin_nact) CU(cudaHostAlloc((void**)&h->pin_nact, G * sizeof(int), cudaHostAllocDefault));
+        if (!h->pin_logits) CU(cudaHostAlloc((void**)&h->pin_logits, G * M * sizeof(float), cudaHostAllocDefault));
+        if (!h->pin_value) CU(cudaHostAlloc((void**)&h->pin_value, G * sizeof(float), cudaHostAllocDefault));
+        if (!h->pin_variance) CU(cudaHostAlloc((void**)&h->pin_variance, G * sizeof(float), cudaHostAllocDefault));
     } else if (kind == TZ_AGENT_NETWORK) {
         if (!nn_ready(h)) return fail(TZ_ENOWEIGHTS, "TZ_AGENT_NETWORK needs tz_set_weights first");
     } else if (kind != TZ_AGENT_SYNTHETIC) {
