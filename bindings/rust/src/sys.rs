@@ -184,6 +184,8 @@ extern "C" {
     pub fn tz_simhash_indices(h: *mut tz_handle, states: *const tz_state_t, count: c_int, out: *mut u32) -> c_int;
     pub fn tz_set_lcghash(h: *mut tz_handle, init: *const f32, bitset: *const u8) -> c_int;
     pub fn tz_lcghash_indices(h: *mut tz_handle, states: *const tz_state_t, count: c_int, out: *mut u32) -> c_int;
+    pub fn tz_update_counts(h: *mut tz_handle, states: *const tz_state_t, count: c_int) -> c_int;
+    pub fn tz_read_novelty_set(h: *mut tz_handle, out: *mut u8, cap: usize) -> c_int;
     pub fn tz_encode_planes(h: *mut tz_handle, states: *const tz_state_t, count: c_int, out: *mut f32) -> c_int;
     pub fn tz_debug_layer_limit(h: *mut tz_handle, limit: c_int) -> c_int;
     pub fn tz_debug_activations(h: *mut tz_handle, which: c_int, count: c_int, out: *mut f32) -> c_int;

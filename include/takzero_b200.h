@@ -336,6 +336,12 @@ TZ_API int tz_simhash_indices(tz_handle* h, const tz_state_t* states, int count,
  * the SimHash lookup of the handle.  tz_lcghash_indices = `get_indices` (integer hash: bit-exact parity hook). */
 TZ_API int tz_set_lcghash(tz_handle* h, const float* init, const uint8_t* bitset);
 TZ_API int tz_lcghash_indices(tz_handle* h, const tz_state_t* states, int count, uint32_t* out);
+/* `update_counts` (net6_simhash.rs:236-241; net4_lcghash.rs has the same): the hash index of every given position is
+ * marked as seen in the handle's set, with the hash set last (SimHash or LCG).  A handle whose set is still the empty
+ * one of a fresh network gets a real, zeroed set first.  tz_read_novelty_set copies the 2^29-byte image out in the
+ * layout of the reference's `bitvec.bin` (what `Net::save` writes next to the model, net6_simhash.rs:152-170). */
+TZ_API int tz_update_counts(tz_handle* h, const tz_state_t* states, int count);
+TZ_API int tz_read_novelty_set(tz_handle* h, uint8_t* out, size_t cap);
 /* game_repr (repr.rs:169-228): f32 planes [count][C][N][N] */
 TZ_API int tz_encode_planes(tz_handle* h, const tz_state_t* states, int count, float* out);
 /* test hooks: stop the tower after `limit` convolutions (-1 = full network); read back an activation

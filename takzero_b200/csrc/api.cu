@@ -1267,6 +1267,31 @@ extern "C" TZ_API int tz_lcghash_indices(tz_handle* h, const tz_state_t* states,
     return TZ_OK;
 }
 
+extern "C" TZ_API int tz_update_counts(tz_handle* h, const tz_state_t* states, int count) {
+    CHECK_H(h);
+    if (!states || count <= 0) return fail(TZ_EINVAL, "bad argument");
+    CHECK_STATES(states, count, nullptr);
+    Scratch s;
+    TzState* ds;
+    uint32_t* didx;
+    CU(s.get(&ds, (size_t)count));
+    CU(s.get(&didx, (size_t)count));
+    CU(cudaMemcpyAsync(ds, states, (size_t)count * sizeof(TzState), cudaMemcpyHostToDevice, h->stream));
+    const int rc = nn_update_counts(h, ds, count, didx);
+    if (rc) return fail(rc, "tz_update_counts needs tz_set_simhash / tz_set_lcghash first (the set takes 512 MiB of HBM)");
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return TZ_OK;
+}
+
+extern "C" TZ_API int tz_read_novelty_set(tz_handle* h, uint8_t* out, size_t cap) {
+    CHECK_H(h);
+    if (!out || cap < ((size_t)1 << 29)) return fail(TZ_EINVAL, "out must hold 2^29 bytes");
+    const int rc = nn_read_novelty_set(h, out);
+    if (rc) return fail(rc, "tz_read_novelty_set needs tz_set_simhash / tz_set_lcghash first");
+    return TZ_OK;
+}
+
 // ---- single tree (tei / analysis): Node::simulate_simple, simulate_batch, descend, principal_variation ----
 // The tree is game 0 of the handle; batch_size <= n_games because the per-leaf paths reuse the per-game buffers.
 

@@ -1257,3 +1257,43 @@ int nn_simhash_indices(tz_handle* h, const TzState* states, int count, uint32_t*
                                                                    s->simhash_matrix, out_dev);
     return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
 }
+
+// `update_counts` (net6_simhash.rs:236-241, net4_lcghash.rs `update_counts`): mark the hash index of every given
+// position as seen.  The set is created (empty) on first use; indices come from the handle's current hash.
+__global__ void k_set_bits(const uint32_t* __restrict__ idx, int count, uint32_t* __restrict__ set) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) atomicOr(&set[idx[i] >> 5], 1u << (idx[i] & 31));
+}
+
+int nn_update_counts(tz_handle* h, const TzState* states_dev, int count, uint32_t* idx_dev) {
+    NnState* s = h->nn;
+    if (!s || s->novelty == 0) return TZ_ENOWEIGHTS;
+    const size_t bytes = (size_t)1 << 29;
+    if (!s->simhash_set_alloc) {
+        if (cudaMalloc((void**)&s->simhash_set_alloc, bytes) != cudaSuccess) return TZ_ENOMEM;
+        s->allocs.push_back(s->simhash_set_alloc);
+    }
+    if (!s->simhash_set) {  // the empty set of a fresh network becomes a real one
+        if (cudaMemsetAsync(s->simhash_set_alloc, 0, bytes, h->stream) != cudaSuccess) return TZ_ECUDA;
+        s->simhash_set = s->simhash_set_alloc;
+        bind_search(h);
+    }
+    const int rc = s->novelty == 2 ? nn_lcghash_indices(h, states_dev, count, idx_dev)
+                                   : nn_simhash_indices(h, states_dev, count, idx_dev);
+    if (rc) return rc;
+    k_set_bits<<<(count + 255) / 256, 256, 0, h->stream>>>(idx_dev, count, s->simhash_set);
+    return cudaGetLastError() == cudaSuccess ? TZ_OK : TZ_ECUDA;
+}
+
+// the set as the reference saves it (bitvec.bin, 2^29 bytes); all zero while the set is still the empty one
+int nn_read_novelty_set(tz_handle* h, unsigned char* out_host) {
+    NnState* s = h->nn;
+    if (!s || s->novelty == 0) return TZ_ENOWEIGHTS;
+    const size_t bytes = (size_t)1 << 29;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return TZ_ECUDA;
+    if (!s->simhash_set) {
+        memset(out_host, 0, bytes);
+        return TZ_OK;
+    }
+    return cudaMemcpy(out_host, s->simhash_set, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? TZ_OK : TZ_ECUDA;
+}

@@ -29,3 +29,5 @@ int nn_debug_schedule(int count, int count_max, int n, int chunk_min_tiles, int 
                       int cap);
 int nn_set_lcghash(tz_handle* h, const float* init, const unsigned char* bitset);
 int nn_lcghash_indices(tz_handle* h, const TzState* states, int count, uint32_t* out_dev);
+int nn_update_counts(tz_handle* h, const TzState* states_dev, int count, uint32_t* idx_dev);
+int nn_read_novelty_set(tz_handle* h, unsigned char* out_host);

@@ -35,6 +35,8 @@ def _declare():
     capi.declare("tz_simhash_indices", [vp, vp, i32, vp], i32)
     capi.declare("tz_set_lcghash", [vp, vp, vp], i32)
     capi.declare("tz_lcghash_indices", [vp, vp, i32, vp], i32)
+    capi.declare("tz_update_counts", [vp, vp, i32], i32)
+    capi.declare("tz_read_novelty_set", [vp, vp, C.c_size_t], i32)
     capi.declare("tz_debug_layer_limit", [vp, i32], i32)
     capi.declare("tz_debug_activations", [vp, i32, i32, vp], i32)
     capi.declare("tz_debug_time_tower", [vp, i32, i32, C.POINTER(C.c_double)], i32)
@@ -249,4 +251,19 @@ def lcghash_indices(mcts: capi.BatchedMCTS, states: np.ndarray) -> np.ndarray:
     states = np.ascontiguousarray(states, dtype=capi.STATE_DTYPE)
     out = np.zeros(len(states), dtype=np.uint32)
     capi._check(capi.lib().tz_lcghash_indices(mcts.handle, capi._ptr(states), len(states), capi._ptr(out)))
+    return out
+
+
+def update_counts(mcts: capi.BatchedMCTS, states: np.ndarray) -> None:
+    """`Net::update_counts` (net6_simhash.rs:236-241): mark these positions as seen in the novelty set."""
+    _declare()
+    states = np.ascontiguousarray(states, dtype=capi.STATE_DTYPE)
+    capi._check(capi.lib().tz_update_counts(mcts.handle, capi._ptr(states), len(states)))
+
+
+def read_novelty_set(mcts: capi.BatchedMCTS) -> np.ndarray:
+    """The 2^29-byte image of the set, as the reference's `bitvec.bin` holds it."""
+    _declare()
+    out = np.empty(1 << 29, dtype=np.uint8)
+    capi._check(capi.lib().tz_read_novelty_set(mcts.handle, capi._ptr(out), out.size))
     return out

@@ -221,6 +221,51 @@ def test_simhash_indices_and_uncertainty():
     m.close()
 
 
+def test_update_counts_marks_positions_seen_and_survives_a_save(tmp_path):
+    """The reference's `counts_work` and `saving_works` (net6_simhash.rs:368-430): positions five random plies past an
+    opening are all novel for a fresh network (local uncertainty 4.0); after update_counts every one of them is seen
+    (uncertainty strictly lower); the set written like Net::save's bitvec.bin and loaded into another handle says the
+    same.  The set's image has exactly the bits of `get_indices` of those positions."""
+    from takzero_b200 import weights
+
+    n, hk, count = 6, 4, 128
+    ref = net_ref.Net(n, seed=456, blocks=1)
+    games = sample_positions(n, hk, count, 456)
+    actions = [O.possible_moves(g) for g in games]
+    states = games_to_states(games)
+    a = capi.BatchedMCTS(n, hk, count, arena_slots=4096)
+    network.set_weights(a, ref.tensors())
+    network.set_simhash(a, ref.simhash_matrix.numpy())
+    before = network.evaluate(a, states, actions)[2]
+    assert (before == 4.0).all()
+    network.update_counts(a, states)
+    after = network.evaluate(a, states, actions)[2]
+    # forward_hash went from 4.0 to 0.0 for every position, so what is left is clamp(exp(ube), 0, 4)
+    xs = torch.from_numpy(np.stack([O.game_repr(g).reshape(ref.cin, n, n) for g in games]))
+    with torch.no_grad():
+        ube = ref.ube(ref.core(xs)).view(-1).numpy()
+    assert np.abs(after - np.clip(np.exp(ube), 0.0, 4.0)).max() <= 2e-2
+    assert (before > after)[np.exp(ube) < 3.9].all() and (np.exp(ube) < 3.9).mean() > 0.9
+    idx = network.simhash_indices(a, states)
+    image = network.read_novelty_set(a)
+    want = np.zeros(1 << 29, dtype=np.uint8)
+    np.bitwise_or.at(want, idx >> 3, (1 << (idx & 7)).astype(np.uint8))
+    assert np.array_equal(image, want)
+    # a second update with the same positions changes nothing (the set only grows)
+    network.update_counts(a, states[: count // 2])
+    assert np.array_equal(network.read_novelty_set(a), want)
+
+    tensors = dict(ref.tensors())
+    tensors["simhash_matrix"] = ref.simhash_matrix.numpy()
+    weights.save_ot(str(tmp_path / "delete-me.ot"), tensors)
+    image.tofile(str(tmp_path / "bitvec.bin"))
+    b = capi.BatchedMCTS(n, hk, count, arena_slots=4096)
+    network.load_model(b, str(tmp_path / "delete-me.ot"))
+    assert np.array_equal(network.evaluate(b, states, actions)[2], after)
+    for h in (a, b):
+        h.close()
+
+
 @pytest.mark.parametrize("n,hk,count", [(4, 4, 701), (6, 4, 333), (5, 4, 97)])
 def test_chunked_fused_launch_equals_one_chunk_and_per_layer_launches(n, hk, count):
     """The network body runs as one persistent launch whose positions are cut into chunks that walk through all
