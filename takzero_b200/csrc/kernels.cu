@@ -204,55 +204,67 @@ __device__ __forceinline__ bool warp_softmax_inplace(float* buf, int n, int lane
     return !__any_sync(FULL_MASK, bad);
 }
 
-// softmax + backward_network_eval (mcts.rs:171-225) of evaluation-queue entry q of game g whose selection
-// path is traj[0..len)
-__device__ __forceinline__ void warp_expand(const TzDev& d, int g, int q, const uint32_t* traj, int len, float* p,
-                                            int lane) {
+// backward_network_eval (mcts.rs:171-225) of evaluation-queue entry q of game g, in three parts so that the single-tree
+// path can run the parts of different leaves at the same time (k_tree_backward); the batched search runs them back to
+// back (warp_expand).
+struct LeafOutputs {
+    float value, variance;
+    bool priors_ok;
+};
+
+// part 1, private to the entry: the heads' last step, softmax over the legal logits into `p`, outputs made finite
+__device__ __forceinline__ LeafOutputs expand_outputs(const TzDev& d, int q, float* p, int lane) {
     const int n = d.n_actions[q];
-    const GameTree t = game_tree(d.arena, g);
     const float* lg = d.logits + (size_t)q * d.M;
-    const uint16_t* act = d.actions + (size_t)q * d.M;
     for (int i = lane; i < n; i += 32) p[i] = lg[i];
     __syncwarp();
-    float value, variance;
+    LeafOutputs o;
     if (d.nn_head_feat != nullptr)  // device network: the heads' last step happens here (encode.cuh)
-        enc::warp_heads(d.nn_head_feat, d.nn_head_misc, d.nn_novelty_set, d.nn_novelty_idx, d.nn_rnd_unc, q, d.nn, lane, &value,
-                        &variance);
+        enc::warp_heads(d.nn_head_feat, d.nn_head_misc, d.nn_novelty_set, d.nn_novelty_idx, d.nn_rnd_unc, q, d.nn, lane, &o.value,
+                        &o.variance);
     else {
-        value = d.value[q];
-        variance = d.variance[q];
+        o.value = d.value[q];
+        o.variance = d.variance[q];
     }
     // NaN / infinite network outputs: the reference panics (net6_simhash.rs:304, NotNan).  Here the error bit is
     // raised and the outputs are replaced by finite ones (uniform priors, zero logits / value / variance), so that no
     // NaN ever enters a tree: comparisons against NaN would derail the argmax / ranking code that indexes the arena.
-    bool priors_ok = warp_softmax_inplace(p, n, lane);
+    o.priors_ok = warp_softmax_inplace(p, n, lane);
     {
         bool finite = true;
         for (int i = lane; i < n; i += 32) finite = finite && p[i] >= 0.0f && p[i] <= 1.0f;  // false for NaN
-        priors_ok = priors_ok && __all_sync(FULL_MASK, finite);
+        o.priors_ok = o.priors_ok && __all_sync(FULL_MASK, finite);
     }
-    const bool value_ok = fabsf(value) <= 3.0e38f && variance >= 0.0f && variance <= 3.0e38f;  // false for NaN
-    if (!priors_ok || !value_ok) {
+    const bool value_ok = fabsf(o.value) <= 3.0e38f && o.variance >= 0.0f && o.variance <= 3.0e38f;  // false for NaN
+    if (!o.priors_ok || !value_ok) {
         flag_error(d, TZ_ERR_NAN, lane);
-        if (!priors_ok) {
+        if (!o.priors_ok) {
             const float uniform = fdiv(1.0f, (float)(n > 0 ? n : 1));
             for (int i = lane; i < n; i += 32) p[i] = uniform;
             __syncwarp();
         }
         if (!value_ok) {
-            value = 0.0f;
-            variance = 0.0f;
+            o.value = 0.0f;
+            o.variance = 0.0f;
         }
     }
+    return o;
+}
 
-    // leaf: running mean / std (mcts.rs:190-197); the leaf's evaluation is a Value here
-    const uint32_t leaf = traj[len - 1];
+// part 2, the leaf (mcts.rs:190-217, node/mod.rs:66-79): running mean / std of the leaf, its children created in the
+// arena.  False when the arena is full (reported; nothing is backed up then).
+__device__ __forceinline__ bool expand_leaf(const TzDev& d, int g, int q, uint32_t leaf, const float* p,
+                                            const LeafOutputs& o, int lane) {
+    const int n = d.n_actions[q];
+    const GameTree t = game_tree(d.arena, g);
+    const float* lg = d.logits + (size_t)q * d.M;
+    const uint16_t* act = d.actions + (size_t)q * d.M;
+    // the leaf's evaluation is a Value here
     const float nv = (float)t.visits[leaf];
     float m = __uint_as_float(t.eval[leaf]);
     float sd = t.std_dev[leaf];
-    m = fadd(m, fdiv(fadd(fneg(m), value), nv));
-    sd = fadd(sd, fdiv(fadd(fneg(sd), fsqrt(variance)), nv));
-    // children (mcts.rs:199-217, node/mod.rs:66-79)
+    m = fadd(m, fdiv(fadd(fneg(m), o.value), nv));
+    sd = fadd(sd, fdiv(fadd(fneg(sd), fsqrt(o.variance)), nv));
     uint32_t start = 0;
     if (lane == 0) {
         start = d.arena.next_slot[g];
@@ -266,7 +278,7 @@ __device__ __forceinline__ void warp_expand(const TzDev& d, int g, int q, const 
     start = __shfl_sync(FULL_MASK, start, 0);
     if (start == 0) {
         flag_error(d, TZ_ERR_ARENA_FULL, lane);
-        return;
+        return false;
     }
     const uint32_t child_eval = __float_as_uint(fneg(m));
     for (int i = lane; i < n; i += 32) {
@@ -276,7 +288,7 @@ __device__ __forceinline__ void warp_expand(const TzDev& d, int g, int q, const 
         t.visits[c] = 0;
         t.prob[c] = p[i];
         t.std_dev[c] = sd;
-        t.logit[c] = priors_ok ? lg[i] : 0.0f;
+        t.logit[c] = o.priors_ok ? lg[i] : 0.0f;
         t.first[c] = 0;
     }
     if (lane == 0) {
@@ -286,10 +298,22 @@ __device__ __forceinline__ void warp_expand(const TzDev& d, int g, int q, const 
         t.first[leaf] = start;
     }
     __syncwarp();
+    return true;
+}
+
+// part 3 starts from this: what the leaf hands to its parent (mcts.rs:219-224)
+__device__ __forceinline__ Propagated expand_propagated(const LeafOutputs& o) {
     Propagated pr;
-    pr.eval = ev_value(fmul(value, 0.997f));
-    pr.variance = fmul(fmul(variance, 0.997f), 0.997f);
-    warp_backup(t, traj, len, pr, lane);
+    pr.eval = ev_value(fmul(o.value, 0.997f));
+    pr.variance = fmul(fmul(o.variance, 0.997f), 0.997f);
+    return pr;
+}
+
+__device__ __forceinline__ void warp_expand(const TzDev& d, int g, int q, const uint32_t* traj, int len, float* p,
+                                            int lane) {
+    const LeafOutputs o = expand_outputs(d, q, p, lane);
+    if (!expand_leaf(d, g, q, traj[len - 1], p, o, lane)) return;
+    warp_backup(game_tree(d.arena, g), traj, len, expand_propagated(o), lane);
 }
 
 __global__ void __launch_bounds__(32 * WPB) k_expand(TzDev d) {
@@ -303,52 +327,393 @@ __global__ void __launch_bounds__(32 * WPB) k_expand(TzDev d) {
 
 // ---- single tree: Node::simulate_simple / simulate_batch (mcts.rs:235-328) on game 0 -------------------------
 
-// Up to `max_forwards` sequential descents of ONE tree by one warp: the visit increments of earlier
-// descents steer later ones (the reference's only "virtual loss"); known results are backed up at once,
-// leaves that need the network fill queue slots 0..batch_size-1 in order, their paths go to traj[q].
-__global__ void __launch_bounds__(32) k_tree_forward(TzDev d, float beta, int batch_size, int max_forwards) {
-    __shared__ TzState s_state;
-    __shared__ uint16_t s_moves[TZ_MAX_MOVES];
-    const int lane = threadIdx.x & 31;
+// Up to `max_forwards` descents of ONE tree with the reference's SEQUENTIAL semantics: the visit increments of earlier
+// descents steer later ones (its only "virtual loss"), known results are backed up at once, leaves that need the
+// network fill queue slots 0..batch_size-1 in order, their paths go to traj[q].
+//
+// One warp doing them one after the other is bound by the latency of its own dependent loads (~12 us per descent), so
+// TREE_WARPS warps of one CTA run consecutive descents as a wavefront, speculatively, and commit them in order:
+//   * a descent is a chain inc_0, look_0, inc_1, look_1, ...: inc_k counts its visit of the path's node at level k,
+//     look_k reads that node and its children (level k+1) and picks one.  Descent i runs inc_0 after descent i-1's
+//     inc_0 and look_k after descent i-1's inc_(k+1) (or its end): then look_k sees the level-(k+1) increments of
+//     every earlier descent and of no later one (descent i+1's inc_(k+1) follows ITS look_k, which follows this
+//     descent's inc_(k+1)), and the count inc_k returns -- used by look_k instead of a second read -- holds exactly the
+//     earlier descents' visits.  Without known results this is the sequential order of every read and write, with
+//     consecutive descents one look apart.
+//   * a descent is final only when it COMMITS, in index order.  A leaf that needs the network commits by taking the
+//     next queue slot (its move list was generated while it waited).  A known result commits by (1) voiding every
+//     later descent in flight -- they saw evaluations its backup is about to change -- which take back their visit
+//     increments (and a terminal evaluation they may have stored on the way), (2) backing up, (3) letting them start
+//     again.  The batch being full, the forward budget being used up, or a committed error void the rest for good.
+// Control words in shared memory (volatile):
+//   fprog[w]  descent that warp w runs: index * 1024 + increments done (1000 = over)
+//   commit    index of the next descent to commit          filled   queue entries taken
+//   gen       bumped by every voiding                      resume   last generation whose voiding is complete
+//   acks      warps that have taken back their descent since the last voiding          stop   no more descents
+#define TREE_WARPS 8
+#define TREE_SPIN_LIMIT (1 << 24)
+
+struct TreeCtl {
+    volatile int* fprog;
+    volatile int* commit;
+    volatile int* filled;
+    volatile int* gen;
+    volatile int* resume;
+    volatile int* acks;
+    volatile int* stop;
+};
+
+enum { TREE_NEEDS = 0, TREE_KNOWN = 1, TREE_ERROR = -1, TREE_VOID = -2 };
+
+// lane 0 spins until `cond` holds; false when this descent has been voided meanwhile (or the wait gave up)
+template <typename Cond>
+__device__ __forceinline__ bool tree_spin(const TzDev& d, const TreeCtl& c, int my_gen, int lane, Cond cond) {
+    int ok = 1;
+    if (lane == 0) {
+        int spins = 0;
+        while (true) {
+            if (*c.gen != my_gen) {
+                ok = 0;
+                break;
+            }
+            if (cond()) break;
+            if (++spins > TREE_SPIN_LIMIT) {  // never seen; ends the whole launch instead of hanging the GPU
+                atomicOr(d.status, TZ_ERR_NETWORK_STALL);
+                *c.stop = 1;
+                ok = 0;
+                break;
+            }
+        }
+    }
+    ok = __shfl_sync(FULL_MASK, ok, 0);
+    __threadfence_block();
+    return ok != 0;
+}
+
+__device__ __forceinline__ void tree_fpublish(const TreeCtl& c, int it, int steps, int lane) {
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) c.fprog[it % TREE_WARPS] = it * 1024 + steps;
+}
+
+// Node::forward (mcts.rs:107-138) as warp_forward does it, as a chain inc_0, look_0, inc_1, look_1, ...: inc_k counts
+// the visit of the path's node at level k (and keeps the new count for look_k's exploration term), look_k reads that
+// node and its children and picks the next one.  `undo_*`: the terminal evaluation this descent stored on an
+// uninitialised node, to be taken back if the descent is voided.
+__device__ __forceinline__ int tree_descend(const TzDev& d, const GameTree& t, const TreeCtl& c, TzState* st, uint32_t* traj,
+                                            int it, int my_gen, float beta, int lane, int* out_len, Ev* known_ev,
+                                            uint32_t* err_bit, uint32_t* undo_slot, uint32_t* undo_words) {
+    int len = 0;
+    uint32_t slot = 0;
+    *undo_slot = 0xffffffffu;
+    *out_len = 0;
+    volatile int* pred = c.fprog + (it > 0 ? (it - 1) % TREE_WARPS : 0);
+    while (true) {
+        // inc_len: after the previous descent's own inc_len (for level 0; deeper ones follow from the look rule)
+        if (len >= TZ_MAX_DEPTH) {
+            *err_bit = TZ_ERR_DEPTH;
+            return TREE_ERROR;
+        }
+        if (it > 0 && len == 0) {
+            const int want = (it - 1) * 1024 + 1;
+            if (!tree_spin(d, c, my_gen, lane, [=]() { return *pred >= want; })) return TREE_VOID;
+        }
+        uint32_t pv = 0;
+        if (lane == 0) {
+            // atomic: a voided descent may be taking its increment of this very node (the root, say) back right now
+            pv = atomicAdd(&t.visits[slot], 1u) + 1u;
+            traj[len] = slot;
+        }
+        len++;
+        *out_len = len;
+        pv = __shfl_sync(FULL_MASK, pv, 0);
+        tree_fpublish(c, it, len, lane);
+        // look_(len-1): after the previous descent's inc_len, or its end
+        if (it > 0) {
+            const int want = (it - 1) * 1024 + len + 1;
+            if (!tree_spin(d, c, my_gen, lane, [=]() { return *pred >= want; })) return TREE_VOID;
+        }
+        const uint32_t meta = t.meta[slot];
+        const uint32_t tag = tz_meta_tag(meta);
+        if (tag != TZ_E_VALUE && t.eval[slot] == 0) {  // is_terminal
+            *known_ev = ev_make(tag, 0);
+            return TREE_KNOWN;
+        }
+        if (tz_meta_nchild(meta) == 0 && tag == TZ_E_VALUE) {  // needs_initialization
+            const int term = warp_terminal(st, d.n, d.half_komi, d.rev_limit, lane);
+            if (term != TZ_T_NONE) {
+                *known_ev = ev_make(term == TZ_T_WIN ? TZ_E_WIN : (term == TZ_T_LOSS ? TZ_E_LOSS : TZ_E_DRAW), 0);
+                undo_words[0] = t.eval[slot];
+                undo_words[1] = meta;
+                undo_words[2] = __float_as_uint(t.std_dev[slot]);
+                *undo_slot = slot;
+                if (lane == 0) {
+                    node_set_eval(t, slot, *known_ev);
+                    t.std_dev[slot] = 0.0f;
+                }
+                __syncwarp();
+                return TREE_KNOWN;
+            }
+            return TREE_NEEDS;
+        }
+        bool nan_seen;
+        const int idx = warp_select_puct(t, slot, beta, d.ln_table, lane, &nan_seen, (long long)pv);
+        if (nan_seen) flag_error(d, TZ_ERR_NAN, lane);
+        if (idx < 0) {
+            *err_bit = TZ_ERR_NO_CHILD;
+            return TREE_ERROR;
+        }
+        slot = t.first[slot] + (uint32_t)idx;
+        if (!warp_apply(st, d.n, (uint16_t)tz_meta_move(t.meta[slot]), lane)) {
+            *err_bit = TZ_ERR_BAD_MOVE;
+            return TREE_ERROR;
+        }
+    }
+}
+
+// a voided descent takes back what it did to the tree (other voided descents do the same at the same time, and they
+// all went through the root: atomics)
+__device__ __forceinline__ void tree_take_back(const GameTree& t, const uint32_t* traj, int len, uint32_t undo_slot,
+                                               const uint32_t* undo_words, int lane) {
+    for (int i = lane; i < len; i += 32) atomicSub(&t.visits[traj[i]], 1u);
+    if (undo_slot != 0xffffffffu && lane == 0) {
+        t.eval[undo_slot] = undo_words[0];
+        t.meta[undo_slot] = undo_words[1];
+        t.std_dev[undo_slot] = __uint_as_float(undo_words[2]);
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(32 * TREE_WARPS) k_tree_forward(TzDev d, float beta, int batch_size, int max_forwards) {
+    __shared__ TzState s_state[TREE_WARPS];
+    __shared__ uint16_t s_moves[TREE_WARPS][TZ_MAX_MOVES];
+    __shared__ uint32_t s_ranges[TREE_WARPS][TZ_MAX_SQ];
+    __shared__ uint32_t s_traj[TREE_WARPS][TZ_MAX_DEPTH];
+    __shared__ int s_fprog[TREE_WARPS];
+    __shared__ int s_ctl[6];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    TreeCtl c;
+    c.fprog = s_fprog;
+    c.commit = s_ctl + 0;
+    c.filled = s_ctl + 1;
+    c.gen = s_ctl + 2;
+    c.resume = s_ctl + 3;
+    c.acks = s_ctl + 4;
+    c.stop = s_ctl + 5;
+    if (threadIdx.x < 6) s_ctl[threadIdx.x] = 0;
+    if (lane == 0) s_fprog[warp] = -1;
+    __syncthreads();
     const GameTree t = game_tree(d.arena, 0);
     unsigned long long* ctr = d.counters;
-    int filled = 0;
-    for (int it = 0; it < max_forwards && filled < batch_size; it++) {
-        __syncwarp();
-        warp_load_state(&s_state, &d.env[0], lane);
-        uint32_t* traj = d.traj + (size_t)filled * TZ_MAX_DEPTH;
-        if (lane == 0) ctr[0] += 1;
+    TzState* st = &s_state[warp];
+    uint32_t* traj = s_traj[warp];
+    const bool any_work = max_forwards > 0 && batch_size > 0;
+    if (!any_work) {
+        if (threadIdx.x == 0) *d.nn_count = 0;
+        return;
+    }
+
+    int it = warp;
+    int acked_gen = 0;  // lane 0: the last voiding this warp has acknowledged (every warp acknowledges every one)
+    while (true) {
+        // (re)start: not while a voiding is under way; a warp with nothing left keeps answering until the end
+        int my_gen = 0, stopped = 0;
+        if (lane == 0) {
+            int spins = 0;
+            while (true) {
+                stopped = *c.stop;
+                my_gen = *c.gen;
+                if (stopped) break;
+                if (*c.resume != my_gen) {  // a voiding is under way and this warp holds nothing to take back
+                    if (acked_gen != my_gen) {
+                        acked_gen = my_gen;
+                        atomicAdd((int*)c.acks, 1);
+                    }
+                } else if (it < max_forwards) {
+                    break;
+                } else {
+                    __nanosleep(200);
+                }
+                if (++spins > TREE_SPIN_LIMIT) {
+                    atomicOr(d.status, TZ_ERR_NETWORK_STALL);
+                    *c.stop = 1;
+                    stopped = 1;
+                    break;
+                }
+            }
+        }
+        my_gen = __shfl_sync(FULL_MASK, my_gen, 0);
+        stopped = __shfl_sync(FULL_MASK, stopped, 0);
+        __threadfence_block();
+        if (stopped) return;
+        tree_fpublish(c, it, 0, lane);
+        warp_load_state(st, &d.env[0], lane);
         int len = 0;
         Ev known_ev = ev_value(0.0f);
-        const int res = warp_forward(d, t, &s_state, traj, 0, beta, lane, &len, &known_ev);
-        if (res < 0) break;
-        if (res == 1) {
-            if (lane == 0) ctr[2] += 1;
+        uint32_t err_bit = 0, undo_slot = 0xffffffffu, undo_words[3] = {0, 0, 0};
+        int res = tree_descend(d, t, c, st, traj, it, my_gen, beta, lane, &len, &known_ev, &err_bit, &undo_slot, undo_words);
+        int cnt = 0;
+        if (res != TREE_VOID) {
+            tree_fpublish(c, it, 1000, lane);
+            if (res == TREE_NEEDS) {
+                // Forward::NeedsNetwork: the move list and what the input encoding needs, while waiting for the turn
+                cnt = warp_movegen(st, d.n, s_moves[warp], lane, s_ranges[warp]);
+                if (cnt >= 0 && cnt <= d.M) {
+                    const TzBoards b = warp_boards(st, d.nn, lane);
+                    if (lane == 0)
+                        enc::store_position_scalars(st, __popcll(b.flat[0]) - __popcll(b.flat[1]), d.n, d.half_komi, d.nn_f16);
+                    __syncwarp();
+                }
+            }
+            volatile int* commit = c.commit;
+            if (!tree_spin(d, c, my_gen, lane, [=]() { return *commit == it; })) res = TREE_VOID;
+        }
+        if (res == TREE_VOID) {
+            tree_take_back(t, traj, len, undo_slot, undo_words, lane);
+            tree_fpublish(c, it, 0, lane);
+            if (lane == 0 && acked_gen != my_gen + 1) {
+                acked_gen = my_gen + 1;  // one voiding at a time: the next one cannot start before this one is complete
+                atomicAdd((int*)c.acks, 1);
+            }
+            __syncwarp();
+            continue;  // the same descent again, once the voiding is complete (or never, when stopped)
+        }
+
+        // ---- commit: this descent is the oldest one in flight, everything before it is final ----
+        bool stop = false;
+        int filled = *c.filled;
+        const int q = filled;
+        if (lane == 0) ctr[0] += 1;
+        if (res == TREE_ERROR) {
+            flag_error(d, err_bit, lane);
+            stop = true;
+        } else if (res == TREE_KNOWN) {
+            // void the later descents, wait until they have taken their increments back, then back up
+            if (lane == 0) {
+                *c.acks = 0;
+                __threadfence_block();
+                *c.gen = my_gen + 1;
+                int spins = 0;
+                while (*c.acks < TREE_WARPS - 1 && ++spins <= TREE_SPIN_LIMIT) {
+                }
+                if (spins > TREE_SPIN_LIMIT) atomicOr(d.status, TZ_ERR_NETWORK_STALL);
+                ctr[2] += 1;
+            }
+            __syncwarp();
+            __threadfence_block();
             Propagated p;
             p.eval = known_ev;
             p.variance = 0.0f;
             warp_backup(t, traj, len, p, lane);
-            continue;
+        } else {
+            if (lane == 0) ctr[1] += 1;
+            if (cnt < 0 || cnt > d.M) {
+                flag_error(d, TZ_ERR_TOO_MANY_MOVES, lane);
+                stop = true;
+            } else {
+                filled = q + 1;
+            }
         }
-        if (lane == 0) {
-            d.traj_len[filled] = len;
-            ctr[1] += 1;
-        }
-        if (!warp_enqueue(d, 0, filled, &s_state, s_moves, lane)) break;
-        filled++;
+        stop = stop || filled >= batch_size || it + 1 >= max_forwards;
+        __threadfence_block();
         __syncwarp();
+        if (lane == 0) {
+            *c.filled = filled;
+            if (stop) {
+                *d.nn_count = filled;
+                *c.stop = 1;
+                __threadfence_block();
+                if (res != TREE_KNOWN) *c.gen = my_gen + 1;  // whoever is still descending gives up and takes it back
+            } else {
+                *c.commit = it + 1;
+                __threadfence_block();
+                if (res == TREE_KNOWN) *c.resume = my_gen + 1;
+            }
+        }
+        __syncwarp();
+        if (res == TREE_NEEDS) {
+            // queue entry q is this descent's alone from here on: filling it keeps nobody waiting
+            const bool too_many = cnt < 0 || cnt > d.M;  // reported, never truncated (warp_enqueue): an entry without moves
+            if (lane == 0) {
+                d.nn_queue[q] = 0;
+                d.n_actions[q] = too_many ? 0 : cnt;
+                d.traj_len[q] = len;
+            }
+            for (int sq = lane; sq < TZ_MAX_SQ; sq += 32)
+                d.sq_ranges[(size_t)q * TZ_MAX_SQ + sq] = too_many ? 0u : s_ranges[warp][sq];
+            warp_store_state(&d.leaf_state[q], st, lane);
+            if (!too_many) {
+                uint16_t* out = d.actions + (size_t)q * d.M;
+                for (int i = lane; i < cnt; i += 32) out[i] = s_moves[warp][i];
+                uint32_t* tq = d.traj + (size_t)q * TZ_MAX_DEPTH;
+                for (int i = lane; i < len; i += 32) tq[i] = traj[i];
+            }
+            __syncwarp();
+        }
+        if (stop) return;
+        it += TREE_WARPS;
     }
-    if (lane == 0) *d.nn_count = filled;
 }
 
-// backward_network_eval of the queued leaves, in queue order (the order matters: they share one tree)
-__global__ void __launch_bounds__(32) k_tree_backward(TzDev d) {
-    __shared__ float s_p[TZ_MAX_MOVES];
-    const int lane = threadIdx.x & 31;
+// backward_network_eval of the queued leaves IN QUEUE ORDER (they share one tree: every running mean and every solver
+// scan sees what the earlier leaves of the batch left), by TREE_WARPS warps of one CTA as a wavefront:
+//   * the heads, the softmax and the sanitising of an entry touch nothing shared and run at once for TREE_WARPS entries;
+//   * entry q works on depth e of its path (leaf step at e = len-1, then the parents up to the root at 0) only after
+//     entry q-1 has finished depth e-1 -- by induction so have all earlier entries.  A step at depth e reads and writes
+//     the node at depth e and reads its children at depth e+1; the earlier entries are past e-1, so they will not touch
+//     either level again, and what they wrote there is visible (fence + progress word in shared memory); later entries
+//     stay above e+1 until this one has finished e.  The arena allocations happen in the leaf steps, hence in order.
+// progress word of the warp that owns entry q: q * 1024 + (1000 - last finished depth), monotonic over its entries.
+__device__ __forceinline__ int tree_progress(int q, int finished_depth) { return q * 1024 + (1000 - finished_depth); }
+
+// wait until entry `q - 1` has finished depth `need` (-1 = all of it); false when the wait gave up
+__device__ __forceinline__ bool tree_wait_pred(const TzDev& d, volatile int* prog, int q, int need, int lane) {
+    bool ok = true;
+    if (q > 0) {
+        if (lane == 0) {
+            const int want = tree_progress(q - 1, need);
+            int spins = 0;
+            while (prog[(q - 1) % TREE_WARPS] < want)
+                if (++spins > TREE_SPIN_LIMIT) {
+                    ok = false;
+                    break;
+                }
+        }
+        ok = __shfl_sync(FULL_MASK, ok ? 1 : 0, 0) != 0;
+        if (!ok) flag_error(d, TZ_ERR_NETWORK_STALL, lane);
+    }
+    __threadfence_block();
+    return ok;
+}
+
+__device__ __forceinline__ void tree_publish(volatile int* prog, int q, int finished_depth, int lane) {
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) prog[q % TREE_WARPS] = tree_progress(q, finished_depth);
+}
+
+__global__ void __launch_bounds__(32 * TREE_WARPS) k_tree_backward(TzDev d) {
+    __shared__ float s_p[TREE_WARPS][TZ_MAX_MOVES];
+    __shared__ int s_prog[TREE_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int count = *d.nn_count;
-    for (int q = 0; q < count; q++) {
-        warp_expand(d, 0, q, d.traj + (size_t)q * TZ_MAX_DEPTH, d.traj_len[q], s_p, lane);
-        __syncwarp();
+    volatile int* prog = s_prog;
+    if (lane == 0) s_prog[warp] = -1;
+    __syncthreads();
+    const GameTree t = game_tree(d.arena, 0);
+    for (int q = warp; q < count; q += TREE_WARPS) {
+        const uint32_t* traj = d.traj + (size_t)q * TZ_MAX_DEPTH;
+        const int len = d.traj_len[q];
+        const LeafOutputs o = expand_outputs(d, q, s_p[warp], lane);
+        bool ok = tree_wait_pred(d, prog, q, len - 2, lane);
+        ok = ok && expand_leaf(d, 0, q, traj[len - 1], s_p[warp], o, lane);
+        Propagated pr = expand_propagated(o);
+        for (int e = len - 2; ok && e >= 0; e--) {
+            tree_publish(prog, q, e + 1, lane);
+            ok = tree_wait_pred(d, prog, q, e - 1, lane);
+            if (ok) pr = warp_propagate(t, traj[e], pr, lane);
+        }
+        tree_publish(prog, q, -1, lane);  // also after an error: nobody waits for ever
     }
 }
 
@@ -1155,9 +1520,9 @@ void launch_step(const TzDev& d, const uint16_t* moves, cudaStream_t st, int onl
     k_step<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, moves, only_game);
 }
 void launch_tree_forward(const TzDev& d, float beta, int batch_size, int max_forwards, cudaStream_t st) {
-    k_tree_forward<<<1, 32, 0, st>>>(d, beta, batch_size, max_forwards);
+    k_tree_forward<<<1, 32 * TREE_WARPS, 0, st>>>(d, beta, batch_size, max_forwards);
 }
-void launch_tree_backward(const TzDev& d, cudaStream_t st) { k_tree_backward<<<1, 32, 0, st>>>(d); }
+void launch_tree_backward(const TzDev& d, cudaStream_t st) { k_tree_backward<<<1, 32 * TREE_WARPS, 0, st>>>(d); }
 void launch_set_root_priors(const TzDev& d, int stride, const float* prob, const float* logit, cudaStream_t st) {
     k_set_root_priors<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, stride, prob, logit);
 }

@@ -236,13 +236,16 @@ __device__ __forceinline__ float exploration_rate(const float* ln_table, uint32_
 }
 
 // returns the selected child index, or -1 when no child is eligible / a key is NaN
+// (`known_visits` >= 0: the caller already holds the node's visit count -- the single-tree wavefront, where a later
+// descent may be incrementing it at this very moment)
 __device__ __forceinline__ int warp_select_puct(const GameTree& t, uint32_t slot, float beta,
-                                                const float* ln_table, int lane, bool* nan_seen) {
+                                                const float* ln_table, int lane, bool* nan_seen,
+                                                long long known_visits = -1) {
     const uint32_t meta = t.meta[slot];
     const int nchild = (int)tz_meta_nchild(meta);
     const uint32_t first = t.first[slot];
     const bool parent_is_loss = tz_meta_tag(meta) == TZ_E_LOSS;
-    const uint32_t pv = t.visits[slot];
+    const uint32_t pv = known_visits >= 0 ? (uint32_t)known_visits : t.visits[slot];
     const float parent_visits = (float)pv;
     // exploration_rate(Np) * P * sqrt(Np) / (1 + n): the first and third factors are uniform
     const float rate = exploration_rate(ln_table, pv);

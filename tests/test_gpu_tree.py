@@ -86,3 +86,39 @@ def test_simulate_simple_matches_oracle():
             assert_tree_equal(m, tree, f"sim {i}")
     assert_tree_equal(m, tree, "final")
     m.close()
+
+
+TINUE_EASY = ["a3", "c1", "c2", "c3", "b3", "c3-"]  # mcts.rs:345-376
+TINUE_DEEPER = ["a3", "a1", "b1", "c1"]  # mcts.rs:378-411
+
+
+@pytest.mark.parametrize("batch,agent,moves", [(1, "synthetic", TINUE_EASY), (3, "simple", TINUE_EASY),
+                                               (8, "simple", TINUE_EASY), (40, "simple", TINUE_EASY),
+                                               (16, "dummy", TINUE_EASY), (24, "simple", TINUE_DEEPER),
+                                               (128, "simple", TINUE_DEEPER)])
+def test_simulate_batch_with_known_results_in_flight(batch, agent, moves):
+    """The 3x3 position of the reference's `find_tinue_easy` (mcts.rs:345-376), beta = 1, with the reference's test
+    agents: within a few batches most descents end in known results.  Each of them is backed up at once and changes
+    what every later descent of the same batch sees, the forward budget of 4 x batch gets used up before the batch is
+    full, and the root ends up solved -- on the device the descents of a batch run as a speculative wavefront of
+    several warps, so this is the case where later descents have to be taken back and started again.  Bit-exact against
+    the sequential oracle after every batch."""
+    env = O.from_ptn_moves(3, 0, moves)
+    m = capi.BatchedMCTS(3, 0, batch, arena_slots=1 << 20)
+    m.set_positions(games_to_states([env] * batch))
+    if agent != "synthetic":
+        m.set_agent(capi.AGENT_HOST, host_agent_from_oracle(agent, 3, 0))
+    tree = O.Tree()
+    for it in range(120):
+        m.tree_simulate_batch(1.0, batch)
+        tree.simulate_batch(agent, env, 1.0, batch)
+        assert_tree_equal(m, tree, f"batch {it}")
+    assert m.status() == 0
+    c = m.counters()
+    assert c.known > 0 and c.known + c.evaluations == c.simulations
+    if agent == "simple" and batch >= 8 and moves is TINUE_EASY:
+        assert m.root_stats()[0]["eval_tag"] != 0, "the root of this position is solved well within 120 batches"
+        assert c.known > c.evaluations, "most descents ended in known results"
+    pv = list(m.tree_principal_variation())
+    assert pv == oracle_pv(tree)
+    m.close()
