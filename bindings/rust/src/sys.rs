@@ -191,6 +191,7 @@ extern "C" {
     pub fn tz_debug_activations(h: *mut tz_handle, which: c_int, count: c_int, out: *mut f32) -> c_int;
     pub fn tz_debug_schedule(count: c_int, count_max: c_int, board_n: c_int, chunk_min_tiles: c_int, layers: c_int, out: *mut c_longlong, out_items: *mut c_int, cap: c_int) -> c_int;
     pub fn tz_debug_network_mode(h: *mut tz_handle, per_layer_launches: c_int, chunk_min_tiles: c_int, drop_progress: c_int) -> c_int;
+    pub fn tz_debug_tree_warps(h: *mut tz_handle, warps: c_int) -> c_int;
     pub fn tz_debug_weight_set(h: *mut tz_handle, out: *mut u8, cap: usize, out_size: *mut usize) -> c_int;
     pub fn tz_debug_expf(h: *mut tz_handle, in_: *const f32, count: c_int, out: *mut f32) -> c_int;
     pub fn tz_debug_time_tower(h: *mut tz_handle, count: c_int, reps: c_int, ms_per_conv: *mut f64) -> c_int;

@@ -360,6 +360,10 @@ TZ_API int tz_debug_schedule(int count, int count_max, int board_n, int chunk_mi
  * per chunk (-1 = default 150, 0 = one chunk); drop_progress = 1: CTA pair 0 withholds its tiles so that the watchdog
  * (TZ_STATUS_NETWORK_STALL) can be tested.  The defaults (0, -1, 0) are the product. */
 TZ_API int tz_debug_network_mode(tz_handle* h, int per_layer_launches, int chunk_min_tiles, int drop_progress);
+/* Test hook of the single-tree path: the descents and the backups of a batch run as in-order wavefronts of up to 8
+ * warps (kernels.cu, k_tree_forward / k_tree_backward); fewer warps change the interleaving, never the result.
+ * 0 = default (8). */
+TZ_API int tz_debug_tree_warps(tz_handle* h, int warps);
 /* parity hook: the active weight set (folded, arranged 16-bit weights + biases; layout in nn.cu `SetLayout`);
  * out = NULL: only the size */
 TZ_API int tz_debug_weight_set(tz_handle* h, uint8_t* out, size_t cap, size_t* out_size);

@@ -163,6 +163,7 @@ def lib():
         "tz_set_root_priors": ([vp, i32, vp, vp], i32),
         "tz_tree_simulate_simple": ([vp, f32], i32),
         "tz_tree_simulate_batch": ([vp, f32, i32], i32),
+        "tz_debug_tree_warps": ([vp, i32], i32),
         "tz_tree_descend": ([vp, C.c_uint16], i32),
         "tz_tree_principal_variation": ([vp, vp, i32], i32),
         "tz_selfplay_move": ([vp, P(SelfplayParams)], i32),
@@ -438,6 +439,10 @@ class BatchedMCTS:
 
     def tree_simulate_batch(self, beta: float, batch_size: int) -> None:
         _check(lib().tz_tree_simulate_batch(self._h, beta, batch_size))
+
+    def debug_tree_warps(self, warps: int) -> None:
+        """Test hook: warps of the single-tree wavefront kernels (0 = default 8); changes the interleaving only."""
+        _check(lib().tz_debug_tree_warps(self._h, int(warps)))
 
     def tree_descend(self, move: int) -> None:
         _check(lib().tz_tree_descend(self._h, int(move)))

@@ -936,6 +936,13 @@ extern "C" TZ_API int tz_debug_network_mode(tz_handle* h, int per_layer_launches
     return TZ_OK;
 }
 
+extern "C" TZ_API int tz_debug_tree_warps(tz_handle* h, int warps) {
+    if (!h) return fail(TZ_EINVAL, "null handle");
+    if (warps < 0 || warps > 8) return fail(TZ_EINVAL, "warps must be 0 (default) or 1..8");
+    h->dbg_tree_warps = warps;
+    return TZ_OK;
+}
+
 extern "C" TZ_API int tz_debug_weight_set(tz_handle* h, uint8_t* out, size_t cap, size_t* out_size) {
     CHECK_H(h);
     if (!out_size) return fail(TZ_EINVAL, "null out_size");
@@ -1300,10 +1307,10 @@ static int tree_simulate(tz_handle* h, float beta, int batch_size, int max_forwa
     if (batch_size <= 0 || batch_size > d.Q)
         return fail(TZ_EINVAL, "batch_size must be 1..max(n_games, tree_batch) (%d)", d.Q);
     h->prof_active = false;
-    launch_tree_forward(d, beta, batch_size, max_forwards, h->stream);
+    launch_tree_forward(d, beta, batch_size, max_forwards, h->dbg_tree_warps, h->stream);
     int rc = run_agent(h);
     if (rc) return rc;
-    launch_tree_backward(d, h->stream);
+    launch_tree_backward(d, h->dbg_tree_warps, h->stream);
     h->launches += 2;
     return finish(h);
 }

@@ -334,11 +334,11 @@ __global__ void __launch_bounds__(32 * WPB) k_expand(TzDev d) {
 // One warp doing them one after the other is bound by the latency of its own dependent loads (~12 us per descent), so
 // TREE_WARPS warps of one CTA run consecutive descents as a wavefront, speculatively, and commit them in order:
 //   * a descent is a chain inc_0, look_0, inc_1, look_1, ...: inc_k counts its visit of the path's node at level k,
-//     look_k reads that node and its children (level k+1) and picks one.  Descent i runs inc_0 after descent i-1's
-//     inc_0 and look_k after descent i-1's inc_(k+1) (or its end): then look_k sees the level-(k+1) increments of
-//     every earlier descent and of no later one (descent i+1's inc_(k+1) follows ITS look_k, which follows this
-//     descent's inc_(k+1)), and the count inc_k returns -- used by look_k instead of a second read -- holds exactly the
-//     earlier descents' visits.  Without known results this is the sequential order of every read and write, with
+//     look_k reads that node and its children (level k+1) and picks one.  Descent i runs inc_0 after every earlier
+//     descent's inc_0 and look_k after every earlier descent's inc_(k+1) or end (tree_earlier_reached): then look_k sees
+//     the level-(k+1) increments of every earlier descent and of no later one (descent i+1's inc_(k+1) follows ITS
+//     look_k, which follows this descent's inc_(k+1)), and the count inc_k returns -- used by look_k instead of a second
+//     read -- holds exactly the earlier descents' visits.  Without known results this is the sequential order of every read and write, with
 //     consecutive descents one look apart.
 //   * a descent is final only when it COMMITS, in index order.  A leaf that needs the network commits by taking the
 //     next queue slot (its move list was generated while it waited).  A known result commits by (1) voiding every
@@ -350,10 +350,13 @@ __global__ void __launch_bounds__(32 * WPB) k_expand(TzDev d) {
 //   commit    index of the next descent to commit          filled   queue entries taken
 //   gen       bumped by every voiding                      resume   last generation whose voiding is complete
 //   acks      warps that have taken back their descent since the last voiding          stop   no more descents
+#ifndef TREE_WARPS
 #define TREE_WARPS 8
+#endif
 #define TREE_SPIN_LIMIT (1 << 24)
 
 struct TreeCtl {
+    int nw;  // warps of this launch (<= TREE_WARPS; fewer only in tests, to vary the interleaving)
     volatile int* fprog;
     volatile int* commit;
     volatile int* filled;
@@ -390,10 +393,22 @@ __device__ __forceinline__ bool tree_spin(const TzDev& d, const TreeCtl& c, int 
     return ok != 0;
 }
 
+// Have all descents before `it` made at least `need` increments, or ended?  The nearest one still going decides: its
+// own looks waited for the ones before it.  (One that has ENDED says nothing about the ones before it -- its path may
+// just be shorter than theirs -- so the scan goes on behind it; descents a whole round of warps back have committed.)
+__device__ __forceinline__ bool tree_earlier_reached(const TreeCtl& c, int it, int need) {
+    for (int j = it - 1; j >= 0 && j > it - c.nw; j--) {
+        const int v = c.fprog[j % c.nw];
+        if (v >= j * 1024 + 1000) continue;
+        return v >= j * 1024 + need;
+    }
+    return true;
+}
+
 __device__ __forceinline__ void tree_fpublish(const TreeCtl& c, int it, int steps, int lane) {
     __threadfence_block();
     __syncwarp();
-    if (lane == 0) c.fprog[it % TREE_WARPS] = it * 1024 + steps;
+    if (lane == 0) c.fprog[it % c.nw] = it * 1024 + steps;
 }
 
 // Node::forward (mcts.rs:107-138) as warp_forward does it, as a chain inc_0, look_0, inc_1, look_1, ...: inc_k counts
@@ -407,7 +422,6 @@ __device__ __forceinline__ int tree_descend(const TzDev& d, const GameTree& t, c
     uint32_t slot = 0;
     *undo_slot = 0xffffffffu;
     *out_len = 0;
-    volatile int* pred = c.fprog + (it > 0 ? (it - 1) % TREE_WARPS : 0);
     while (true) {
         // inc_len: after the previous descent's own inc_len (for level 0; deeper ones follow from the look rule)
         if (len >= TZ_MAX_DEPTH) {
@@ -415,8 +429,7 @@ __device__ __forceinline__ int tree_descend(const TzDev& d, const GameTree& t, c
             return TREE_ERROR;
         }
         if (it > 0 && len == 0) {
-            const int want = (it - 1) * 1024 + 1;
-            if (!tree_spin(d, c, my_gen, lane, [=]() { return *pred >= want; })) return TREE_VOID;
+            if (!tree_spin(d, c, my_gen, lane, [=]() { return tree_earlier_reached(c, it, 1); })) return TREE_VOID;
         }
         uint32_t pv = 0;
         if (lane == 0) {
@@ -430,8 +443,8 @@ __device__ __forceinline__ int tree_descend(const TzDev& d, const GameTree& t, c
         tree_fpublish(c, it, len, lane);
         // look_(len-1): after the previous descent's inc_len, or its end
         if (it > 0) {
-            const int want = (it - 1) * 1024 + len + 1;
-            if (!tree_spin(d, c, my_gen, lane, [=]() { return *pred >= want; })) return TREE_VOID;
+            const int need = len + 1;
+            if (!tree_spin(d, c, my_gen, lane, [=]() { return tree_earlier_reached(c, it, need); })) return TREE_VOID;
         }
         const uint32_t meta = t.meta[slot];
         const uint32_t tag = tz_meta_tag(meta);
@@ -484,15 +497,27 @@ __device__ __forceinline__ void tree_take_back(const GameTree& t, const uint32_t
     __syncwarp();
 }
 
+struct TreeForwardSmem {
+    TzState state[TREE_WARPS];
+    uint16_t moves[TREE_WARPS][TZ_MAX_MOVES];
+    uint32_t ranges[TREE_WARPS][TZ_MAX_SQ];
+    uint32_t traj[TREE_WARPS][TZ_MAX_DEPTH];
+    int fprog[TREE_WARPS];
+    int ctl[6];
+};
+
 __global__ void __launch_bounds__(32 * TREE_WARPS) k_tree_forward(TzDev d, float beta, int batch_size, int max_forwards) {
-    __shared__ TzState s_state[TREE_WARPS];
-    __shared__ uint16_t s_moves[TREE_WARPS][TZ_MAX_MOVES];
-    __shared__ uint32_t s_ranges[TREE_WARPS][TZ_MAX_SQ];
-    __shared__ uint32_t s_traj[TREE_WARPS][TZ_MAX_DEPTH];
-    __shared__ int s_fprog[TREE_WARPS];
-    __shared__ int s_ctl[6];
+    extern __shared__ __align__(128) unsigned char tree_smem[];
+    TreeForwardSmem& sm = *reinterpret_cast<TreeForwardSmem*>(tree_smem);
+    TzState* s_state = sm.state;
+    uint16_t(*s_moves)[TZ_MAX_MOVES] = sm.moves;
+    uint32_t(*s_ranges)[TZ_MAX_SQ] = sm.ranges;
+    uint32_t(*s_traj)[TZ_MAX_DEPTH] = sm.traj;
+    int* s_fprog = sm.fprog;
+    int* s_ctl = sm.ctl;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TreeCtl c;
+    c.nw = blockDim.x >> 5;
     c.fprog = s_fprog;
     c.commit = s_ctl + 0;
     c.filled = s_ctl + 1;
@@ -594,7 +619,7 @@ __global__ void __launch_bounds__(32 * TREE_WARPS) k_tree_forward(TzDev d, float
                 __threadfence_block();
                 *c.gen = my_gen + 1;
                 int spins = 0;
-                while (*c.acks < TREE_WARPS - 1 && ++spins <= TREE_SPIN_LIMIT) {
+                while (*c.acks < c.nw - 1 && ++spins <= TREE_SPIN_LIMIT) {
                 }
                 if (spins > TREE_SPIN_LIMIT) atomicOr(d.status, TZ_ERR_NETWORK_STALL);
                 ctr[2] += 1;
@@ -651,7 +676,7 @@ __global__ void __launch_bounds__(32 * TREE_WARPS) k_tree_forward(TzDev d, float
             __syncwarp();
         }
         if (stop) return;
-        it += TREE_WARPS;
+        it += c.nw;
     }
 }
 
@@ -667,13 +692,13 @@ __global__ void __launch_bounds__(32 * TREE_WARPS) k_tree_forward(TzDev d, float
 __device__ __forceinline__ int tree_progress(int q, int finished_depth) { return q * 1024 + (1000 - finished_depth); }
 
 // wait until entry `q - 1` has finished depth `need` (-1 = all of it); false when the wait gave up
-__device__ __forceinline__ bool tree_wait_pred(const TzDev& d, volatile int* prog, int q, int need, int lane) {
+__device__ __forceinline__ bool tree_wait_pred(const TzDev& d, volatile int* prog, int nw, int q, int need, int lane) {
     bool ok = true;
     if (q > 0) {
         if (lane == 0) {
             const int want = tree_progress(q - 1, need);
             int spins = 0;
-            while (prog[(q - 1) % TREE_WARPS] < want)
+            while (prog[(q - 1) % nw] < want)
                 if (++spins > TREE_SPIN_LIMIT) {
                     ok = false;
                     break;
@@ -686,34 +711,42 @@ __device__ __forceinline__ bool tree_wait_pred(const TzDev& d, volatile int* pro
     return ok;
 }
 
-__device__ __forceinline__ void tree_publish(volatile int* prog, int q, int finished_depth, int lane) {
+__device__ __forceinline__ void tree_publish(volatile int* prog, int nw, int q, int finished_depth, int lane) {
     __threadfence_block();
     __syncwarp();
-    if (lane == 0) prog[q % TREE_WARPS] = tree_progress(q, finished_depth);
+    if (lane == 0) prog[q % nw] = tree_progress(q, finished_depth);
 }
 
+struct TreeBackwardSmem {
+    float p[TREE_WARPS][TZ_MAX_MOVES];
+    int prog[TREE_WARPS];
+};
+
 __global__ void __launch_bounds__(32 * TREE_WARPS) k_tree_backward(TzDev d) {
-    __shared__ float s_p[TREE_WARPS][TZ_MAX_MOVES];
-    __shared__ int s_prog[TREE_WARPS];
+    extern __shared__ __align__(128) unsigned char tree_smem[];
+    TreeBackwardSmem& sm = *reinterpret_cast<TreeBackwardSmem*>(tree_smem);
+    float(*s_p)[TZ_MAX_MOVES] = sm.p;
+    int* s_prog = sm.prog;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int count = *d.nn_count;
     volatile int* prog = s_prog;
     if (lane == 0) s_prog[warp] = -1;
     __syncthreads();
     const GameTree t = game_tree(d.arena, 0);
-    for (int q = warp; q < count; q += TREE_WARPS) {
+    const int nw = blockDim.x >> 5;
+    for (int q = warp; q < count; q += nw) {
         const uint32_t* traj = d.traj + (size_t)q * TZ_MAX_DEPTH;
         const int len = d.traj_len[q];
         const LeafOutputs o = expand_outputs(d, q, s_p[warp], lane);
-        bool ok = tree_wait_pred(d, prog, q, len - 2, lane);
+        bool ok = tree_wait_pred(d, prog, nw, q, len - 2, lane);
         ok = ok && expand_leaf(d, 0, q, traj[len - 1], s_p[warp], o, lane);
         Propagated pr = expand_propagated(o);
         for (int e = len - 2; ok && e >= 0; e--) {
-            tree_publish(prog, q, e + 1, lane);
-            ok = tree_wait_pred(d, prog, q, e - 1, lane);
+            tree_publish(prog, nw, q, e + 1, lane);
+            ok = tree_wait_pred(d, prog, nw, q, e - 1, lane);
             if (ok) pr = warp_propagate(t, traj[e], pr, lane);
         }
-        tree_publish(prog, q, -1, lane);  // also after an error: nobody waits for ever
+        tree_publish(prog, nw, q, -1, lane);  // also after an error: nobody waits for ever
     }
 }
 
@@ -1519,10 +1552,20 @@ void launch_finalize(const TzDev& d, uint16_t* out_moves, cudaStream_t st) {
 void launch_step(const TzDev& d, const uint16_t* moves, cudaStream_t st, int only_game) {
     k_step<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, moves, only_game);
 }
-void launch_tree_forward(const TzDev& d, float beta, int batch_size, int max_forwards, cudaStream_t st) {
-    k_tree_forward<<<1, 32 * TREE_WARPS, 0, st>>>(d, beta, batch_size, max_forwards);
+static int tree_warps(int warps) { return warps >= 1 && warps <= TREE_WARPS ? warps : TREE_WARPS; }
+
+void launch_tree_forward(const TzDev& d, float beta, int batch_size, int max_forwards, int warps, cudaStream_t st) {
+    static const cudaError_t attr = cudaFuncSetAttribute(k_tree_forward, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                        (int)sizeof(TreeForwardSmem));
+    (void)attr;
+    k_tree_forward<<<1, 32 * tree_warps(warps), sizeof(TreeForwardSmem), st>>>(d, beta, batch_size, max_forwards);
 }
-void launch_tree_backward(const TzDev& d, cudaStream_t st) { k_tree_backward<<<1, 32 * TREE_WARPS, 0, st>>>(d); }
+void launch_tree_backward(const TzDev& d, int warps, cudaStream_t st) {
+    static const cudaError_t attr = cudaFuncSetAttribute(k_tree_backward, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                        (int)sizeof(TreeBackwardSmem));
+    (void)attr;
+    k_tree_backward<<<1, 32 * tree_warps(warps), sizeof(TreeBackwardSmem), st>>>(d);
+}
 void launch_set_root_priors(const TzDev& d, int stride, const float* prob, const float* logit, cudaStream_t st) {
     k_set_root_priors<<<blocks_for(d.G), 32 * WPB, 0, st>>>(d, stride, prob, logit);
 }

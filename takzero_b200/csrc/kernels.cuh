@@ -11,8 +11,8 @@ void launch_gumbel_init(const TzDev& d, int k, const float* gumbel, int stride, 
 void launch_halve(const TzDev& d, const float* betas, float visits, int remaining, cudaStream_t st);
 void launch_finalize(const TzDev& d, uint16_t* out_moves, cudaStream_t st);
 void launch_step(const TzDev& d, const uint16_t* moves, cudaStream_t st, int only_game = -1);
-void launch_tree_forward(const TzDev& d, float beta, int batch_size, int max_forwards, cudaStream_t st);
-void launch_tree_backward(const TzDev& d, cudaStream_t st);
+void launch_tree_forward(const TzDev& d, float beta, int batch_size, int max_forwards, int warps, cudaStream_t st);
+void launch_tree_backward(const TzDev& d, int warps, cudaStream_t st);
 void launch_tree_pv(const TzDev& d, uint16_t* out_moves, int cap, int* out_len, cudaStream_t st);
 void launch_new_openings(const TzDev& d, const uint8_t* mask, const int* sym, const int* adj, unsigned long long seed,
                          unsigned long long counter, cudaStream_t st);

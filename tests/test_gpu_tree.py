@@ -122,3 +122,23 @@ def test_simulate_batch_with_known_results_in_flight(batch, agent, moves):
     pv = list(m.tree_principal_variation())
     assert pv == oracle_pv(tree)
     m.close()
+
+
+@pytest.mark.parametrize("n,half_komi,batch,batches", [(5, 4, 128, 40), (4, 4, 100, 60), (6, 4, 37, 60)])
+@pytest.mark.parametrize("warps", [1, 2, 3, 5, 8])
+def test_simulate_batch_is_sequential_whatever_the_wavefront(n, half_komi, batch, batches, warps):
+    """Longer runs on one growing tree, with the descents / backups of a batch spread over 1..8 warps: a descent whose
+    path ends early must not let later ones run ahead of the still longer descents before it (the ordering mistake
+    this test was written for showed only with some warp counts).  Bit-exact after every batch."""
+    env = O.new_opening(n, half_komi, 5, 0)
+    m = capi.BatchedMCTS(n, half_komi, batch, arena_slots=1 << 20)
+    m.debug_tree_warps(warps)
+    m.set_positions(games_to_states([env] * batch))
+    tree = O.Tree()
+    for it in range(batches):
+        m.tree_simulate_batch(0.25, batch)
+        tree.simulate_batch("synthetic", env, 0.25, batch)
+        assert_tree_equal(m, tree, f"batch {it}")
+    assert m.status() == 0
+    assert list(m.tree_principal_variation()) == oracle_pv(tree)
+    m.close()
