@@ -338,8 +338,8 @@ __global__ void __launch_bounds__(32 * WPB) k_expand(TzDev d) {
 //     descent's inc_0 and look_k after every earlier descent's inc_(k+1) or end (tree_earlier_reached): then look_k sees
 //     the level-(k+1) increments of every earlier descent and of no later one (descent i+1's inc_(k+1) follows ITS
 //     look_k, which follows this descent's inc_(k+1)), and the count inc_k returns -- used by look_k instead of a second
-//     read -- holds exactly the earlier descents' visits.  Without known results this is the sequential order of every read and write, with
-//     consecutive descents one look apart.
+//     read -- holds exactly the earlier descents' visits.  Without known results this is the sequential order of every
+//     read and write, with consecutive descents one look apart.
 //   * a descent is final only when it COMMITS, in index order.  A leaf that needs the network commits by taking the
 //     next queue slot (its move list was generated while it waited).  A known result commits by (1) voiding every
 //     later descent in flight -- they saw evaluations its backup is about to change -- which take back their visit
@@ -527,16 +527,13 @@ __global__ void __launch_bounds__(32 * TREE_WARPS) k_tree_forward(TzDev d, float
     c.stop = s_ctl + 5;
     if (threadIdx.x < 6) s_ctl[threadIdx.x] = 0;
     if (lane == 0) s_fprog[warp] = -1;
+    if (threadIdx.x == 0) *d.nn_count = 0;  // the committing warp that ends the batch writes the real count
     __syncthreads();
     const GameTree t = game_tree(d.arena, 0);
     unsigned long long* ctr = d.counters;
     TzState* st = &s_state[warp];
     uint32_t* traj = s_traj[warp];
-    const bool any_work = max_forwards > 0 && batch_size > 0;
-    if (!any_work) {
-        if (threadIdx.x == 0) *d.nn_count = 0;
-        return;
-    }
+    if (max_forwards <= 0 || batch_size <= 0) return;
 
     int it = warp;
     int acked_gen = 0;  // lane 0: the last voiding this warp has acknowledged (every warp acknowledges every one)

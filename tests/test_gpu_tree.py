@@ -142,3 +142,27 @@ def test_simulate_batch_is_sequential_whatever_the_wavefront(n, half_komi, batch
     assert m.status() == 0
     assert list(m.tree_principal_variation()) == oracle_pv(tree)
     m.close()
+
+
+def test_simulate_batch_soak_with_tree_reuse():
+    """tei's loop at its own batch size (128 leaves, tei/src/main.rs) for 300 batches on a 6x6 tree that is re-rooted
+    every 60 batches (subtree kept): 38k descents through one growing tree, compared every 20 batches."""
+    n, half_komi, batch = 6, 4, 128
+    env = O.new_opening(n, half_komi, 2, 1)
+    m = capi.BatchedMCTS(n, half_komi, batch, arena_slots=1 << 22)
+    m.set_positions(games_to_states([env] * batch))
+    tree = O.Tree()
+    for it in range(300):
+        m.tree_simulate_batch(0.0, batch)
+        tree.simulate_batch("synthetic", env, 0.0, batch)
+        if it % 20 == 19:
+            assert_tree_equal(m, tree, f"batch {it}")
+        if it % 60 == 59:
+            best = int(m.tree_principal_variation()[0])
+            assert best == O.lib().tk_node_select_best_action(tree.ptr)
+            m.tree_descend(best)
+            tree.descend(best)
+            O.play(env, best)
+            assert_tree_equal(m, tree, f"after descend at batch {it}")
+    assert m.status() == 0
+    m.close()
