@@ -252,9 +252,15 @@ __device__ __forceinline__ LeafOutputs expand_outputs(const TzDev& d, int q, flo
 }
 
 // part 2, the leaf (mcts.rs:190-217, node/mod.rs:66-79): running mean / std of the leaf, its children created in the
-// arena.  False when the arena is full (reported; nothing is backed up then).
-__device__ __forceinline__ bool expand_leaf(const TzDev& d, int g, int q, uint32_t leaf, const float* p,
-                                            const LeafOutputs& o, int lane) {
+// arena.  In two halves for the single-tree wavefront: (a) reads the leaf and writes only fresh arena slots, (b) stores
+// the leaf's own words.  False when the arena is full (reported; nothing is backed up then).
+struct LeafUpdate {
+    float mean, std_dev;
+    uint32_t start;
+};
+
+__device__ __forceinline__ bool expand_leaf_children(const TzDev& d, int g, int q, uint32_t leaf, const float* p,
+                                                     const LeafOutputs& o, int lane, LeafUpdate* u) {
     const int n = d.n_actions[q];
     const GameTree t = game_tree(d.arena, g);
     const float* lg = d.logits + (size_t)q * d.M;
@@ -291,13 +297,28 @@ __device__ __forceinline__ bool expand_leaf(const TzDev& d, int g, int q, uint32
         t.logit[c] = o.priors_ok ? lg[i] : 0.0f;
         t.first[c] = 0;
     }
+    u->mean = m;
+    u->std_dev = sd;
+    u->start = start;
+    return true;
+}
+
+__device__ __forceinline__ void expand_leaf_store(const TzDev& d, int g, int q, uint32_t leaf, const LeafUpdate& u, int lane) {
+    const GameTree t = game_tree(d.arena, g);
     if (lane == 0) {
-        t.eval[leaf] = __float_as_uint(m);
-        t.std_dev[leaf] = sd;
-        t.meta[leaf] = tz_meta(tz_meta_move(t.meta[leaf]), TZ_E_VALUE, (uint32_t)n);
-        t.first[leaf] = start;
+        t.eval[leaf] = __float_as_uint(u.mean);
+        t.std_dev[leaf] = u.std_dev;
+        t.meta[leaf] = tz_meta(tz_meta_move(t.meta[leaf]), TZ_E_VALUE, (uint32_t)d.n_actions[q]);
+        t.first[leaf] = u.start;
     }
     __syncwarp();
+}
+
+__device__ __forceinline__ bool expand_leaf(const TzDev& d, int g, int q, uint32_t leaf, const float* p,
+                                            const LeafOutputs& o, int lane) {
+    LeafUpdate u;
+    if (!expand_leaf_children(d, g, q, leaf, p, o, lane, &u)) return false;
+    expand_leaf_store(d, g, q, leaf, u, lane);
     return true;
 }
 
@@ -431,6 +452,10 @@ __device__ __forceinline__ int tree_descend(const TzDev& d, const GameTree& t, c
         if (it > 0 && len == 0) {
             if (!tree_spin(d, c, my_gen, lane, [=]() { return tree_earlier_reached(c, it, 1); })) return TREE_VOID;
         }
+        // the node's own words ride along with the increment: nothing but a known result's commit changes them during
+        // this launch, and that voids this descent anyway
+        const uint32_t meta = t.meta[slot];
+        const uint32_t eval_bits = t.eval[slot];
         uint32_t pv = 0;
         if (lane == 0) {
             // atomic: a voided descent may be taking its increment of this very node (the root, say) back right now
@@ -439,16 +464,22 @@ __device__ __forceinline__ int tree_descend(const TzDev& d, const GameTree& t, c
         }
         len++;
         *out_len = len;
+        // the move that leads here is played while the increment is on its way (the next descent waits for the
+        // increment, not for the board)
+        const bool applied = len == 1 || warp_apply(st, d.n, (uint16_t)tz_meta_move(meta), lane);
         pv = __shfl_sync(FULL_MASK, pv, 0);
         tree_fpublish(c, it, len, lane);
-        // look_(len-1): after the previous descent's inc_len, or its end
+        if (!applied) {
+            *err_bit = TZ_ERR_BAD_MOVE;
+            return TREE_ERROR;
+        }
+        // look_(len-1): after every earlier descent's inc_len, or its end
         if (it > 0) {
             const int need = len + 1;
             if (!tree_spin(d, c, my_gen, lane, [=]() { return tree_earlier_reached(c, it, need); })) return TREE_VOID;
         }
-        const uint32_t meta = t.meta[slot];
         const uint32_t tag = tz_meta_tag(meta);
-        if (tag != TZ_E_VALUE && t.eval[slot] == 0) {  // is_terminal
+        if (tag != TZ_E_VALUE && eval_bits == 0) {  // is_terminal
             *known_ev = ev_make(tag, 0);
             return TREE_KNOWN;
         }
@@ -457,7 +488,7 @@ __device__ __forceinline__ int tree_descend(const TzDev& d, const GameTree& t, c
             if (term != TZ_T_NONE) {
                 *known_ev = ev_make(term == TZ_T_WIN ? TZ_E_WIN : (term == TZ_T_LOSS ? TZ_E_LOSS : TZ_E_DRAW), 0);
                 undo_words[0] = t.eval[slot];
-                undo_words[1] = meta;
+                undo_words[1] = t.meta[slot];
                 undo_words[2] = __float_as_uint(t.std_dev[slot]);
                 *undo_slot = slot;
                 if (lane == 0) {
@@ -477,10 +508,6 @@ __device__ __forceinline__ int tree_descend(const TzDev& d, const GameTree& t, c
             return TREE_ERROR;
         }
         slot = t.first[slot] + (uint32_t)idx;
-        if (!warp_apply(st, d.n, (uint16_t)tz_meta_move(t.meta[slot]), lane)) {
-            *err_bit = TZ_ERR_BAD_MOVE;
-            return TREE_ERROR;
-        }
     }
 }
 
@@ -680,11 +707,13 @@ __global__ void __launch_bounds__(32 * TREE_WARPS) k_tree_forward(TzDev d, float
 // backward_network_eval of the queued leaves IN QUEUE ORDER (they share one tree: every running mean and every solver
 // scan sees what the earlier leaves of the batch left), by TREE_WARPS warps of one CTA as a wavefront:
 //   * the heads, the softmax and the sanitising of an entry touch nothing shared and run at once for TREE_WARPS entries;
-//   * entry q works on depth e of its path (leaf step at e = len-1, then the parents up to the root at 0) only after
-//     entry q-1 has finished depth e-1 -- by induction so have all earlier entries.  A step at depth e reads and writes
-//     the node at depth e and reads its children at depth e+1; the earlier entries are past e-1, so they will not touch
-//     either level again, and what they wrote there is visible (fence + progress word in shared memory); later entries
-//     stay above e+1 until this one has finished e.  The arena allocations happen in the leaf steps, hence in order.
+//   * entry q works on depth e of its path (leaf step at e = len-1, then the parents up to the root at 0) in two halves:
+//     it READS the node at depth e and its children at depth e+1 once entry q-1 has finished depth e (by induction so
+//     have all earlier entries: what they wrote on both levels is final and visible -- fence + progress word in shared
+//     memory), and it STORES the node at depth e once entry q-1 has finished depth e-1, because until then that entry's
+//     solver scan at depth e-1 may still be reading this node as one of its children.  So consecutive entries run one
+//     step apart, the reads and the arithmetic of one overlapping the step above it of the other.  The arena allocations
+//     happen in the leaf steps, hence in order; fresh child slots are written in the read half (nobody can reach them).
 // progress word of the warp that owns entry q: q * 1024 + (1000 - last finished depth), monotonic over its entries.
 __device__ __forceinline__ int tree_progress(int q, int finished_depth) { return q * 1024 + (1000 - finished_depth); }
 
@@ -735,13 +764,20 @@ __global__ void __launch_bounds__(32 * TREE_WARPS) k_tree_backward(TzDev d) {
         const uint32_t* traj = d.traj + (size_t)q * TZ_MAX_DEPTH;
         const int len = d.traj_len[q];
         const LeafOutputs o = expand_outputs(d, q, s_p[warp], lane);
-        bool ok = tree_wait_pred(d, prog, nw, q, len - 2, lane);
-        ok = ok && expand_leaf(d, 0, q, traj[len - 1], s_p[warp], o, lane);
+        const uint32_t leaf = traj[len - 1];
+        LeafUpdate u;
+        bool ok = tree_wait_pred(d, prog, nw, q, len - 1, lane);  // reads at the leaf's depth
+        ok = ok && expand_leaf_children(d, 0, q, leaf, s_p[warp], o, lane, &u);
+        ok = tree_wait_pred(d, prog, nw, q, len - 2, lane) && ok;  // stores at the leaf's depth
+        if (ok) expand_leaf_store(d, 0, q, leaf, u, lane);
         Propagated pr = expand_propagated(o);
         for (int e = len - 2; ok && e >= 0; e--) {
             tree_publish(prog, nw, q, e + 1, lane);
-            ok = tree_wait_pred(d, prog, nw, q, e - 1, lane);
-            if (ok) pr = warp_propagate(t, traj[e], pr, lane);
+            PendingNode w;
+            ok = tree_wait_pred(d, prog, nw, q, e, lane);  // reads at depth e (and e+1)
+            if (ok) pr = warp_propagate_compute(t, traj[e], pr, lane, &w);
+            ok = ok && tree_wait_pred(d, prog, nw, q, e - 1, lane);  // stores at depth e
+            if (ok) warp_propagate_store(t, w, lane);
         }
         tree_publish(prog, nw, q, -1, lane);  // also after an error: nobody waits for ever
     }

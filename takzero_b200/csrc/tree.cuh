@@ -328,6 +328,63 @@ __device__ __forceinline__ Propagated warp_propagate(const GameTree& t, uint32_t
     return p;
 }
 
+// `propagate_child_eval` in two halves for the single-tree wavefront (kernels.cu, k_tree_backward): everything but the
+// stores -- same reads, same arithmetic, same order as warp_propagate -- and then the stores.
+struct PendingNode {
+    uint32_t slot;
+    int kind;  // 0 nothing, 1 solved (tag + bits, std_dev 0), 2 running mean (bits, std_dev)
+    uint32_t meta, bits;
+    float std_dev;
+};
+
+__device__ __forceinline__ Propagated warp_propagate_compute(const GameTree& t, uint32_t slot, Propagated child, int lane,
+                                                             PendingNode* w) {
+    const uint32_t meta = t.meta[slot];
+    const int nchild = (int)tz_meta_nchild(meta);
+    const uint32_t first = t.first[slot];
+    Ev ev = ev_make(tz_meta_tag(meta), t.eval[slot]);
+    float std_dev = t.std_dev[slot];
+    w->slot = slot;
+    w->kind = 0;
+    const int flags = warp_children_flags(t, first, nchild, lane);
+    if (child.eval.tag == TZ_E_LOSS || (flags & 1)) {
+        Ev m;
+        warp_min_child(t, first, nchild, lane, &m);
+        ev = ev_negate(m);
+        std_dev = 0.0f;
+        w->kind = 1;
+        w->meta = (meta & ~(3u << 16)) | (ev.tag << 16);  // node_set_eval
+        w->bits = ev.bits;
+        w->std_dev = 0.0f;
+    }
+    Propagated p;
+    if (ev_known(ev)) {
+        p.eval = ev;
+        p.variance = fmul(std_dev, std_dev);
+    } else {
+        const float negated = ev_notnan(ev_negate(child.eval));
+        const float n = (float)t.visits[slot];
+        float m = __uint_as_float(ev.bits);
+        m = fadd(m, fdiv(fadd(fneg(m), negated), n));
+        std_dev = fadd(std_dev, fdiv(fadd(fneg(std_dev), fsqrt(child.variance)), n));
+        w->kind = 2;
+        w->bits = __float_as_uint(m);
+        w->std_dev = std_dev;
+        p.eval = ev_value(fmul(negated, 0.997f));
+        p.variance = fmul(fmul(child.variance, 0.997f), 0.997f);
+    }
+    return p;
+}
+
+__device__ __forceinline__ void warp_propagate_store(const GameTree& t, const PendingNode& w, int lane) {
+    if (lane == 0 && w.kind != 0) {
+        if (w.kind == 1) t.meta[w.slot] = w.meta;
+        t.eval[w.slot] = w.bits;
+        t.std_dev[w.slot] = w.std_dev;
+    }
+    __syncwarp();
+}
+
 // unwind `p` from the parent of the leaf (traj[len-2]) to the simulation root (traj[0])
 __device__ __forceinline__ void warp_backup(const GameTree& t, const uint32_t* traj, int len,
                                             Propagated p, int lane) {
