@@ -100,6 +100,16 @@ impl BatchedMcts {
         let (p, n) = match tensors { Some(t) => (t.as_ptr(), t.len() as i32), None => (ptr::null(), 0) };
         check(unsafe { sys::tz_broadcast_weights(self.h, p, n, res_blocks, root) }).map(|_| ())
     }
+    /// `Net::update_counts` (net6_simhash.rs:236-241): the novelty set remembers these positions.
+    pub fn update_counts(&mut self, states: &[State]) -> Result<(), String> {
+        check(unsafe { sys::tz_update_counts(self.h, states.as_ptr(), states.len() as i32) }).map(|_| ())
+    }
+    /// The set as `Net::save` writes it next to the model (`bitvec.bin`, 2^29 bytes; net6_simhash.rs:152-170).
+    pub fn novelty_set(&self) -> Result<Vec<u8>, String> {
+        let mut out = vec![0u8; 1 << 29];
+        check(unsafe { sys::tz_read_novelty_set(self.h, out.as_mut_ptr(), out.len()) })?;
+        Ok(out)
+    }
     /// Whole-job totals of per-rank counters (what `learn` adds up through `buffer_lengths.txt`).
     pub fn allreduce_sum(&mut self, values: &mut [u64]) -> Result<(), String> {
         check(unsafe { sys::tz_allreduce_sum(self.h, values.as_mut_ptr(), values.len() as i32) }).map(|_| ())
