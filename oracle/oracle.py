@@ -192,6 +192,8 @@ def lib():
     L.tk_games_pack.argtypes = [P(Game), C.c_int, C.c_void_p]
     L.tk_games_unpack.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, P(Game)]
     L.tk_game_repr_batch.argtypes = [P(Game), C.c_int, C.c_void_p]
+    L.tk_perft.argtypes = [P(Game), C.c_int]
+    L.tk_perft.restype = C.c_ulonglong
     L.tk_move_index_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.tk_game_result5.argtypes = [P(Game)]
     L.tk_game_result5.restype = C.c_int
@@ -510,3 +512,8 @@ class Batched:
         out = (C.c_uint16 * self.batch)()
         lib().tk_batched_select_best_actions(self.ptr, out)
         return list(out)
+
+
+def perft(g: Game, depth: int) -> int:
+    """Move sequences of length `depth` from `g` (none continues past a finished game)."""
+    return int(lib().tk_perft(C.byref(g), depth))

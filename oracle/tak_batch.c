@@ -166,3 +166,20 @@ long long tk_expf_compare(uint32_t lo_bits, uint32_t hi_bits, uint32_t step, lon
 void tk_expf_restated_batch(const float* in, int count, float* out) {
     for (int i = 0; i < count; i++) out[i] = tk_expf_restated(in[i]);
 }
+
+/* perft: number of move sequences of length `depth` from `g`, none continuing past a finished game -- the usual
+ * known-answer test of Tak move generators.  Loops tk_terminal / tk_possible_moves / tk_play only. */
+unsigned long long tk_perft(const tk_game* g, int depth) {
+    if (depth <= 0) return 1;
+    if (tk_terminal(g) != TK_T_NONE) return 0;
+    tk_move moves[TK_MAX_MOVES];
+    const int n = tk_possible_moves(g, moves);
+    if (depth == 1) return (unsigned long long)n;
+    unsigned long long total = 0;
+    for (int i = 0; i < n; i++) {
+        tk_game child = *g;
+        tk_play_unchecked(&child, moves[i]);
+        total += tk_perft(&child, depth - 1);
+    }
+    return total;
+}

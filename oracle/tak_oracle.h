@@ -189,6 +189,7 @@ void tk_batched_select_best_actions(tk_batched* b, tk_move* out);
 void tk_games_pack(const tk_game* games, int count, uint8_t* out384);
 void tk_games_unpack(const uint8_t* in384, int count, int n, int half_komi, int reversible_limit, tk_game* games);
 void tk_game_repr_batch(const tk_game* games, int count, float* out);
+unsigned long long tk_perft(const tk_game* g, int depth);
 void tk_move_index_batch(int n, const tk_move* actions, const int* n_actions, int stride, int count, int32_t* out);
 int tk_game_result5(const tk_game* g);
 long long tk_expf_compare(uint32_t lo_bits, uint32_t hi_bits, uint32_t step, long long* tested, float* first_bad);

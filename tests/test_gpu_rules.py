@@ -177,3 +177,33 @@ def test_impossible_host_states_are_refused():
     m.set_positions(good)
     assert m.status() == 0
     m.close()
+
+
+@pytest.mark.parametrize("n,depth", [(3, 6), (4, 5), (5, 4), (6, 4)])
+def test_perft_through_the_c_abi(n, depth):
+    """The published perft counts of Tak (tests/test_oracle_golden.py::PERFT, where their provenance is stated) from
+    the CUDA rules alone: breadth-first through tz_result / tz_legal_moves / tz_apply, no oracle in the loop.  3x3 to
+    depth 6 includes finished games that must not be continued; 6x6 to depth 4 is 13.6 M move sequences."""
+    from test_oracle_golden import PERFT
+
+    m = capi.BatchedMCTS(n, 0, 4, arena_slots=4096)
+    frontier = games_to_states([O.new_game(n, 0)])
+    chunk = 16384
+    for d in range(1, depth + 1):
+        live = frontier[m.result(frontier) == 0]
+        total, children = 0, []
+        for lo in range(0, len(live), chunk):
+            part = live[lo:lo + chunk]
+            moves, cnt = m.legal_moves(part)
+            assert (cnt >= 0).all()
+            total += int(cnt.sum())
+            if d < depth:
+                parent = np.repeat(np.arange(len(part)), cnt)
+                played = moves[np.arange(moves.shape[1])[None, :] < cnt[:, None]]  # row-major = parent order
+                states, ok = m.apply(part[parent], played)
+                assert ok.all()
+                children.append(states)
+        assert total == PERFT[n][d - 1], f"{n}x{n} perft({d})"
+        if d < depth:
+            frontier = np.concatenate(children)
+    m.close()

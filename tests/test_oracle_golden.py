@@ -507,3 +507,24 @@ def test_replay_consistency(oracle):
     sample = lines[:: max(1, len(lines) // 3000)]
     got = _format_check([f"replay 5 {line}" for line in sample])
     assert got == sample and len(sample) > 1000
+
+
+# Published perft counts of Tak from the empty board (move sequences of a given length, none continuing past a finished
+# game).  [RECALLED: these are the numbers the Tak engines' own move-generator tests carry -- fast-tak's among them; the
+# crate's source is not under /root/reference, so they are written down from memory and say so.]  They pin the restated
+# rules independently of anything derived from this repository: placements and the opening swap (depth 1-2), every
+# spread / drop pattern over one- and two-high stacks with walls blocking (depth 3-4), capstone crushes and the first
+# finished games -- roads on 3x3 from depth 5, where a finished position must not be continued -- (depth 5-6).
+PERFT = {
+    3: [9, 72, 1200, 17792, 271812, 3712952],
+    4: [16, 240, 7440, 216464, 6468872],
+    5: [25, 600, 43320, 2999784],
+    6: [36, 1260, 132720, 13586048],
+}
+
+
+@pytest.mark.parametrize("n", [3, 4, 5, 6])
+def test_perft_known_answers(oracle, n):
+    g = oracle.new_game(n, 0)
+    for depth, want in enumerate(PERFT[n], start=1):
+        assert oracle.perft(g, depth) == want, f"{n}x{n} perft({depth})"
