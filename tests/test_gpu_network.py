@@ -447,6 +447,15 @@ def test_lcghash_indices_bit_exact_and_uncertainty(n, hk, tmp_path):
     network.load_model(b, str(tmp_path / "model_latest.ot"))
     assert np.array_equal(network.lcghash_indices(b, states), want)
     assert np.array_equal(network.evaluate(b, states, actions)[2], variances)
+    # update_counts with this hash (net4_lcghash.rs has the same `update_counts`): the other half becomes seen too,
+    # on top of the set that came with the file
+    network.update_counts(b, states[1::2])
+    after = network.evaluate(b, states, actions)[2]
+    assert np.abs(after - np.clip(np.exp(ube), 0.0, 4.0)).max() <= 2e-2
+    image = network.read_novelty_set(b)
+    full = np.zeros(1 << 29, dtype=np.uint8)
+    np.bitwise_or.at(full, got >> 3, (1 << (got & 7)).astype(np.uint8))
+    assert np.array_equal(image, full)
     for h in (m, b):
         h.close()
 
