@@ -101,7 +101,7 @@ constexpr int B_STAGES = TZ_B_STAGES;
 constexpr int N_OUT = 256;
 constexpr int THREADS = 256;
 constexpr int W_EPI0 = 0, W_APROD = 4, W_BPROD = 5, W_MMA = 6, W_ALLOC = 7;
-constexpr int MASK_BYTES = 36 * 9 * 16;        // [N*N][9 taps] 128-bit lane masks
+constexpr int MASK_BYTES = 37 * 9 * 16;        // [N*N + 1][9 taps] 128-bit lane masks (the last entry: packed tiles)
 constexpr int GATHER_BYTES = 4 * 32 * 32 * 4;  // policy epilogue: 32 rows x 32 channels f32 per epilogue warp
 constexpr int SMEM_BYTES =
     A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + 4096 /*bias, one copy per epilogue warp*/ + 512 /*barriers*/ +
@@ -153,6 +153,11 @@ struct Params {
     unsigned* status;               // the handle's sticky error word (watchdog of the dependency waits)
     int debug_drop_progress;        // test hook: CTA pair 0 never publishes its tiles (exercises the watchdog)
     int allow_local;                // 0: never use the local chain (debug read-backs of the activation buffers)
+    int pack;                       // > 0: PACKED rows for small batches of boards whose N*N does not divide 128 (5x5,
+                                    // 6x6): every CTA tile holds `pack` whole positions (row = tile * 128 + position
+                                    // in tile * N*N + square) and its last 128 - pack * N*N rows are dead, so no
+                                    // position straddles two CTAs and the local chain applies; masks[N*N] is the lane
+                                    // mask table of such a tile.  0: dense rows.
 };
 
 // work item -> (chunk, layer, pair tile); every role of the kernel walks the same sequence
@@ -224,6 +229,19 @@ __device__ __forceinline__ long long gtime() {
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// row of the launch -> (position, square); false for a dead row of a packed tile or a position past the count
+__device__ __forceinline__ bool row_position(int pack, int nn, int count, unsigned row, int* q, int* sq) {
+    if (pack == 0) {
+        *q = (int)(row / (unsigned)nn);
+        *sq = (int)(row - (unsigned)*q * (unsigned)nn);
+        return true;  // the callers bound dense rows by the chunk's row count
+    }
+    const unsigned tile = row / (unsigned)TILE_M, w = row - tile * (unsigned)TILE_M, b = w / (unsigned)nn;
+    *q = (int)(tile * (unsigned)pack + b);
+    *sq = (int)(w - b * (unsigned)nn);
+    return (int)b < pack && *q < count;
+}
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -405,8 +423,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
 
     const int count = p.count_ptr ? *p.count_ptr : p.count_max;
     const int nn = p.n * p.n;
+    // packed rows: the schedule sees "positions" of 128 rows (one CTA tile = p.pack real positions + dead rows)
+    const int period = p.pack ? TILE_M : nn;
     Schedule sched;
-    sched.init(count, nn, p.chunk_min_tiles, p.n_layers);
+    sched.init(p.pack ? (count + p.pack - 1) / p.pack : count, period, p.chunk_min_tiles, p.n_layers);
     const int items = sched.items;
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
     // With fewer than two tiles per pair and layer the launch is bound by the layer-to-layer dependency chain: the
@@ -414,7 +434,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
     // rest of the epilogue.  With more tiles that only costs (four device-wide fences per tile instead of one).
     const bool fine = sched.chunk_tiles < 2 * npairs;
     // Local chain (see the header): pair p owns tile p of every layer, activations stay in shared memory.
-    const bool local = p.allow_local && p.n_layers > 1 && (TILE_M % nn) == 0 && sched.chunk_tiles <= npairs &&
+    const bool local = p.allow_local && p.n_layers > 1 && (TILE_M % period) == 0 && sched.chunk_tiles <= npairs &&
                        items == sched.chunk_tiles * p.n_layers;
     const int item0 = local ? (pair < sched.chunk_tiles ? pair : items) : pair;
     const int istep = local ? sched.chunk_tiles : npairs;
@@ -444,7 +464,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < nn * 9; i += THREADS) s_masks[i] = p.masks[i];
+    for (int i = threadIdx.x; i < (nn + 1) * 9; i += THREADS) s_masks[i] = p.masks[i];
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();  // both CTAs' barriers are initialised before anyone arrives remotely
@@ -492,11 +512,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                     tail[k] = make_uint4(0u, 0u, 0u, 0u);
                     if (r < A_ROWS && rel >= 0 && rel < it.rows) {
                         const unsigned grow = (unsigned)(it.chunk * sched.chunk_rows + rel);
-                        const int q = (int)(grow / (unsigned)nn), sq = (int)(grow - (unsigned)q * (unsigned)nn);
-                        const uint8_t* st = reinterpret_cast<const uint8_t*>(L.enc_states + q);
-                        stack[k] = *reinterpret_cast<const uint64_t*>(st + 8 * sq);
-                        hts[k] = (uint32_t)st[288 + sq] | ((uint32_t)st[324 + sq] << 8) | ((uint32_t)st[360] << 16);
-                        tail[k] = *reinterpret_cast<const uint4*>(st + 368);
+                        int q, sq;
+                        if (row_position(p.pack, nn, count, grow, &q, &sq)) {
+                            const uint8_t* st = reinterpret_cast<const uint8_t*>(L.enc_states + q);
+                            stack[k] = *reinterpret_cast<const uint64_t*>(st + 8 * sq);
+                            hts[k] = (uint32_t)st[288 + sq] | ((uint32_t)st[324 + sq] << 8) | ((uint32_t)st[360] << 16);
+                            tail[k] = *reinterpret_cast<const uint4*>(st + 368);
+                        }
                     }
                 }
 #pragma unroll
@@ -651,8 +673,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                 TWAIT(w_t, mbar_wait(t_empty + 8 * acc, ((it >> 1) & 1) ^ 1));
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * N_OUT;
-                const uint4* masks0 = s_masks + ((size_t)(pt * 2) * TILE_M % nn) * 9;
-                const uint4* masks1 = s_masks + ((size_t)(pt * 2 + 1) * TILE_M % nn) * 9;
+                const uint4* masks0 = s_masks + (p.pack ? (size_t)nn : (size_t)(pt * 2) * TILE_M % nn) * 9;
+                const uint4* masks1 = s_masks + (p.pack ? (size_t)nn : (size_t)(pt * 2 + 1) * TILE_M % nn) * 9;
                 for (int kb = 0; kb < kblocks; kb++) {
 #ifdef TZ_DEBUG_TIMING
                     if (p.layers[wi.layer].enc_states != nullptr)
@@ -736,10 +758,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
             const int relu = L.relu;
             const int acc = it & 1;
             const int t = pt * 2 + (int)rank;
-            const int rel = t * TILE_M + wq * 32 + lane;  // row of the chunk = position * n*n + square
-            const bool valid = rel < wi.rows;
+            const int rel = t * TILE_M + wq * 32 + lane;  // row of the chunk = position * n*n + square (dense rows)
             const size_t grow = (size_t)(p.guard + rel) * 8;  // element offset of the row inside a plane
-            const size_t grel = (size_t)wi.chunk * sched.chunk_rows + (size_t)rel;  // row among all positions
+            const size_t grel = (size_t)wi.chunk * sched.chunk_rows + (size_t)rel;  // row among all rows of the launch
+            int q_row = 0, sq_row = 0;  // the position (evaluation-queue slot) and square this thread's row belongs to
+            const bool valid = rel < wi.rows && row_position(p.pack, nn, count, (unsigned)grel, &q_row, &sq_row);
             float head_v = 0.0f, head_u = 0.0f;
             // policy layer: the legal moves that start on this thread's square (their logits are all it keeps)
             float* g_row = nullptr;
@@ -751,8 +774,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
             uint32_t g_ch0 = 0, g_ch1 = 0, g_valid = 0, g_blocks = 0;
             int g_q = 0;
             if (L.g_out != nullptr && valid) {
-                const unsigned ug = (unsigned)grel;
-                const int q = (int)(ug / (unsigned)nn), sq = (int)(ug - (unsigned)q * (unsigned)nn);
+                const int q = q_row, sq = sq_row;
                 g_q = q;
                 const uint32_t range = L.g_ranges[(size_t)q * 36 + sq];
                 g_first = (int)(range & 0xffffu);
@@ -927,7 +949,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_conv3x
                     }
                 }
             }
-            if (head_w && valid) *reinterpret_cast<float2*>(L.head_out + grel * 2) = make_float2(head_v, head_u);
+            if (head_w && valid)
+                *reinterpret_cast<float2*>(L.head_out + ((size_t)q_row * nn + sq_row) * 2) = make_float2(head_v, head_u);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {

@@ -54,6 +54,7 @@ struct NnState {
     int in_channels = 0, out_channels = 0;
     int max_positions = 0;
     size_t rows_set = 0;  // rows per chunk plane of one activation set (one chunk of positions)
+    int pack = 0;         // positions per CTA tile of the packed small-batch layout (conv::Params::pack), 0: never
     int chunk_min_tiles = 0;   // least pair tiles the network runs through all layers at a time (conv_tcgen05.cuh)
     int chunk_tiles = 0, max_chunks = 0;  // bounds: pair tiles of one chunk, chunks of one launch
     // weights: two sets, `active` is the one new launches read (-1: none yet)
@@ -562,6 +563,21 @@ static int ensure_state(tz_handle* h, int blocks) {
         s->chunk_tiles = cb.chunk_tiles;
         s->max_chunks = cb.chunks;
         s->rows_set = conv::HALO + (size_t)s->chunk_tiles * (2 * conv::TILE_M) + 2 * conv::HALO;
+        // Small batches of 5x5 / 6x6 positions (the single tree of `tei`: 128 leaves): N*N does not divide the 128 rows
+        // of a CTA, so positions straddle CTAs and the layers of a tile wait for their neighbours' (16 us per layer).
+        // Packed rows -- 5 / 3 whole positions per CTA tile, the rest of its rows dead -- make every tile independent,
+        // and the local chain of the 4x4 small batches applies (activations stay in shared memory from layer to layer).
+        // Worth its 16 % / 2 % of dead tensor-core rows only while every CTA has at most one tile.
+        s->pack = 0;
+        if (s->fused && h->dbg_chunk_tiles < 0 && conv::TILE_M % nn != 0) {
+            const int per_tile = conv::TILE_M / nn;
+            const int tiles = (s->max_positions + per_tile - 1) / per_tile;
+            if (tiles <= 2 * (s->sm_count / 2)) {
+                s->pack = per_tile;
+                const size_t rows = conv::HALO + (size_t)((tiles + 1) / 2) * (2 * conv::TILE_M) + 2 * conv::HALO;
+                if (rows > s->rows_set) s->rows_set = rows;
+            }
+        }
     }
     // both activation buffers are one allocation
     const size_t act_bytes = 2 * s->rows_set * FILTERS * 2;
@@ -576,7 +592,7 @@ static int ensure_state(tz_handle* h, int blocks) {
     {
         // lane masks: bit i of mask[start][tap] is set when tile row i (board square (start + i) mod nn)
         // has no (dy,dx) neighbour on the board
-        std::vector<uint32_t> mk((size_t)nn * 9 * 4, 0);
+        std::vector<uint32_t> mk((size_t)(nn + 1) * 9 * 4, 0);
         for (int start = 0; start < nn; start++)
             for (int tap = 0; tap < 9; tap++) {
                 const int dy = tap / 3 - 1, dx = tap % 3 - 1;
@@ -586,6 +602,15 @@ static int ensure_state(tz_handle* h, int blocks) {
                     if (off) mk[((size_t)start * 9 + tap) * 4 + i / 32] |= 1u << (i % 32);
                 }
             }
+        // entry nn: a packed tile (positions at rows 0, nn, 2 nn, ...; the dead rows at its end take no tap at all)
+        for (int tap = 0; tap < 9; tap++) {
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            for (int i = 0; i < conv::TILE_M; i++) {
+                const int sq = i % nn, y = sq / n, x = sq % n;
+                const bool off = i / nn >= conv::TILE_M / nn || y + dy < 0 || y + dy >= n || x + dx < 0 || x + dx >= n;
+                if (off) mk[((size_t)nn * 9 + tap) * 4 + i / 32] |= 1u << (i % 32);
+            }
+        }
         if (!dalloc((void**)&s->masks, mk.size() * 4) ||
             cudaMemcpy(s->masks, mk.data(), mk.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
             nn_free(h);
@@ -609,7 +634,8 @@ static int ensure_state(tz_handle* h, int blocks) {
             s->max_pairs = clusters < s->sm_count / 2 ? clusters : s->sm_count / 2;
         else
             s->max_pairs = s->sm_count / 2;
-        s->progress_len = (size_t)s->max_chunks * s->chunk_tiles * 4 + s->max_chunks + 16;
+        if (s->pack && (s->max_positions + s->pack - 1) / s->pack > 2 * s->max_pairs) s->pack = 0;
+        s->progress_len = (size_t)s->max_chunks * s->chunk_tiles * 4 + s->max_chunks + 16 + (s->pack ? 4 * (size_t)s->max_pairs : 0);
         if (!dalloc((void**)&s->progress, s->progress_len * sizeof(unsigned))) {
             nn_free(h);
             NN_FAIL(TZ_ENOMEM, "cudaMalloc progress");
@@ -930,9 +956,12 @@ static conv::Layer conv_layer(const NnState* s, int set, int l, const __nv_bfloa
 // one chunk (at least `chunk_min_tiles` pair tiles) each.  With more than one layer the CTA pairs synchronise through s->progress
 // inside the kernel, so the launch is cooperative (all pairs resident, or it fails loudly).
 static cudaError_t launch_layers(tz_handle* h, conv::Params& p, int set, const int* count_ptr, int count_max, size_t rows_set,
-                                 int chunk_min_tiles) {
+                                 int chunk_min_tiles, int pack = 0) {
     const NnState* s = h->nn;
-    const int nn = s->n * s->n;
+    p.pack = pack;
+    // what the kernel's schedule counts: positions of N*N rows, or (packed) CTA tiles of 128 rows
+    const int nn = pack ? conv::TILE_M : s->n * s->n;
+    const int units_max = pack ? (count_max + pack - 1) / pack : count_max;
     p.rows_set = (long long)rows_set;
     p.set_stride = (long long)rows_set * FILTERS;
     p.chunk_min_tiles = chunk_min_tiles;
@@ -943,8 +972,8 @@ static cudaError_t launch_layers(tz_handle* h, conv::Params& p, int set, const i
     p.masks = s->masks;
     p.f16 = s->set_f16[set];
     // upper bounds of what the kernel derives from the device-side count (conv::Schedule::init)
-    const int all_tiles = (count_max * nn + 2 * conv::TILE_M - 1) / (2 * conv::TILE_M);
-    const ChunkBounds cb = chunk_bounds(count_max, nn, chunk_min_tiles);
+    const int all_tiles = (units_max * nn + 2 * conv::TILE_M - 1) / (2 * conv::TILE_M);
+    const ChunkBounds cb = chunk_bounds(units_max, nn, chunk_min_tiles);
     const int chunks = cb.chunks, chunk_tiles = cb.chunk_tiles;
     const size_t counters = (size_t)chunks * chunk_tiles * 4 + chunks;  // 4 channel blocks per tile, then the chunks
     p.progress = s->progress;
@@ -1014,7 +1043,8 @@ static int launch_network(tz_handle* h, const Boundary& io, const int* count_ptr
         }
         p.n_layers = (int)chunk;
         p.allow_local = upto < 0;  // the debug read-backs look at the activation buffers in global memory
-        if (launch_layers(h, p, set, count_ptr, count_max, s->rows_set, s->chunk_min_tiles) != cudaSuccess) return -1;
+        const int pack = p.allow_local && chunk == all.size() ? s->pack : 0;
+        if (launch_layers(h, p, set, count_ptr, count_max, s->rows_set, s->chunk_min_tiles, pack) != cudaSuccess) return -1;
         first += chunk;
         launches++;
     }

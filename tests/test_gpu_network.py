@@ -334,7 +334,7 @@ def test_watchdog_turns_a_stalled_dependency_into_a_status_bit():
     launch ends, and the handle reports the error instead of hanging the GPU."""
     import time
 
-    n, hk, count = 5, 4, 160  # 5x5: positions straddle tiles, so the pairs do depend on each other (no local chain)
+    n, hk, count = 5, 4, 800  # 5x5, more tiles than CTAs: dense rows, positions straddle tiles, the pairs depend on each other
     ref = net_ref.Net(n, seed=2, blocks=2)
     games = sample_positions(n, hk, count, 5)
     actions = [O.possible_moves(g) for g in games]
