@@ -328,6 +328,38 @@ def test_local_chain_of_4x4_small_batches_is_bit_identical(count):
     assert float(np.abs(outs[0][1][:64] - want_values).max()) <= TOL
 
 
+@pytest.mark.parametrize("n,count", [(6, 1), (6, 3), (6, 4), (6, 128), (6, 444), (6, 445), (5, 5), (5, 6), (5, 128),
+                                     (5, 740), (5, 741)])
+def test_packed_local_chain_of_5x5_and_6x6_small_batches_is_bit_identical(n, count):
+    """5x5 / 6x6: 25 / 36 squares do not divide the 128 rows of a CTA.  With at most one tile per CTA (<= 740 / 444
+    positions on 148 SMs) the fused launch packs 5 / 3 whole positions into every CTA tile (the rest of its rows are
+    dead), so no position straddles two CTAs and the shared-memory local chain applies.  Same bits as one launch per
+    layer on dense rows: a single position, exactly one tile, one position more, the 128 leaves of tei's batches, the
+    largest packed size and the first one that is dense again."""
+    hk = 4
+    ref = net_ref.Net(n, seed=8, blocks=3, randomize_bn=True)
+    games = sample_positions(n, hk, min(count, 200), 99)
+    games = [games[i % len(games)] for i in range(count)]
+    actions = [O.possible_moves(g) for g in games]
+    states = games_to_states(games)
+    outs = []
+    for per_layer in (False, True):
+        m = capi.BatchedMCTS(n, hk, count, arena_slots=4096)
+        network.debug_network_mode(m, per_layer_launches=per_layer)
+        network.set_weights(m, ref.tensors())
+        outs.append(network.evaluate(m, states, actions))
+        if not per_layer:
+            again = network.evaluate(m, states, actions)
+            assert all(np.array_equal(a, b) for a, b in zip(outs[0][0], again[0])) and np.array_equal(outs[0][1], again[1])
+        assert m.status() == 0
+        m.close()
+    assert all(np.array_equal(a, b) for a, b in zip(outs[0][0], outs[1][0]))
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
+    want_logits, want_values, _ = ref.policy_value_uncertainty(games[:32], actions[:32])
+    assert max(float(np.abs(a - b).max()) for a, b in zip(outs[0][0][:32], want_logits)) <= TOL
+    assert float(np.abs(outs[0][1][:32] - want_values).max()) <= TOL
+
+
 def test_watchdog_turns_a_stalled_dependency_into_a_status_bit():
     """The fused launch waits on other CTA pairs' progress counters.  With the test hook that makes pair 0 withhold
     its tiles, the dependent pairs must not spin forever: the watchdog raises TZ_STATUS_NETWORK_STALL (256), the
