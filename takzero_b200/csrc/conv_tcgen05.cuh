@@ -6,7 +6,8 @@
 // weights / bias on the host (nn.cu), inference mode like `forward_t(xs, false)`.
 //
 // Data layout ("chunk-planar"): activations are bf16 [C/8][rows][8]: one plane per 8-channel chunk, rows
-// dense (row = guard + position * N*N + square, no padding anywhere).  A 3x3 tap (dy,dx) of output row r is
+// dense (row = guard + position * N*N + square, no padding anywhere; small 5x5 / 6x6 batches use PACKED rows instead,
+// whole positions per 128-row CTA tile, see Params::pack).  A 3x3 tap (dy,dx) of output row r is
 // input row r + dy*N + dx, so the convolution is the GEMM
 //   out[r, co] = sum_{tap, ci} act[r + off(tap), ci] * W[tap][co][ci]
 // * The A tile of a 64-channel block is 8 contiguous 2304-byte runs of global memory (144 halo rows x 16 B
