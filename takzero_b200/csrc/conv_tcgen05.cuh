@@ -71,6 +71,9 @@
 // after a round trip through L2 with gpu-scope release / acquire flags (measured chain: 6.5 us per layer, which bounded
 // 1024 games of 4x4 at 16.5 us per layer against 10 us of MMAs).  Only the residual stream x still goes through
 // global memory, written and read back by the same thread.
+// 5x5 / 6x6 boards get the same chain on PACKED rows (Params::pack): 5 / 3 whole positions per CTA tile, the tile's last
+// 3 / 20 rows dead (masked for every tap, nothing stored), whenever every CTA has at most one such tile (<= 740 / 444
+// positions on 148 SMs).  The schedule then counts 128-row units; row_position() is the only place that knows.
 //
 // TZ_DEBUG_TIMING is a compile-time tuning experiment (tools/build_variant.sh); the numbers it produced for
 // the earlier row-major one-CTA / pair kernels are in profiles/r1_conv_timing.txt.
