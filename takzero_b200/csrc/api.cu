@@ -879,6 +879,7 @@ extern "C" TZ_API int tz_broadcast_weights(tz_handle* h, const tz_tensor_t* tens
     std::vector<std::vector<long long>> shapes;
     std::vector<const long long*> shape_ptrs;
     std::vector<int> ndims;
+    if (root < 0 || root >= comm_nranks(h)) return fail(TZ_EINVAL, "root %d is not a rank of this communicator (%d ranks)", root, comm_nranks(h));
     if (comm_rank(h) == root) {
         if (!tensors || count <= 0) return fail(TZ_EINVAL, "the root rank passes the tensors");
         names.resize(count);

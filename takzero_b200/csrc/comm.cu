@@ -13,6 +13,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "comm.cuh"
 
 // the slice of nccl.h this file uses (stable NCCL 2.x ABI)
@@ -50,6 +52,8 @@ static int comm_fail(const char* what, int rc) {
 }
 
 static int load_nccl() {
+    static std::mutex once;  // handles of different host threads may get here together
+    std::lock_guard<std::mutex> lock(once);
     if (g_nccl.lib) return TZ_OK;
     const char* env = getenv("TZ_NCCL_LIB");
     const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
