@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -54,6 +55,8 @@ const char* rnd_last_error() { return g_rnd_err; }
     } while (0)
 
 static int load_cublas() {
+    static std::mutex once;
+    std::lock_guard<std::mutex> lock(once);
     if (g_cublas.lib) return TZ_OK;
     const char* env = getenv("TZ_CUBLAS_LIB");
     void* lib = nullptr;
