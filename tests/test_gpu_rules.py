@@ -179,31 +179,53 @@ def test_impossible_host_states_are_refused():
     m.close()
 
 
-@pytest.mark.parametrize("n,depth", [(3, 6), (4, 5), (5, 4), (6, 4)])
+def _perft(m, states, depth, stride, chunk=8192):
+    """Move sequences of length `depth` from `states`, depth-first over chunks (the frontier of the last level never
+    exists as a whole): tz_result filters finished games, tz_legal_moves counts, tz_apply expands."""
+    total = 0
+    for lo in range(0, len(states), chunk):
+        part = states[lo:lo + chunk]
+        part = part[m.result(part) == 0]
+        if len(part) == 0:
+            continue
+        moves, cnt = m.legal_moves(part, stride)
+        assert (cnt >= 0).all() and (cnt <= stride).all()
+        if depth == 1:
+            total += int(cnt.sum())
+            continue
+        parent = np.repeat(np.arange(len(part)), cnt)
+        played = moves[np.arange(stride)[None, :] < cnt[:, None]]  # row-major = parent order
+        children, ok = m.apply(part[parent], played)
+        assert ok.all()
+        total += _perft(m, children, depth - 1, stride, chunk)
+    return total
+
+
+@pytest.mark.parametrize("n,depth", [(3, 7), (4, 5), (5, 5), (6, 4)])
 def test_perft_through_the_c_abi(n, depth):
     """The published perft counts of Tak (tests/test_oracle_golden.py::PERFT, where their provenance is stated) from
-    the CUDA rules alone: breadth-first through tz_result / tz_legal_moves / tz_apply, no oracle in the loop.  3x3 to
-    depth 6 includes finished games that must not be continued; 6x6 to depth 4 is 13.6 M move sequences."""
+    the CUDA rules alone: tz_result / tz_legal_moves / tz_apply, no oracle in the loop.  3x3 to depth 7 (52 M move
+    sequences, most lines finished on the way and must not be continued), 5x5 to depth 5 (188 M, capstones flatten
+    walls), 6x6 to depth 4 (13.6 M)."""
     from test_oracle_golden import PERFT
 
     m = capi.BatchedMCTS(n, 0, 4, arena_slots=4096)
-    frontier = games_to_states([O.new_game(n, 0)])
-    chunk = 16384
+    root = games_to_states([O.new_game(n, 0)])
     for d in range(1, depth + 1):
-        live = frontier[m.result(frontier) == 0]
-        total, children = 0, []
-        for lo in range(0, len(live), chunk):
-            part = live[lo:lo + chunk]
-            moves, cnt = m.legal_moves(part)
-            assert (cnt >= 0).all()
-            total += int(cnt.sum())
-            if d < depth:
-                parent = np.repeat(np.arange(len(part)), cnt)
-                played = moves[np.arange(moves.shape[1])[None, :] < cnt[:, None]]  # row-major = parent order
-                states, ok = m.apply(part[parent], played)
-                assert ok.all()
-                children.append(states)
-        assert total == PERFT[n][d - 1], f"{n}x{n} perft({d})"
-        if d < depth:
-            frontier = np.concatenate(children)
+        if d < depth - 1 and d > 2:
+            continue  # the deepest two levels say it all; the shallow ones are cheap
+        assert _perft(m, root, d, stride=256) == PERFT[n][d - 1], f"{n}x{n} perft({d})"
+    m.close()
+
+
+def test_a_move_that_completes_both_roads_wins_for_the_mover():
+    """The rule of tests/test_oracle_golden.py::test_a_move_that_completes_both_roads_wins_for_the_mover through
+    tz_apply / tz_game_result / tz_result."""
+    m = capi.BatchedMCTS(3, 0, 2, arena_slots=4096)
+    games = [O.from_tps(3, 0, "x2,21/2,2,x/1,1,x 1 10"), O.from_tps(3, 0, "x2,12/1,1,x/2,2,x 2 10")]
+    move = O.parse_move("2c3-11")
+    states, ok = m.apply(games_to_states(games), [move, move])
+    assert ok.all()
+    assert list(m.game_result(states)) == [1, 2]  # R-0, 0-R: the mover's road counts
+    assert list(m.result(states)) == [2, 2]  # a loss for the side to move, both times
     m.close()

@@ -513,13 +513,14 @@ def test_replay_consistency(oracle):
 # game).  [RECALLED: these are the numbers the Tak engines' own move-generator tests carry -- fast-tak's among them; the
 # crate's source is not under /root/reference, so they are written down from memory and say so.]  They pin the restated
 # rules independently of anything derived from this repository: placements and the opening swap (depth 1-2), every
-# spread / drop pattern over one- and two-high stacks with walls blocking (depth 3-4), capstone crushes and the first
-# finished games -- roads on 3x3 from depth 5, where a finished position must not be continued -- (depth 5-6).
+# spread / drop pattern over one- and two-high stacks with walls blocking (depth 3-4), capstones flattening walls (5x5 and
+# 6x6 from depth 5) and finished games that must not be continued (roads on 3x3 from depth 5, on 4x4 from depth 7; most
+# 3x3 lines of depth 7 have ended).  The deepest entries were computed here first and only then compared with memory.
 PERFT = {
-    3: [9, 72, 1200, 17792, 271812, 3712952],
-    4: [16, 240, 7440, 216464, 6468872],
-    5: [25, 600, 43320, 2999784],
-    6: [36, 1260, 132720, 13586048],
+    3: [9, 72, 1200, 17792, 271812, 3712952, 52364896],
+    4: [16, 240, 7440, 216464, 6468872, 181954216],
+    5: [25, 600, 43320, 2999784, 187855252],
+    6: [36, 1260, 132720, 13586048, 1253506520],
 }
 
 
@@ -528,3 +529,18 @@ def test_perft_known_answers(oracle, n):
     g = oracle.new_game(n, 0)
     for depth, want in enumerate(PERFT[n], start=1):
         assert oracle.perft(g, depth) == want, f"{n}x{n} perft({depth})"
+
+
+def test_a_move_that_completes_both_roads_wins_for_the_mover(oracle):
+    """Rules of Tak (published; what fast-tak's `Game::result` implements and env.rs:47-59 consumes): when one move
+    completes a road for both players, the player who made it wins.  3x3: White spreads the stack c3 = [black, white]
+    downwards, dropping the black stone on c2 (Black's a2-b2-c2) and the white one on c1 (White's a1-b1-c1)."""
+    g = oracle.from_tps(3, 0, "x2,21/2,2,x/1,1,x 1 10")
+    assert "2c3-11" in [oracle.move_str(m) for m in oracle.possible_moves(g)]
+    oracle.play(g, oracle.parse_move("2c3-11"))
+    assert oracle.to_tps(g).startswith("x3/2,2,2/1,1,1 2")
+    assert oracle.result(g) == 1  # TK_WHITE_WIN
+    assert oracle.terminal(g) == 2  # a loss for Black, who is to move
+    g = oracle.from_tps(3, 0, "x2,12/1,1,x/2,2,x 2 10")  # colours swapped, Black moves
+    oracle.play(g, oracle.parse_move("2c3-11"))
+    assert oracle.result(g) == 2 and oracle.terminal(g) == 2
