@@ -104,8 +104,8 @@ def test_simulate_batch_with_known_results_in_flight(batch, agent, moves):
     several warps, so this is the case where later descents have to be taken back and started again.  Bit-exact against
     the sequential oracle after every batch."""
     env = O.from_ptn_moves(3, 0, moves)
-    m = capi.BatchedMCTS(3, 0, batch, arena_slots=1 << 20)
-    m.set_positions(games_to_states([env] * batch))
+    m = capi.BatchedMCTS(3, 0, 1, tree_batch=batch, arena_slots=1 << 20)  # one game = the tree; `batch` queue slots
+    m.set_positions(games_to_states([env]))
     if agent != "synthetic":
         m.set_agent(capi.AGENT_HOST, host_agent_from_oracle(agent, 3, 0))
     tree = O.Tree()
@@ -131,9 +131,9 @@ def test_simulate_batch_is_sequential_whatever_the_wavefront(n, half_komi, batch
     path ends early must not let later ones run ahead of the still longer descents before it (the ordering mistake
     this test was written for showed only with some warp counts).  Bit-exact after every batch."""
     env = O.new_opening(n, half_komi, 5, 0)
-    m = capi.BatchedMCTS(n, half_komi, batch, arena_slots=1 << 20)
+    m = capi.BatchedMCTS(n, half_komi, 1, tree_batch=batch, arena_slots=1 << 20)
     m.debug_tree_warps(warps)
-    m.set_positions(games_to_states([env] * batch))
+    m.set_positions(games_to_states([env]))
     tree = O.Tree()
     for it in range(batches):
         m.tree_simulate_batch(0.25, batch)
@@ -149,8 +149,8 @@ def test_simulate_batch_soak_with_tree_reuse():
     every 60 batches (subtree kept): 38k descents through one growing tree, compared every 20 batches."""
     n, half_komi, batch = 6, 4, 128
     env = O.new_opening(n, half_komi, 2, 1)
-    m = capi.BatchedMCTS(n, half_komi, batch, arena_slots=1 << 22)
-    m.set_positions(games_to_states([env] * batch))
+    m = capi.BatchedMCTS(n, half_komi, 1, tree_batch=batch, arena_slots=1 << 22)
+    m.set_positions(games_to_states([env]))
     tree = O.Tree()
     for it in range(300):
         m.tree_simulate_batch(0.0, batch)
